@@ -1,0 +1,69 @@
+"""Builds libsfmb200.so (the C-ABI product, include/sfmb200.h) in-tree with nvcc for sm_100a.
+
+    python sfm-toy-library_b200/build.py            # incremental
+    python sfm-toy-library_b200/build.py --force
+
+nvcc cross-compiles without a GPU; the .so lands in sfm-toy-library_b200/lib/ (git-ignored, but it travels to the GPU
+box with the gpurun snapshot).
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIBDIR = os.path.join(HERE, "lib")
+SO = os.path.join(LIBDIR, "libsfmb200.so")
+SOURCES = ["ctx.cu", "comm.cu", "match.cu", "triangulate.cu", "ba.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O3",
+         "-ccbin", HOST_CXX, "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True); os.makedirs(LIBDIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "sfmb200.h"))
+    headers.append(os.path.abspath(__file__))
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s); obj = os.path.join(OBJ, s.replace(".cu", ".o"))
+        if force or _stale(obj, [src] + headers):
+            jobs.append((src, obj))
+
+    def cc(job):
+        src, obj = job
+        r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+        return src, r
+    with ThreadPoolExecutor(max_workers=len(jobs) or 1) as ex:
+        for src, r in ex.map(cc, jobs):
+            log = os.path.join(OBJ, os.path.basename(src) + ".log")
+            with open(log, "w") as f:
+                f.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"nvcc failed on {src}")
+            if verbose:
+                sys.stderr.write(r.stderr)
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    if force or jobs or _stale(SO, objs):
+        r = subprocess.run([NVCC, "-shared", "-o", SO] + objs + ["-ccbin", HOST_CXX, "-cudart", "static", "-ldl", "-lpthread"],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

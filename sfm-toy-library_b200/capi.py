@@ -1,0 +1,295 @@
+"""ctypes binding of the C ABI (include/sfmb200.h -> lib/libsfmb200.so).
+
+Thin by design: numpy arrays in, numpy arrays out, every call goes straight to the shared library.  There is NO
+fallback: if the library is missing or there is no GPU, calls raise SfmB200Error.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsfmb200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sfmb200.h")
+UNIQUE_ID_BYTES = 128
+RATIO_REFERENCE = float(np.float64(np.float32(0.8)))     # NN_MATCH_RATIO = (double)0.8f, SfM2DFeatureUtilities.cpp:35
+MIN_REPROJECTION_ERROR = 10.0                            # SfMStereoUtilities.cpp:42
+CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
+
+_lib = None
+
+
+class SfmB200Error(RuntimeError):
+    pass
+
+
+class BAOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("max_solver_time_in_seconds", C.c_double),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+                ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int),
+                ("max_num_consecutive_invalid_steps", C.c_int), ("verbose", C.c_int), ("profile", C.c_int)]
+
+
+class BASummary(C.Structure):
+    _fields_ = [("termination_type", C.c_int), ("num_iterations", C.c_int), ("num_successful_steps", C.c_int),
+                ("num_unsuccessful_steps", C.c_int), ("num_jacobian_passes", C.c_int), ("num_linear_solves", C.c_int),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("total_time_s", C.c_double),
+                ("schur_ms_total", C.c_double), ("schur_launches", C.c_int), ("kernel_launches", C.c_int64),
+                ("message", C.c_char * 160)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["message"] = self.message.decode()
+        return d
+
+
+def lib():
+    """Load libsfmb200.so (built by build.py / __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SfmB200Error(f"{LIB_PATH} not found: run `python sfm-toy-library_b200/build.py` (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.sfmb200_last_error.restype = C.c_char_p
+        L.sfmb200_last_error.argtypes = [C.c_void_p]
+        L.sfmb200_stream.restype = C.c_void_p
+        L.sfmb200_stream.argtypes = [C.c_void_p]
+        L.sfmb200_kernel_launches.restype = C.c_int64
+        L.sfmb200_kernel_launches.argtypes = [C.c_void_p]
+        for name in ("sfmb200_destroy", "sfmb200_descset_destroy", "sfmb200_ba_problem_destroy"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _vp(x):
+    return C.c_void_p(x)
+
+
+class Context:
+    """sfmb200_ctx: one per GPU."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().sfmb200_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise SfmB200Error(f"sfmb200_create failed ({rc}): {lib().sfmb200_last_error(None).decode()}")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().sfmb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SfmB200Error(f"libsfmb200 error {rc}: {lib().sfmb200_last_error(self._h).decode()}")
+
+    @property
+    def stream(self):
+        return lib().sfmb200_stream(self._h)
+
+    @property
+    def kernel_launches(self):
+        return int(lib().sfmb200_kernel_launches(self._h))
+
+    def synchronize(self):
+        self._check(lib().sfmb200_synchronize(self._h))
+
+    # ------------------------------------------------------------------ a-1 matching
+    def match_knn2_ratio(self, q, t, ratio=RATIO_REFERENCE):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        nq, nt = q.shape[0], t.shape[0]
+        nb = q.shape[1] if q.ndim == 2 and nq else (t.shape[1] if t.ndim == 2 else 32)
+        oq = np.empty(max(nq, 1), np.int32); ot = np.empty(max(nq, 1), np.int32); od = np.empty(max(nq, 1), np.float32)
+        n = C.c_int(0)
+        self._check(lib().sfmb200_match_knn2_ratio(self._h, _p(q, C.c_uint8), nq, _p(t, C.c_uint8), nt, nb, C.c_double(ratio),
+                                                   _p(oq, C.c_int32), _p(ot, C.c_int32), _p(od, C.c_float), C.byref(n)))
+        return oq[:n.value].copy(), ot[:n.value].copy(), od[:n.value].copy()
+
+    def match_knn2_ratio_l2(self, q, t, ratio=RATIO_REFERENCE):
+        q = np.ascontiguousarray(q, np.float32); t = np.ascontiguousarray(t, np.float32)
+        nq, nt, dim = q.shape[0], t.shape[0], q.shape[1]
+        oq = np.empty(max(nq, 1), np.int32); ot = np.empty(max(nq, 1), np.int32); od = np.empty(max(nq, 1), np.float32)
+        n = C.c_int(0)
+        self._check(lib().sfmb200_match_knn2_ratio_l2(self._h, _p(q, C.c_float), nq, _p(t, C.c_float), nt, dim, C.c_double(ratio),
+                                                      _p(oq, C.c_int32), _p(ot, C.c_int32), _p(od, C.c_float), C.byref(n)))
+        return oq[:n.value].copy(), ot[:n.value].copy(), od[:n.value].copy()
+
+    def descriptor_set(self, desc_list):
+        return DescriptorSet(self, desc_list)
+
+    # ------------------------------------------------------------------ a-2 triangulation
+    def triangulate(self, K, Pl, Pr, pts_left, pts_right, match_q=None, match_t=None, max_reproj=MIN_REPROJECTION_ERROR):
+        K = np.ascontiguousarray(K, np.float32).reshape(9); Pl = np.ascontiguousarray(Pl, np.float32).reshape(12)
+        Pr = np.ascontiguousarray(Pr, np.float32).reshape(12)
+        L = np.ascontiguousarray(pts_left, np.float32).reshape(-1, 2); R = np.ascontiguousarray(pts_right, np.float32).reshape(-1, 2)
+        if match_q is not None:
+            match_q = np.ascontiguousarray(match_q, np.int32); match_t = np.ascontiguousarray(match_t, np.int32); m = match_q.shape[0]
+        else:
+            m = min(L.shape[0], R.shape[0])
+        X = np.empty((max(m, 1), 3), np.float32); keep = np.empty(max(m, 1), np.uint8); nk = C.c_int(0)
+        self._check(lib().sfmb200_triangulate(self._h, _p(K, C.c_float), _p(Pl, C.c_float), _p(Pr, C.c_float), _p(L, C.c_float), L.shape[0],
+                                              _p(R, C.c_float), R.shape[0], _p(match_q, C.c_int32), _p(match_t, C.c_int32), m,
+                                              C.c_float(max_reproj), _p(X, C.c_float), _p(keep, C.c_uint8), C.byref(nk)))
+        return X[:m], keep[:m], nk.value
+
+    def triangulate_device(self, K, Pl, Pr, d_left, d_right, d_mq, d_mt, m, d_X, d_keep, d_nkeep, max_reproj=MIN_REPROJECTION_ERROR):
+        """All d_* are raw device pointers (ints); nothing is synchronised."""
+        K = np.ascontiguousarray(K, np.float32).reshape(9); Pl = np.ascontiguousarray(Pl, np.float32).reshape(12)
+        Pr = np.ascontiguousarray(Pr, np.float32).reshape(12)
+        self._check(lib().sfmb200_triangulate_device(self._h, _p(K, C.c_float), _p(Pl, C.c_float), _p(Pr, C.c_float), _vp(d_left), _vp(d_right),
+                                                     _vp(d_mq), _vp(d_mt), int(m), C.c_float(max_reproj), _vp(d_X), _vp(d_keep), _vp(d_nkeep)))
+
+    # ------------------------------------------------------------------ a-3/a-4 bundle adjustment
+    def ba_problem(self, cams, pts, focal, obs_xy, obs_cam, pt_off):
+        return BAProblem(self, cams, pts, focal, obs_xy, obs_cam, pt_off)
+
+    def ba_solve(self, cams, pts, focal, obs_xy, obs_cam, pt_off, options=None):
+        """One-shot sfmb200_ba_solve with host buffers.  Returns (cams, pts, focal, summary dict)."""
+        cams = np.array(cams, np.float64, order="C").reshape(-1, 6); pts = np.array(pts, np.float64, order="C").reshape(-1, 3)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2); obs_cam = np.ascontiguousarray(obs_cam, np.int32)
+        pt_off = np.ascontiguousarray(pt_off, np.int32)
+        f = C.c_double(float(focal)); s = BASummary(); o = options or ba_default_options()
+        self._check(lib().sfmb200_ba_solve(self._h, C.byref(o), cams.shape[0], pts.shape[0], obs_cam.shape[0], _p(cams, C.c_double),
+                                           _p(pts, C.c_double), C.byref(f), _p(obs_xy, C.c_float), _p(obs_cam, C.c_int32),
+                                           _p(pt_off, C.c_int32), C.byref(s)))
+        return cams, pts, f.value, s.as_dict()
+
+    # ------------------------------------------------------------------ multi-GPU
+    def comm_init(self, unique_id, rank, nranks):
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        self._check(lib().sfmb200_comm_init(self._h, buf, int(rank), int(nranks)))
+
+    @property
+    def comm_size(self):
+        return lib().sfmb200_comm_size(self._h)
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * UNIQUE_ID_BYTES)()
+    rc = lib().sfmb200_comm_unique_id(buf)
+    if rc != 0:
+        raise SfmB200Error(f"sfmb200_comm_unique_id failed ({rc}): {lib().sfmb200_last_error(None).decode()}")
+    return bytes(buf)
+
+
+def ba_default_options(**kw):
+    o = BAOptions()
+    lib().sfmb200_ba_default_options(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def rotmat_to_angle_axis_f32(R):
+    R = np.ascontiguousarray(R, np.float32).reshape(9); aa = np.empty(3, np.float32)
+    lib().sfmb200_rotmat_to_angle_axis_f32(_p(R, C.c_float), _p(aa, C.c_float))
+    return aa
+
+
+def angle_axis_to_rotmat(aa):
+    aa = np.ascontiguousarray(aa, np.float64).reshape(3); R = np.empty(9, np.float64)
+    lib().sfmb200_angle_axis_to_rotmat(_p(aa, C.c_double), _p(R, C.c_double))
+    return R.reshape(3, 3)
+
+
+class DescriptorSet:
+    """sfmb200_descset: the descriptors of all images resident in HBM; all-pairs matching in one call."""
+
+    def __init__(self, ctx, desc_list):
+        self.ctx = ctx
+        desc_list = [np.ascontiguousarray(d, np.uint8) for d in desc_list]
+        self.sizes = [d.shape[0] for d in desc_list]
+        nb = desc_list[0].shape[1] if desc_list else 32
+        off = np.zeros(len(desc_list) + 1, np.int32); off[1:] = np.cumsum(self.sizes)
+        allrows = np.ascontiguousarray(np.concatenate(desc_list, 0)) if desc_list else np.zeros((0, nb), np.uint8)
+        self._h = C.c_void_p()
+        ctx._check(lib().sfmb200_descset_create(ctx._h, _p(allrows, C.c_uint8), _p(off, C.c_int32), len(desc_list), nb, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sfmb200_descset_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def match_pairs(self, pairs, ratio=RATIO_REFERENCE):
+        """pairs: [(left, right), ...] -> list of (queryIdx, trainIdx, distance) per pair."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        npairs = pairs.shape[0]
+        total = int(sum(self.sizes[l] for l, _ in pairs))
+        oq = np.empty(max(total, 1), np.int32); ot = np.empty(max(total, 1), np.int32); od = np.empty(max(total, 1), np.float32)
+        off = np.zeros(npairs + 1, np.int64); cnt = np.zeros(max(npairs, 1), np.int32)
+        self.ctx._check(lib().sfmb200_match_pairs(self.ctx._h, self._h, _p(pairs, C.c_int32), npairs, C.c_double(ratio),
+                                                  _p(oq, C.c_int32), _p(ot, C.c_int32), _p(od, C.c_float), _p(off, C.c_int64), _p(cnt, C.c_int32)))
+        return [(oq[off[p]:off[p] + cnt[p]].copy(), ot[off[p]:off[p] + cnt[p]].copy(), od[off[p]:off[p] + cnt[p]].copy()) for p in range(npairs)]
+
+    def match_pairs_device(self, pairs, d_q, d_t, d_d, d_pair_start, d_total, ratio=RATIO_REFERENCE):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        self.ctx._check(lib().sfmb200_match_pairs_device(self.ctx._h, self._h, _p(pairs, C.c_int32), pairs.shape[0], C.c_double(ratio),
+                                                         _vp(d_q), _vp(d_t), _vp(d_d), _vp(d_pair_start), _vp(d_total)))
+
+
+class BAProblem:
+    """sfmb200_ba_problem: a flattened adjustBundle problem resident in HBM."""
+
+    def __init__(self, ctx, cams, pts, focal, obs_xy, obs_cam, pt_off):
+        self.ctx = ctx
+        cams = np.ascontiguousarray(cams, np.float64).reshape(-1, 6); pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2); obs_cam = np.ascontiguousarray(obs_cam, np.int32)
+        pt_off = np.ascontiguousarray(pt_off, np.int32)
+        self.nc, self.np, self.nobs = cams.shape[0], pts.shape[0], obs_cam.shape[0]
+        self._h = C.c_void_p()
+        ctx._check(lib().sfmb200_ba_problem_create(ctx._h, self.nc, self.np, self.nobs, _p(cams, C.c_double), _p(pts, C.c_double),
+                                                   C.c_double(float(focal)), _p(obs_xy, C.c_float), _p(obs_cam, C.c_int32),
+                                                   _p(pt_off, C.c_int32), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sfmb200_ba_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self.ctx._check(lib().sfmb200_ba_problem_reset(self._h))
+
+    def run(self, options=None):
+        s = BASummary(); o = options or ba_default_options()
+        self.ctx._check(lib().sfmb200_ba_problem_run(self._h, C.byref(o), C.byref(s)))
+        return s.as_dict()
+
+    def download(self):
+        cams = np.empty((self.nc, 6)); pts = np.empty((self.np, 3)); f = C.c_double()
+        self.ctx._check(lib().sfmb200_ba_problem_download(self._h, _p(cams, C.c_double), _p(pts, C.c_double), C.byref(f)))
+        return cams, pts, f.value
+
+    def reduced_system(self, radius=1e4, options=None):
+        n = 6 * self.nc + 1
+        S = np.empty((n, n)); rhs = np.empty(n); g = np.empty(n); cost = C.c_double()
+        o = options or ba_default_options()
+        self.ctx._check(lib().sfmb200_ba_problem_reduced_system(self._h, C.byref(o), C.c_double(radius), _p(S, C.c_double),
+                                                                _p(rhs, C.c_double), _p(g, C.c_double), C.byref(cost)))
+        return dict(S=S, rhs=rhs, grad_cf=g, cost=cost.value)

@@ -1,0 +1,1045 @@
+// ba.cu -- K3/K4: bundle adjustment as Levenberg-Marquardt with per-point Schur elimination, all on the device.
+//
+// Replaces SfMBundleAdjustmentUtils::adjustBundle (reference SfMToyLib/SfMBundleAdjustmentUtils.cpp:99-222), i.e.
+// ceres::Solve with LM + DENSE_SCHUR over AutoDiffCostFunction<SimpleReprojectionError,2,6,3,1> blocks (:58-97,
+// :158-164, :171-179).  Ceres' algorithm is restated: Jacobi column scaling fixed at x0,
+// LM diagonal clamp(diag(J^T J), 1e-6, 1e32)/radius, step-quality radius update, the four termination tests.
+//
+// Design (B200-first, not a Ceres translation):
+//   * The Jacobian is never materialised.  Every pass re-evaluates the closed-form 2x(6+3+1) blocks from 8-byte
+//     observations (ba_math.cuh) -- HBM traffic per LM iteration is the observation list + the point/camera state.
+//   * ba_point_kernel   (K3a, point-major, one sub-warp group per 3D point): U_p = sum Jp^T Jp + D_p^2, its Cholesky
+//     inverse M_p, g_p, and the OFF-diagonal blocks  S[ci,cj] -= Z_i Z_j^T  (Z = Jc^T Jp M^T) of the reduced camera
+//     system, accumulated with fp64 reductions (red.global.add.f64) into a block-major upper-triangular S.
+//   * ba_camera_kernel  (K3b, camera-major): everything that would be same-address contention -- the diagonal blocks,
+//     the camera-focal column, rhs and gradient -- is accumulated in registers over one camera's observation list and
+//     reduced once per CTA (the shared focal block makes every observation touch S[:,focal]).
+//   * reduced system summed over ranks with ONE NCCL all-reduce (S, rhs, gradient, diag, cost in one buffer).
+//   * ba_assemble + blocked Cholesky (right-looking, 32x32 tiles in shared memory, rhs carried as an extra row so the
+//     forward substitution is free) + back substitution: K4.
+//   * ba_backsub_eval_kernel (point-major): delta_p, candidate point, model cost change and candidate cost fused.
+//   LM control runs on the host from ~20 doubles read back once per iteration.
+#include "common.cuh"
+#include "ba_math.cuh"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+
+namespace {
+
+constexpr int PT_THREADS = 128;
+constexpr int CAM_THREADS = 128;
+constexpr int NB = 32;                 // Cholesky tile
+
+struct BAView {
+    int nc, np, nobs, maxk;
+    // point-major observations
+    const float2* obs_xy; const int32_t* obs_cam; const int32_t* pt_off;
+    // camera-major copy
+    const int32_t* cm_off; const float2* cm_xy; const int32_t* cm_pt;
+    // state
+    const double* cams; const double* pts; const double* focal;      // current x (focal = cams + 6*nc)
+    const CamDerived* camd;                                           // derived per camera at x
+    const double* scale_cf; const double* scale_pt;                   // Jacobi scaling
+    double* ptblk;                                                    // [np*12] M(6) zg(3) zf(3)
+    // reduced system (block layout) + sums
+    double* Sblk; double* Scf; double* Sff; double* rhs; double* gcf; double* dcf; double* sums;
+    unsigned long long* gmax_pt_bits;                                 // max |g_p| (bit pattern of a non-negative double)
+    int* fail;                                                        // count of non-SPD point blocks
+    double min_diag, max_diag;
+};
+
+__device__ __forceinline__ void red_add(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+__device__ __forceinline__ size_t blk_index(int i, int j, int nb) {   // i <= j
+    return (size_t)i * nb - (size_t)i * (i - 1) / 2 + (j - i);
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned mask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// scaled Jacobian blocks of one observation
+struct ObsJ { double r[2], Jc[12], Jp[6], Jf[2]; };
+__device__ __forceinline__ void eval_scaled(const CamDerived& d, const double* X, double f, float2 xy,
+                                            const double* sc /*6*/, const double* sp /*3*/, double sf, ObsJ& o) {
+    obs_eval(d, X, f, (double)xy.x, (double)xy.y, o.r, o.Jc, o.Jp, o.Jf);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { o.Jc[a] *= sc[a]; o.Jc[6 + a] *= sc[a]; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { o.Jp[a] *= sp[a]; o.Jp[3 + a] *= sp[a]; }
+    o.Jf[0] *= sf; o.Jf[1] *= sf;
+}
+
+__global__ void cam_derive_kernel(const double* __restrict__ cams, int nc, CamDerived* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nc) { CamDerived d; cam_derive(cams + 6 * c, d); out[c] = d; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Jacobi scaling (computed once at x0): squared column norms of the UNSCALED Jacobian.
+// points: scale_pt written directly; cameras/focal: accumulated into colnorm_cf (summed over ranks afterwards).
+// ---------------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(PT_THREADS) ba_point_norm_kernel(BAView v, double* __restrict__ scale_pt_out) {
+    const int lane = threadIdx.x & 31, gl = lane % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    const int groups_per_block = PT_THREADS / G;
+    const double f = *v.focal;
+    for (int p = blockIdx.x * groups_per_block + threadIdx.x / G; p < v.np; p += gridDim.x * groups_per_block) {
+        const int o0 = v.pt_off[p], k = v.pt_off[p + 1] - o0;
+        const double X[3] = {v.pts[3 * p], v.pts[3 * p + 1], v.pts[3 * p + 2]};
+        double n0 = 0, n1 = 0, n2 = 0;
+        for (int j = gl; j < k; j += G) {
+            const int o = o0 + j;
+            double r[2], Jc[12], Jp[6], Jf[2];
+            const float2 xy = v.obs_xy[o];
+            obs_eval(v.camd[v.obs_cam[o]], X, f, (double)xy.x, (double)xy.y, r, Jc, Jp, Jf);
+            n0 += Jp[0] * Jp[0] + Jp[3] * Jp[3]; n1 += Jp[1] * Jp[1] + Jp[4] * Jp[4]; n2 += Jp[2] * Jp[2] + Jp[5] * Jp[5];
+        }
+        n0 = group_sum<G>(n0, gmask); n1 = group_sum<G>(n1, gmask); n2 = group_sum<G>(n2, gmask);
+        if (gl == 0) {
+            scale_pt_out[3 * p] = 1.0 / (1.0 + sqrt(n0)); scale_pt_out[3 * p + 1] = 1.0 / (1.0 + sqrt(n1));
+            scale_pt_out[3 * p + 2] = 1.0 / (1.0 + sqrt(n2));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CAM_THREADS) ba_camera_norm_kernel(BAView v, double* __restrict__ colnorm_cf) {
+    const int c = blockIdx.y;
+    const int begin = v.cm_off[c], end = v.cm_off[c + 1];
+    const CamDerived d = v.camd[c];
+    const double f = *v.focal;
+    double n[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = begin + blockIdx.x * CAM_THREADS + threadIdx.x; i < end; i += gridDim.x * CAM_THREADS) {
+        const int p = v.cm_pt[i];
+        const double X[3] = {v.pts[3 * p], v.pts[3 * p + 1], v.pts[3 * p + 2]};
+        double r[2], Jc[12], Jp[6], Jf[2];
+        const float2 xy = v.cm_xy[i];
+        obs_eval(d, X, f, (double)xy.x, (double)xy.y, r, Jc, Jp, Jf);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) n[a] += Jc[a] * Jc[a] + Jc[6 + a] * Jc[6 + a];
+        n[6] += Jf[0] * Jf[0] + Jf[1] * Jf[1];
+    }
+    __shared__ double red[CAM_THREADS / 32][7];
+#pragma unroll
+    for (int a = 0; a < 7; ++a) { const double s = warp_sum(n[a]); if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][a] = s; }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double s = 0;
+        for (int w = 0; w < CAM_THREADS / 32; ++w) s += red[w][threadIdx.x];
+        if (s != 0.0) red_add(threadIdx.x < 6 ? colnorm_cf + 6 * c + threadIdx.x : colnorm_cf + 6 * v.nc, s);
+    }
+}
+
+__global__ void scale_from_norm_kernel(const double* __restrict__ colnorm, int n, double* __restrict__ scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) scale[i] = 1.0 / (1.0 + sqrt(colnorm[i]));
+}
+__global__ void fill_kernel(double* __restrict__ p, size_t n, double v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3a: point-major elimination.  One group of G lanes per 3D point (G = 4/8/16/32 >= observations per point when
+// possible); lanes evaluate the point's observations in parallel, group-reduce U_p / g_p with warp shuffles, and the
+// whole warp then sweeps the pair blocks of each of its points so that 32 consecutive doubles go out per RED.
+// Shared memory per group: Z [maxk][18] + camera ids [maxk]; pair table shared by the CTA.
+// ---------------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double inv_radius) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int GB = PT_THREADS / G, GW = 32 / G;
+    const int maxk = v.maxk;
+    double* Zall = reinterpret_cast<double*>(smem_raw);                           // [GB][maxk][18]
+    int* camall = reinterpret_cast<int*>(Zall + (size_t)GB * maxk * 18);          // [GB][maxk]
+    unsigned short* pair_tab = reinterpret_cast<unsigned short*>(camall + GB * maxk);   // [maxk*(maxk-1)/2]  (i | j<<8)
+    for (int j = 1 + threadIdx.x / 32; j < maxk; j += PT_THREADS / 32)
+        for (int i = threadIdx.x & 31; i < j; i += 32) pair_tab[j * (j - 1) / 2 + i] = (unsigned short)(i | (j << 8));
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, gi = lane / G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
+    const int group_in_block = warp * GW + gi;
+    double* Zg = Zall + (size_t)group_in_block * maxk * 18;
+    int* camg = camall + group_in_block * maxk;
+    const double f = *v.focal, sf = v.scale_cf[6 * v.nc];
+    const int nb = v.nc;
+
+    double acc_cost = 0, acc_xn = 0, acc_sff = 0, acc_rf = 0, acc_gmax = 0;
+    const int np_round = (v.np + GB - 1) / GB * GB;
+    for (int base = blockIdx.x * GB; base < np_round; base += gridDim.x * GB) {
+        const int p = base + group_in_block;
+        const bool active = p < v.np;
+        int o0 = 0, k = 0;
+        double X[3] = {0, 0, 0}, sp[3] = {1, 1, 1};
+        if (active) {
+            o0 = v.pt_off[p]; k = v.pt_off[p + 1] - o0;
+            X[0] = v.pts[3 * p]; X[1] = v.pts[3 * p + 1]; X[2] = v.pts[3 * p + 2];
+            sp[0] = v.scale_pt[3 * p]; sp[1] = v.scale_pt[3 * p + 1]; sp[2] = v.scale_pt[3 * p + 2];
+        }
+        double U[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, wf[3] = {0, 0, 0}, cost = 0;
+        for (int j = gl; j < k; j += G) {
+            const int o = o0 + j, c = v.obs_cam[o];
+            ObsJ J;
+            eval_scaled(v.camd[c], X, f, v.obs_xy[o], v.scale_cf + 6 * c, sp, sf, J);
+            const double* e = J.Jp;
+            U[0] += e[0] * e[0] + e[3] * e[3]; U[1] += e[0] * e[1] + e[3] * e[4]; U[2] += e[0] * e[2] + e[3] * e[5];
+            U[3] += e[1] * e[1] + e[4] * e[4]; U[4] += e[1] * e[2] + e[4] * e[5]; U[5] += e[2] * e[2] + e[5] * e[5];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { g[a] += e[a] * J.r[0] + e[3 + a] * J.r[1]; wf[a] += e[a] * J.Jf[0] + e[3 + a] * J.Jf[1]; }
+            cost += J.r[0] * J.r[0] + J.r[1] * J.r[1];
+            double* W = Zg + j * 18;              // W = Jc^T Jp (6x3), turned into Z below
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) W[a * 3 + b] = J.Jc[a] * e[b] + J.Jc[6 + a] * e[3 + b];
+            camg[j] = c;
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) U[a] = group_sum<G>(U[a], gmask);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { g[a] = group_sum<G>(g[a], gmask); wf[a] = group_sum<G>(wf[a], gmask); }
+        cost = group_sum<G>(cost, gmask);
+
+        // LM diagonal of the point block: clamp(diag(J^T J)) / radius
+        U[0] += clampd(U[0], v.min_diag, v.max_diag) * inv_radius;
+        U[3] += clampd(U[3], v.min_diag, v.max_diag) * inv_radius;
+        U[5] += clampd(U[5], v.min_diag, v.max_diag) * inv_radius;
+        double M[6] = {0, 0, 0, 0, 0, 0};
+        const bool ok = chol3_inverse(U, M);
+        if (!ok) { M[0] = M[1] = M[2] = M[3] = M[4] = M[5] = 0.0; }
+        // zg = M g, zf = M wf
+        const double zg[3] = {M[0] * g[0], M[1] * g[0] + M[2] * g[1], M[3] * g[0] + M[4] * g[1] + M[5] * g[2]};
+        const double zf[3] = {M[0] * wf[0], M[1] * wf[0] + M[2] * wf[1], M[3] * wf[0] + M[4] * wf[1] + M[5] * wf[2]};
+        if (active) {
+            const double blk[12] = {M[0], M[1], M[2], M[3], M[4], M[5], zg[0], zg[1], zg[2], zf[0], zf[1], zf[2]};
+#pragma unroll
+            for (int q = 0; q < 12; ++q) if ((q % G) == gl) v.ptblk[(size_t)p * 12 + q] = blk[q];
+            if (gl == 0) {
+                if (!ok && k > 0) atomicAdd(v.fail, 1);
+                acc_cost += cost;
+                acc_xn += X[0] * X[0] + X[1] * X[1] + X[2] * X[2];
+                acc_sff += zf[0] * zf[0] + zf[1] * zf[1] + zf[2] * zf[2];
+                acc_rf += zf[0] * zg[0] + zf[1] * zg[1] + zf[2] * zg[2];
+                acc_gmax = fmax(acc_gmax, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
+            }
+        }
+        // Z = W M^T  (own rows; same thread wrote W)
+        for (int j = gl; j < k; j += G) {
+            double* W = Zg + j * 18;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double w0 = W[a * 3], w1 = W[a * 3 + 1], w2 = W[a * 3 + 2];
+                W[a * 3] = w0 * M[0]; W[a * 3 + 1] = w0 * M[1] + w1 * M[2]; W[a * 3 + 2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
+            }
+        }
+        __syncwarp();
+        // pair sweep: the whole warp handles the points of its GW groups one after the other
+#pragma unroll 1
+        for (int gs = 0; gs < GW; ++gs) {
+            const int kk = __shfl_sync(0xffffffffu, k, gs * G);
+            const double* Zs = Zall + (size_t)(warp * GW + gs) * maxk * 18;
+            const int* cs = camall + (warp * GW + gs) * maxk;
+            const int total = kk * (kk - 1) / 2 * 36;
+            for (int e = lane; e < total; e += 32) {
+                const int pr = e / 36, ab = e - pr * 36, a = ab / 6, b = ab - a * 6;
+                const unsigned ij = pair_tab[pr];
+                const int i = ij & 0xff, j = ij >> 8;
+                const double* zi = Zs + i * 18 + a * 3; const double* zj = Zs + j * 18 + b * 3;
+                const double val = zi[0] * zj[0] + zi[1] * zj[1] + zi[2] * zj[2];
+                red_add(v.Sblk + blk_index(cs[i], cs[j], nb) * 36 + ab, -val);
+            }
+        }
+        __syncwarp();
+    }
+    // CTA reduction of the scalar accumulators
+    __shared__ double sred[PT_THREADS / 32][5];
+    const double c0 = warp_sum(acc_cost), c1 = warp_sum(acc_xn), c2 = warp_sum(acc_sff), c3 = warp_sum(acc_rf), c4 = warp_max(acc_gmax);
+    if (lane == 0) { sred[warp][0] = c0; sred[warp][1] = c1; sred[warp][2] = c2; sred[warp][3] = c3; sred[warp][4] = c4; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) { t0 += sred[w][0]; t1 += sred[w][1]; t2 += sred[w][2]; t3 += sred[w][3]; t4 = fmax(t4, sred[w][4]); }
+        red_add(v.sums + 0, t0); red_add(v.sums + 1, t1);
+        red_add(v.Sff, -t2); red_add(v.rhs + 6 * v.nc, -t3);
+        atomicMax(v.gmax_pt_bits, (unsigned long long)__double_as_longlong(t4));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3b: camera-major pass.  grid (chunks, nc).  Per camera: diagonal block, camera-focal column, rhs, gradient and
+// J^T J diagonal, all in registers; one reduction per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v) {
+    const int c = blockIdx.y;
+    const int begin = v.cm_off[c], end = v.cm_off[c + 1];
+    if (begin + (int)blockIdx.x * CAM_THREADS >= end) return;
+    const CamDerived d = v.camd[c];
+    const double f = *v.focal, sf = v.scale_cf[6 * v.nc];
+    double sc[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) sc[a] = v.scale_cf[6 * c + a];
+    // accumulators: A[21] diag block (upper), C[6] cam-focal, R[6] rhs, Gd[6] gradient, D[6] diag, ff, gf
+    double A[21], Cf[6], R[6], Gd[6], D[6], ff = 0, gf = 0;
+#pragma unroll
+    for (int a = 0; a < 21; ++a) A[a] = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { Cf[a] = 0; R[a] = 0; Gd[a] = 0; D[a] = 0; }
+    for (int i = begin + blockIdx.x * CAM_THREADS + threadIdx.x; i < end; i += gridDim.x * CAM_THREADS) {
+        const int p = v.cm_pt[i];
+        const double X[3] = {v.pts[3 * p], v.pts[3 * p + 1], v.pts[3 * p + 2]};
+        const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
+        const double* pb = v.ptblk + (size_t)p * 12;
+        const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
+        const double zg[3] = {pb[6], pb[7], pb[8]}, zf[3] = {pb[9], pb[10], pb[11]};
+        ObsJ J;
+        eval_scaled(d, X, f, v.cm_xy[i], sc, sp, sf, J);
+        ff += J.Jf[0] * J.Jf[0] + J.Jf[1] * J.Jf[1];
+        gf += J.Jf[0] * J.r[0] + J.Jf[1] * J.r[1];
+        double Z[6][3];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double w0 = J.Jc[a] * J.Jp[0] + J.Jc[6 + a] * J.Jp[3], w1 = J.Jc[a] * J.Jp[1] + J.Jc[6 + a] * J.Jp[4],
+                         w2 = J.Jc[a] * J.Jp[2] + J.Jc[6 + a] * J.Jp[5];
+            Z[a][0] = w0 * M[0]; Z[a][1] = w0 * M[1] + w1 * M[2]; Z[a][2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
+            const double jr = J.Jc[a] * J.r[0] + J.Jc[6 + a] * J.r[1];
+            Gd[a] += jr;
+            R[a] += jr - (Z[a][0] * zg[0] + Z[a][1] * zg[1] + Z[a][2] * zg[2]);
+            Cf[a] += J.Jc[a] * J.Jf[0] + J.Jc[6 + a] * J.Jf[1] - (Z[a][0] * zf[0] + Z[a][1] * zf[1] + Z[a][2] * zf[2]);
+            D[a] += J.Jc[a] * J.Jc[a] + J.Jc[6 + a] * J.Jc[6 + a];
+        }
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b, ++q)
+                A[q] += J.Jc[a] * J.Jc[b] + J.Jc[6 + a] * J.Jc[6 + b] - (Z[a][0] * Z[b][0] + Z[a][1] * Z[b][1] + Z[a][2] * Z[b][2]);
+    }
+    // CTA reduction: 47 values
+    __shared__ double red[CAM_THREADS / 32][48];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 21; ++a) { const double s = warp_sum(A[a]); if (lane == 0) red[warp][a] = s; }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const double s0 = warp_sum(Cf[a]), s1 = warp_sum(R[a]), s2 = warp_sum(Gd[a]), s3 = warp_sum(D[a]);
+        if (lane == 0) { red[warp][21 + a] = s0; red[warp][27 + a] = s1; red[warp][33 + a] = s2; red[warp][39 + a] = s3; }
+    }
+    { const double s0 = warp_sum(ff), s1 = warp_sum(gf); if (lane == 0) { red[warp][45] = s0; red[warp][46] = s1; } }
+    __syncthreads();
+    if (threadIdx.x < 47) {
+        double s = 0;
+        for (int w = 0; w < CAM_THREADS / 32; ++w) s += red[w][threadIdx.x];
+        const int t = threadIdx.x, fidx = 6 * v.nc;
+        if (t < 21) {
+            // upper-triangular index t -> (a,b); write both halves of the (symmetric) diagonal block
+            int a = 0, rem = t; while (rem >= 6 - a) { rem -= 6 - a; ++a; } const int b = a + rem;
+            double* blk = v.Sblk + blk_index(c, c, v.nc) * 36;
+            red_add(blk + a * 6 + b, s);
+            if (a != b) red_add(blk + b * 6 + a, s);
+        } else if (t < 27) red_add(v.Scf + 6 * c + (t - 21), s);
+        else if (t < 33) red_add(v.rhs + 6 * c + (t - 27), s);
+        else if (t < 39) red_add(v.gcf + 6 * c + (t - 33), s);
+        else if (t < 45) red_add(v.dcf + 6 * c + (t - 39), s);
+        else if (t == 45) { red_add(v.Sff, s); red_add(v.dcf + fidx, s); }
+        else { red_add(v.rhs + fidx, s); red_add(v.gcf + fidx, s); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4: dense reduced system.  A is (npad x npad) row-major, lower triangle used, npad = multiple of NB > n;
+// row n carries the right-hand side (forward substitution for free), remaining pad rows are identity.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double* __restrict__ Scf, const double* __restrict__ Sff,
+                                   const double* __restrict__ rhs, const double* __restrict__ dcf, int nc, int npad,
+                                   double inv_radius, double min_diag, double max_diag, double* __restrict__ A) {
+    const int n = 6 * nc + 1;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= npad || c > r) return;
+    double val;
+    if (r < n) {
+        if (r == n - 1) val = (c == n - 1) ? *Sff : Scf[c];
+        else {
+            const int bi = r / 6, a = r - 6 * bi, bj = c / 6, b = c - 6 * bj;      // bj <= bi
+            val = Sblk[blk_index(bj, bi, nc) * 36 + b * 6 + a];
+        }
+        if (r == c) val += clampd(dcf[r], min_diag, max_diag) * inv_radius;
+    } else if (r == n) val = c < n ? rhs[c] : 0.0;          // augmented row (its own pivot is forced to 1)
+    else val = (r == c) ? 1.0 : 0.0;
+    A[(size_t)r * npad + c] = val;
+}
+
+// Panel step k: every CTA (block row i >= k) factors the 32x32 diagonal tile redundantly in shared memory; CTA i == k
+// writes it back, the others solve their tile against it: A[i][k] <- A[i][k] L_kk^-T.  Pivots with global index >= n
+// are forced to 1 (augmented / padding rows).  blockDim = (32, 32).
+__global__ void __launch_bounds__(1024) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int* __restrict__ fail) {
+    __shared__ double L[NB][NB + 1], B[NB][NB + 1];
+    const int r = threadIdx.y, c = threadIdx.x, i = k + blockIdx.x;
+    L[r][c] = A[(size_t)(k * NB + r) * npad + k * NB + c];
+    if (i != k) B[r][c] = A[(size_t)(i * NB + r) * npad + k * NB + c];
+    __syncthreads();
+    for (int j = 0; j < NB; ++j) {
+        const int gj = k * NB + j;
+        if (r == j && c == j) {
+            double d = L[j][j];
+            if (gj >= n) d = 1.0;
+            else if (!(d > 0.0) || !isfinite(d)) { if (i == k) atomicAdd(fail, 1); d = 1.0; }
+            else d = sqrt(d);
+            L[j][j] = d;
+        }
+        __syncthreads();
+        if (c == j && r > j) L[r][j] = (gj >= n) ? 0.0 : L[r][j] / L[j][j];
+        __syncthreads();
+        if (c > j && r >= c) L[r][c] -= L[r][j] * L[c][j];
+        __syncthreads();
+    }
+    if (i == k) {
+        if (c <= r) A[(size_t)(k * NB + r) * npad + k * NB + c] = L[r][c];
+        return;
+    }
+    // X L^T = B  ->  column by column
+    for (int j = 0; j < NB; ++j) {
+        if (c == j) B[r][j] = B[r][j] / L[j][j];
+        __syncthreads();
+        if (c > j) B[r][c] -= B[r][j] * L[c][j];
+        __syncthreads();
+    }
+    A[(size_t)(i * NB + r) * npad + k * NB + c] = B[r][c];
+}
+
+// Trailing update step k: tile (i, j), k < j <= i:  A[i][j] -= A[i][k] A[j][k]^T.  blockDim = (32, 32), grid = T(T+1)/2.
+__global__ void __launch_bounds__(1024) chol_update_kernel(double* __restrict__ A, int npad, int k, int nbk) {
+    __shared__ double P[NB][NB + 1], Q[NB][NB + 1];
+    // decode blockIdx.x -> (i, j) over the lower triangle of the trailing (T x T) tile matrix
+    int t = blockIdx.x, ii = 0;
+    while (t > ii) { t -= ii + 1; ++ii; }
+    const int i = k + 1 + ii, j = k + 1 + t;
+    (void)nbk;
+    const int r = threadIdx.y, c = threadIdx.x;
+    P[r][c] = A[(size_t)(i * NB + r) * npad + k * NB + c];
+    Q[r][c] = A[(size_t)(j * NB + r) * npad + k * NB + c];
+    __syncthreads();
+    double s = 0;
+#pragma unroll 8
+    for (int m = 0; m < NB; ++m) s += P[r][m] * Q[c][m];
+    if (i != j || c <= r) A[(size_t)(i * NB + r) * npad + j * NB + c] -= s;
+}
+
+// Back substitution L^T x = y with y = row n of the factored matrix.  Single CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) chol_backsolve_kernel(const double* __restrict__ A, int npad, int n, double* __restrict__ x) {
+    extern __shared__ double y[];                 // [npad]
+    __shared__ double T[NB][NB + 1];
+    const int tid = threadIdx.x, nbk = npad / NB;
+    for (int i = tid; i < npad; i += blockDim.x) y[i] = i < n ? A[(size_t)n * npad + i] : 0.0;
+    __syncthreads();
+    for (int kb = (n - 1) / NB; kb >= 0; --kb) {
+        for (int e = tid; e < NB * NB; e += blockDim.x) { const int r = e / NB, c = e % NB; T[r][c] = A[(size_t)(kb * NB + r) * npad + kb * NB + c]; }
+        __syncthreads();
+        if (tid < 32) {     // solve the 32x32 upper system T^T x = y_kb with one warp
+            double yi = y[kb * NB + tid];
+            for (int j = NB - 1; j >= 0; --j) {
+                const int gj = kb * NB + j;
+                double xj = 0.0;
+                if (tid == j) { xj = gj < n ? yi / T[j][j] : 0.0; yi = xj; }
+                xj = __shfl_sync(0xffffffffu, xj, j);
+                if (tid < j) yi -= T[j][tid] * xj;
+            }
+            y[kb * NB + tid] = yi;
+        }
+        __syncthreads();
+        // y[0 .. kb*NB) -= L[kb block rows][cols]^T x_kb
+        for (int c = tid; c < kb * NB; c += blockDim.x) {
+            double s = 0;
+#pragma unroll 8
+            for (int m = 0; m < NB; ++m) s += A[(size_t)(kb * NB + m) * npad + c] * y[kb * NB + m];
+            y[c] -= s;
+        }
+        __syncthreads();
+    }
+    (void)nbk;
+    for (int i = tid; i < n; i += blockDim.x) x[i] = y[i];
+}
+
+// cameras + focal: candidate = x - y*scale ; derived table of the candidate ; norms.  Single CTA.
+// locals[0] = |delta_cf|^2, [1] = |x_cf|^2, [2] = |cand_cf|^2, [3] = max |g_cf| (unscaled), [4] = max |g_pts| (max-reduced over ranks)
+__global__ void __launch_bounds__(256) ba_cam_update_kernel(const double* __restrict__ x_cf, const double* __restrict__ y_cf,
+                                                            const double* __restrict__ scale_cf, const double* __restrict__ gcf, int nc,
+                                                            double* __restrict__ cand_cf, CamDerived* __restrict__ camd_c, double* __restrict__ locals,
+                                                            double* __restrict__ post, const unsigned long long* __restrict__ gmax_pt_bits,
+                                                            const int* __restrict__ fail) {
+    const int n = 6 * nc + 1;
+    double dn = 0, xn = 0, cn = 0, gm = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = -y_cf[i] * scale_cf[i], xv = x_cf[i], cv = xv + d;
+        cand_cf[i] = cv;
+        const double dd = xv - cv;
+        dn += dd * dd; xn += xv * xv; cn += cv * cv;
+        gm = fmax(gm, fabs(gcf[i] / scale_cf[i]));
+    }
+    __shared__ double red[8][4];
+    const double a = warp_sum(dn), b = warp_sum(xn), c = warp_sum(cn), g = warp_max(gm);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = a; red[threadIdx.x >> 5][1] = b; red[threadIdx.x >> 5][2] = c; red[threadIdx.x >> 5][3] = g; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int w = 0; w < 8; ++w) { s0 += red[w][0]; s1 += red[w][1]; s2 += red[w][2]; s3 = fmax(s3, red[w][3]); }
+        locals[0] = s0; locals[1] = s1; locals[2] = s2; locals[3] = s3;
+        // rank-local flags -> buffers that are reduced over ranks (sum / max) so that every rank takes the same decision
+        locals[4] = __longlong_as_double((long long)*gmax_pt_bits);
+        post[4] = (double)fail[0]; post[5] = (double)fail[1];
+    }
+    __syncthreads();            // cand_cf complete
+    for (int c2 = threadIdx.x; c2 < nc; c2 += blockDim.x) { CamDerived d; cam_derive(cand_cf + 6 * c2, d); camd_c[c2] = d; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Back substitution for the points + step evaluation, fused (point-major, same grouping as K3a):
+//   y_p = M^T (zg - M sum_o Jp^T (Jc y_c + Jf y_f)) ;  candidate X' = X - y_p*scale
+//   model cost change accumulates  m.(r + m/2)  with m = J*step ;  candidate cost from the residual at the candidate.
+// post[0] = sum r'^2, post[1] = sum m.(r+m/2), post[2] = |delta_pts|^2, post[3] = |cand_pts|^2
+// ---------------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, const double* __restrict__ y_cf, const double* __restrict__ cand_cf,
+                                                                     const CamDerived* __restrict__ camd_c, double* __restrict__ pts_c,
+                                                                     double* __restrict__ post) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    constexpr int GB = PT_THREADS / G;
+    const double f = *v.focal, sf = v.scale_cf[6 * v.nc], yf = y_cf[6 * v.nc], fc = cand_cf[6 * v.nc];
+    double acc_cc = 0, acc_m = 0, acc_dn = 0, acc_cn = 0;
+    for (int p = blockIdx.x * GB + threadIdx.x / G; p < v.np; p += gridDim.x * GB) {
+        const int o0 = v.pt_off[p], k = v.pt_off[p + 1] - o0;
+        const double X[3] = {v.pts[3 * p], v.pts[3 * p + 1], v.pts[3 * p + 2]};
+        const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
+        const double* pb = v.ptblk + (size_t)p * 12;
+        const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
+        const double zg[3] = {pb[6], pb[7], pb[8]};
+        // pass 1: t = sum_o Jp^T (Jc y_c + Jf y_f)
+        double t[3] = {0, 0, 0};
+        for (int j = gl; j < k; j += G) {
+            const int o = o0 + j, c = v.obs_cam[o];
+            ObsJ J;
+            eval_scaled(v.camd[c], X, f, v.obs_xy[o], v.scale_cf + 6 * c, sp, sf, J);
+            double m0 = J.Jf[0] * yf, m1 = J.Jf[1] * yf;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { const double yc = y_cf[6 * c + a]; m0 += J.Jc[a] * yc; m1 += J.Jc[6 + a] * yc; }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) t[a] += J.Jp[a] * m0 + J.Jp[3 + a] * m1;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t[a] = group_sum<G>(t[a], gmask);
+        // u = zg - M t ; y_p = M^T u
+        const double u0 = zg[0] - M[0] * t[0], u1 = zg[1] - (M[1] * t[0] + M[2] * t[1]), u2 = zg[2] - (M[3] * t[0] + M[4] * t[1] + M[5] * t[2]);
+        const double yp[3] = {M[0] * u0 + M[1] * u1 + M[3] * u2, M[2] * u1 + M[4] * u2, M[5] * u2};
+        const double Xc[3] = {X[0] - yp[0] * sp[0], X[1] - yp[1] * sp[1], X[2] - yp[2] * sp[2]};
+        if (gl == 0) {
+            pts_c[3 * p] = Xc[0]; pts_c[3 * p + 1] = Xc[1]; pts_c[3 * p + 2] = Xc[2];
+            const double d0 = X[0] - Xc[0], d1 = X[1] - Xc[1], d2 = X[2] - Xc[2];
+            acc_dn += d0 * d0 + d1 * d1 + d2 * d2;
+            acc_cn += Xc[0] * Xc[0] + Xc[1] * Xc[1] + Xc[2] * Xc[2];
+        }
+        // pass 2: model residual m = -J y and candidate residual
+        for (int j = gl; j < k; j += G) {
+            const int o = o0 + j, c = v.obs_cam[o];
+            const float2 xy = v.obs_xy[o];
+            ObsJ J;
+            eval_scaled(v.camd[c], X, f, xy, v.scale_cf + 6 * c, sp, sf, J);
+            double m0 = J.Jf[0] * yf, m1 = J.Jf[1] * yf;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { const double yc = y_cf[6 * c + a]; m0 += J.Jc[a] * yc; m1 += J.Jc[6 + a] * yc; }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { m0 += J.Jp[a] * yp[a]; m1 += J.Jp[3 + a] * yp[a]; }
+            m0 = -m0; m1 = -m1;
+            acc_m += m0 * (J.r[0] + 0.5 * m0) + m1 * (J.r[1] + 0.5 * m1);
+            double rc[2];
+            obs_residual(camd_c[c], Xc, fc, (double)xy.x, (double)xy.y, rc);
+            acc_cc += rc[0] * rc[0] + rc[1] * rc[1];
+        }
+    }
+    __shared__ double sred[PT_THREADS / 32][4];
+    const double c0 = warp_sum(acc_cc), c1 = warp_sum(acc_m), c2 = warp_sum(acc_dn), c3 = warp_sum(acc_cn);
+    if (lane == 0) { sred[warp][0] = c0; sred[warp][1] = c1; sred[warp][2] = c2; sred[warp][3] = c3; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w][threadIdx.x];
+        red_add(post + threadIdx.x, s);
+    }
+}
+
+// camera-major copy of the observation list: counting sort by camera (structure is fixed across LM iterations)
+__global__ void count_cams_kernel(const int32_t* __restrict__ obs_cam, int nobs, int* __restrict__ cnt) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < nobs) atomicAdd(cnt + obs_cam[o], 1);
+}
+__global__ void scan_small_kernel(const int* __restrict__ cnt, int n, int32_t* __restrict__ off, int* __restrict__ cursor) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { int s = 0; for (int i = 0; i < n; ++i) { off[i] = s; cursor[i] = s; s += cnt[i]; } off[n] = s; }
+}
+__global__ void expand_obs_pt_kernel(const int32_t* __restrict__ pt_off, int np, int32_t* __restrict__ obs_pt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < np) for (int o = pt_off[p]; o < pt_off[p + 1]; ++o) obs_pt[o] = p;
+}
+__global__ void scatter_cm_kernel(const int32_t* __restrict__ obs_cam, const float2* __restrict__ obs_xy, const int32_t* __restrict__ obs_pt,
+                                  int nobs, int* __restrict__ cursor, float2* __restrict__ cm_xy, int32_t* __restrict__ cm_pt) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < nobs) { const int pos = atomicAdd(cursor + obs_cam[o], 1); cm_xy[pos] = obs_xy[o]; cm_pt[pos] = obs_pt[o]; }
+}
+
+}  // namespace
+
+// =================================================================================================================
+struct sfmb200_ba_problem {
+    sfmb200_ctx* ctx = nullptr;
+    int nc = 0, np = 0, nobs = 0, maxk = 0, G = 8, n = 0, npad = 0;
+    DevBuf mem;                       // one allocation, carved below
+    // observations
+    float2* obs_xy; int32_t* obs_cam; int32_t* pt_off; int32_t* cm_off; float2* cm_xy; int32_t* cm_pt;
+    // state: x = (cf, pts), candidate, initial
+    double* cf[2]; double* pts[2]; double* cf0; double* pts0; int cur = 0;
+    CamDerived* camd[2];
+    double* scale_cf; double* scale_pt; double* ptblk;
+    // reduced system buffer (one all-reduce): Sblk | Scf | Sff | rhs | gcf | dcf | sums[8]
+    double* red; size_t red_n; double* Sblk; double* Scf; double* Sff; double* rhs; double* gcf; double* dcf; double* sums;
+    double* post;                     // [8] summed over ranks
+    double* locals;                   // [8] identical on every rank
+    unsigned long long* gmax_pt_bits; int* fail;   // fail[0] point blocks, fail[1] dense Cholesky
+    double* A; double* y_cf;
+    double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
+    bool have_scale = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* opt) {
+    BAView v;
+    v.nc = P->nc; v.np = P->np; v.nobs = P->nobs; v.maxk = P->maxk;
+    v.obs_xy = P->obs_xy; v.obs_cam = P->obs_cam; v.pt_off = P->pt_off; v.cm_off = P->cm_off; v.cm_xy = P->cm_xy; v.cm_pt = P->cm_pt;
+    v.cams = P->cf[P->cur]; v.focal = P->cf[P->cur] + 6 * P->nc; v.pts = P->pts[P->cur]; v.camd = P->camd[P->cur];
+    v.scale_cf = P->scale_cf; v.scale_pt = P->scale_pt; v.ptblk = P->ptblk;
+    v.Sblk = P->Sblk; v.Scf = P->Scf; v.Sff = P->Sff; v.rhs = P->rhs; v.gcf = P->gcf; v.dcf = P->dcf; v.sums = P->sums;
+    v.gmax_pt_bits = P->gmax_pt_bits; v.fail = P->fail;
+    v.min_diag = opt->min_lm_diagonal; v.max_diag = opt->max_lm_diagonal;
+    return v;
+}
+
+static size_t point_smem_bytes(int G, int maxk) {
+    const int GB = PT_THREADS / G;
+    return (size_t)GB * maxk * 18 * 8 + (size_t)GB * maxk * 4 + (size_t)maxk * (maxk - 1) / 2 * 2 + 16;
+}
+
+template <int G> static int launch_point_pass(sfmb200_ba_problem* P, const BAView& v, double inv_radius) {
+    sfmb200_ctx* ctx = P->ctx;
+    const size_t smem = point_smem_bytes(G, P->maxk);
+    if (smem > 48 * 1024) SFM_CUDA(ctx, cudaFuncSetAttribute(ba_point_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int GB = PT_THREADS / G;
+    const int blocks = std::max(1, std::min(ceil_div(P->np, GB), ctx->sm_count * 8));
+    ba_point_kernel<G><<<blocks, PT_THREADS, smem, ctx->stream>>>(v, inv_radius);
+    SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
+template <int G> static int launch_point_norm(sfmb200_ba_problem* P, const BAView& v) {
+    sfmb200_ctx* ctx = P->ctx;
+    const int GB = PT_THREADS / G;
+    const int blocks = std::max(1, std::min(ceil_div(P->np, GB), ctx->sm_count * 16));
+    ba_point_norm_kernel<G><<<blocks, PT_THREADS, 0, ctx->stream>>>(v, P->scale_pt);
+    SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
+template <int G> static int launch_backsub(sfmb200_ba_problem* P, const BAView& v) {
+    sfmb200_ctx* ctx = P->ctx;
+    const int GB = PT_THREADS / G, nxt = P->cur ^ 1;
+    const int blocks = std::max(1, std::min(ceil_div(P->np, GB), ctx->sm_count * 16));
+    ba_backsub_eval_kernel<G><<<blocks, PT_THREADS, 0, ctx->stream>>>(v, P->y_cf, P->cf[nxt], P->camd[nxt], P->pts[nxt], P->post);
+    SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
+#define DISPATCH_G(P, call)                                   \
+    ((P)->G == 4 ? call<4> : (P)->G == 8 ? call<8> : (P)->G == 16 ? call<16> : call<32>)
+
+static dim3 camera_grid(const sfmb200_ba_problem* P) {
+    // enough CTAs per camera to fill the machine ~4x, at least one
+    const int avg = P->nc > 0 ? std::max(1, P->nobs / std::max(1, P->nc)) : 1;
+    int chunks = std::max(1, std::min(ceil_div(avg, CAM_THREADS), ceil_div(4 * P->ctx->sm_count, std::max(1, P->nc))));
+    return dim3(chunks, std::max(1, P->nc));
+}
+
+// Jacobi scaling at the current x (iteration 0).  Multi-GPU: camera/focal column norms are summed over ranks.
+static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt) {
+    sfmb200_ctx* ctx = P->ctx;
+    const int n = P->n;
+    if (!opt->jacobi_scaling) {
+        fill_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(P->scale_cf, n, 1.0); SFM_LAUNCH_CHECK(ctx);
+        if (P->np) { fill_kernel<<<ceil_div(3 * P->np, 256), 256, 0, ctx->stream>>>(P->scale_pt, 3 * (size_t)P->np, 1.0); SFM_LAUNCH_CHECK(ctx); }
+        P->have_scale = true;
+        return SFMB200_OK;
+    }
+    BAView v = make_view(P, opt);
+    cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
+    double* colnorm = P->gcf;    // scratch: reuse (zeroed here, re-zeroed before every pass)
+    SFM_CUDA(ctx, cudaMemsetAsync(colnorm, 0, sizeof(double) * n, ctx->stream));
+    if (P->np > 0 && P->nobs > 0) {
+        int rc = DISPATCH_G(P, launch_point_norm)(P, v); if (rc) return rc;
+        ba_camera_norm_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v, colnorm); SFM_LAUNCH_CHECK(ctx);
+    }
+    int rc = sfmb200_allreduce_sum_f64(ctx, colnorm, n); if (rc) return rc;
+    scale_from_norm_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(colnorm, n, P->scale_cf); SFM_LAUNCH_CHECK(ctx);
+    P->have_scale = true;
+    return SFMB200_OK;
+}
+
+// One residual+Jacobian+Schur pass at the current x for a given radius; leaves the (rank-summed) reduced system in red.
+static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius, bool profile) {
+    sfmb200_ctx* ctx = P->ctx;
+    BAView v = make_view(P, opt);
+    SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * P->red_n, ctx->stream));
+    SFM_CUDA(ctx, cudaMemsetAsync(P->post, 0, sizeof(double) * 8 + sizeof(double) * 8 + 16 + 16, ctx->stream));   // post, locals, gmax, fail
+    cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
+    if (P->np > 0 && P->nobs > 0) {
+        if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev0, ctx->stream));
+        int rc = DISPATCH_G(P, launch_point_pass)(P, v, 1.0 / radius); if (rc) return rc;
+        if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev1, ctx->stream));
+        ba_camera_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v); SFM_LAUNCH_CHECK(ctx);
+    }
+    return sfmb200_allreduce_sum_f64(ctx, P->red, P->red_n);
+}
+
+static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius) {
+    sfmb200_ctx* ctx = P->ctx;
+    const int npad = P->npad, nbk = npad / NB;
+    ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(P->Sblk, P->Scf, P->Sff, P->rhs, P->dcf, P->nc, npad, 1.0 / radius,
+                                                                                 opt->min_lm_diagonal, opt->max_lm_diagonal, P->A);
+    SFM_LAUNCH_CHECK(ctx);
+    for (int k = 0; k < nbk; ++k) {
+        chol_panel_kernel<<<nbk - k, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, P->n, k, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
+        const int T = nbk - k - 1;
+        if (T > 0) { chol_update_kernel<<<T * (T + 1) / 2, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, k, nbk); SFM_LAUNCH_CHECK(ctx); }
+    }
+    chol_backsolve_kernel<<<1, 1024, sizeof(double) * npad, ctx->stream>>>(P->A, npad, P->n, P->y_cf); SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
+
+extern "C" {
+
+void sfmb200_ba_default_options(sfmb200_ba_options* o) {
+    if (!o) return;
+    o->max_num_iterations = 500; o->max_solver_time_in_seconds = 10.0;
+    o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+    o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+    o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+    o->jacobi_scaling = 1; o->max_num_consecutive_invalid_steps = 5; o->verbose = 0; o->profile = 0;
+}
+
+int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const double* cams6, const double* pts3, double focal,
+                              const float* obs_xy, const int32_t* obs_cam, const int32_t* pt_off, sfmb200_ba_problem** out) {
+    if (!ctx || !out || nc < 0 || np < 0 || nobs < 0) return SFMB200_ERR_INVALID;
+    *out = nullptr;
+    if ((nc && !cams6) || (np && (!pts3 || !pt_off)) || (nobs && (!obs_xy || !obs_cam))) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "null buffer");
+    // validate the CSR: offsets monotone, cameras in range and strictly ascending within a point (std::map order, :146)
+    int maxk = 0;
+    if (np) {
+        if (pt_off[0] != 0 || pt_off[np] != nobs) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "pt_off must start at 0 and end at nobs");
+        for (int p = 0; p < np; ++p) {
+            const int k = pt_off[p + 1] - pt_off[p];
+            if (k < 0) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "pt_off not monotone at point %d", p);
+            maxk = std::max(maxk, k);
+            for (int o = pt_off[p]; o < pt_off[p + 1]; ++o) {
+                if (obs_cam[o] < 0 || obs_cam[o] >= nc) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "observation %d: camera %d out of range", o, obs_cam[o]);
+                if (o > pt_off[p] && obs_cam[o] <= obs_cam[o - 1]) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "point %d: cameras must be strictly ascending", p);
+            }
+        }
+    } else if (nobs) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "observations without points");
+    if (maxk > 255) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "a point is observed by %d views; at most 255 supported", maxk);
+
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    sfmb200_ba_problem* P = new sfmb200_ba_problem();
+    P->ctx = ctx; P->nc = nc; P->np = np; P->nobs = nobs; P->maxk = std::max(maxk, 1);
+    P->G = maxk <= 4 ? 4 : maxk <= 8 ? 8 : maxk <= 16 ? 16 : 32;
+    if (point_smem_bytes(P->G, P->maxk) > 200 * 1024) { delete P; return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "observations per point (%d) exceed the shared-memory budget", maxk); }
+    P->n = 6 * nc + 1; P->npad = ((P->n + 1) + NB - 1) / NB * NB;
+    const size_t nblk = (size_t)nc * (nc + 1) / 2, n = P->n;
+    P->red_n = 36 * nblk + 6 * (size_t)nc + 1 + 3 * n + 8;
+
+    size_t bytes = 0;
+    auto add = [&](size_t b) { bytes += Carver::pad(b) + 256; };
+    add(8 * (size_t)nobs); add(4 * (size_t)nobs); add(4 * (size_t)(np + 1)); add(4 * (size_t)(nc + 1)); add(8 * (size_t)nobs); add(4 * (size_t)nobs);
+    for (int i = 0; i < 3; ++i) { add(8 * n); add(24 * (size_t)np); }
+    add(sizeof(CamDerived) * (size_t)nc); add(sizeof(CamDerived) * (size_t)nc);
+    add(8 * n); add(24 * (size_t)np); add(96 * (size_t)np); add(8 * P->red_n); add(64 + 64 + 16 + 16);
+    add(8 * (size_t)P->npad * P->npad); add(8 * n); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
+    cudaError_t e = P->mem.reserve(bytes);
+    if (e != cudaSuccess) { delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    Carver cv(P->mem.p);
+    P->obs_xy = cv.take<float2>(nobs); P->obs_cam = cv.take<int32_t>(nobs); P->pt_off = cv.take<int32_t>(np + 1); P->cm_off = cv.take<int32_t>(nc + 1);
+    P->cm_xy = cv.take<float2>(nobs); P->cm_pt = cv.take<int32_t>(nobs);
+    P->cf[0] = cv.take<double>(n); P->pts[0] = cv.take<double>(3 * (size_t)np); P->cf[1] = cv.take<double>(n); P->pts[1] = cv.take<double>(3 * (size_t)np);
+    P->cf0 = cv.take<double>(n); P->pts0 = cv.take<double>(3 * (size_t)np);
+    P->camd[0] = cv.take<CamDerived>(nc); P->camd[1] = cv.take<CamDerived>(nc);
+    P->scale_cf = cv.take<double>(n); P->scale_pt = cv.take<double>(3 * (size_t)np); P->ptblk = cv.take<double>(12 * (size_t)np);
+    P->red = cv.take<double>(P->red_n);
+    P->Sblk = P->red; P->Scf = P->Sblk + 36 * nblk; P->Sff = P->Scf + 6 * (size_t)nc; P->rhs = P->Sff + 1; P->gcf = P->rhs + n; P->dcf = P->gcf + n; P->sums = P->dcf + n;
+    P->post = cv.take<double>(8 + 8 + 2 + 2); P->locals = P->post + 8; P->gmax_pt_bits = (unsigned long long*)(P->locals + 8); P->fail = (int*)(P->locals + 10);
+    P->A = cv.take<double>((size_t)P->npad * P->npad); P->y_cf = cv.take<double>(n);
+    int32_t* obs_pt = cv.take<int32_t>(nobs); int* cnt = cv.take<int>(2 * (size_t)(nc + 1)); int* cursor = cnt + nc + 1;
+
+    cudaStream_t st = ctx->stream;
+#define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { P->mem.release(); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
+    if (nobs) { CRT(cudaMemcpyAsync(P->obs_xy, obs_xy, 8 * (size_t)nobs, cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->obs_cam, obs_cam, 4 * (size_t)nobs, cudaMemcpyHostToDevice, st)); }
+    if (np) { CRT(cudaMemcpyAsync(P->pt_off, pt_off, 4 * (size_t)(np + 1), cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->pts0, pts3, 24 * (size_t)np, cudaMemcpyHostToDevice, st)); }
+    if (nc) CRT(cudaMemcpyAsync(P->cf0, cams6, 48 * (size_t)nc, cudaMemcpyHostToDevice, st));
+    CRT(cudaMemcpyAsync(P->cf0 + 6 * nc, &focal, 8, cudaMemcpyHostToDevice, st));
+    CRT(cudaStreamSynchronize(st));     // `focal` is a stack variable
+    // camera-major copy (device counting sort)
+    CRT(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * (nc + 1), st));
+    if (nobs) {
+        count_cams_kernel<<<ceil_div(nobs, 256), 256, 0, st>>>(P->obs_cam, nobs, cnt);
+        scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor);
+        expand_obs_pt_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, np, obs_pt);
+        scatter_cm_kernel<<<ceil_div(nobs, 256), 256, 0, st>>>(P->obs_cam, P->obs_xy, obs_pt, nobs, cursor, P->cm_xy, P->cm_pt);
+        ctx->launches += 4;
+    } else {
+        scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor); ctx->launches += 1;
+    }
+    CRT(cudaGetLastError());
+    CRT(cudaMallocHost((void**)&P->h_scal, sizeof(double) * 32));
+    CRT(cudaEventCreate(&P->ev0)); CRT(cudaEventCreate(&P->ev1));
+#undef CRT
+    *out = P;
+    SFM_CUDA(ctx, cudaMemcpyAsync(P->cf[0], P->cf0, 8 * n, cudaMemcpyDeviceToDevice, st));
+    if (np) SFM_CUDA(ctx, cudaMemcpyAsync(P->pts[0], P->pts0, 24 * (size_t)np, cudaMemcpyDeviceToDevice, st));
+    P->cur = 0; P->have_scale = false;
+    SFM_CUDA(ctx, cudaStreamSynchronize(st));
+    return SFMB200_OK;
+}
+
+void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
+    if (!P) return;
+    cudaSetDevice(P->ctx->device);
+    cudaStreamSynchronize(P->ctx->stream);
+    if (P->h_scal) cudaFreeHost(P->h_scal);
+    if (P->ev0) cudaEventDestroy(P->ev0);
+    if (P->ev1) cudaEventDestroy(P->ev1);
+    P->mem.release();
+    delete P;
+}
+
+int sfmb200_ba_problem_reset(sfmb200_ba_problem* P) {
+    if (!P) return SFMB200_ERR_INVALID;
+    sfmb200_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SFM_CUDA(ctx, cudaMemcpyAsync(P->cf[0], P->cf0, 8 * (size_t)P->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (P->np) SFM_CUDA(ctx, cudaMemcpyAsync(P->pts[0], P->pts0, 24 * (size_t)P->np, cudaMemcpyDeviceToDevice, ctx->stream));
+    P->cur = 0; P->have_scale = false;
+    return SFMB200_OK;
+}
+
+int sfmb200_ba_problem_download(sfmb200_ba_problem* P, double* cams6, double* pts3, double* focal) {
+    if (!P) return SFMB200_ERR_INVALID;
+    sfmb200_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (cams6 && P->nc) SFM_CUDA(ctx, cudaMemcpyAsync(cams6, P->cf[P->cur], 48 * (size_t)P->nc, cudaMemcpyDeviceToHost, ctx->stream));
+    if (focal) SFM_CUDA(ctx, cudaMemcpyAsync(focal, P->cf[P->cur] + 6 * P->nc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pts3 && P->np) SFM_CUDA(ctx, cudaMemcpyAsync(pts3, P->pts[P->cur], 24 * (size_t)P->np, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFMB200_OK;
+}
+
+int sfmb200_ba_problem_reduced_system(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_in, double radius,
+                                      double* S, double* rhs, double* grad_cf, double* cost) {
+    if (!P || !(radius > 0)) return SFMB200_ERR_INVALID;
+    sfmb200_ctx* ctx = P->ctx;
+    sfmb200_ba_options opt; if (opt_in) opt = *opt_in; else sfmb200_ba_default_options(&opt);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (!P->have_scale) { rc = compute_scaling(P, &opt); if (rc) return rc; }
+    rc = schur_pass(P, &opt, radius, false); if (rc) return rc;
+    const int n = P->n, npad = P->npad;
+    ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(P->Sblk, P->Scf, P->Sff, P->rhs, P->dcf, P->nc, npad, 1.0 / radius,
+                                                                                 opt.min_lm_diagonal, opt.max_lm_diagonal, P->A);
+    SFM_LAUNCH_CHECK(ctx);
+    std::vector<double> hA((size_t)npad * npad), hg(n), hs(n), hsum(8);
+    SFM_CUDA(ctx, cudaMemcpyAsync(hA.data(), P->A, 8 * hA.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(hg.data(), P->gcf, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(hs.data(), P->scale_cf, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(hsum.data(), P->sums, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (S) for (int r = 0; r < n; ++r) for (int c = 0; c <= r; ++c) { const double v = hA[(size_t)r * npad + c]; S[(size_t)r * n + c] = v; S[(size_t)c * n + r] = v; }
+    if (rhs) for (int c = 0; c < n; ++c) rhs[c] = hA[(size_t)n * npad + c];
+    if (grad_cf) for (int c = 0; c < n; ++c) grad_cf[c] = hg[c] / hs[c];
+    if (cost) *cost = 0.5 * hsum[0];
+    return SFMB200_OK;
+}
+
+int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_in, sfmb200_ba_summary* sum) {
+    if (!P || !sum) return SFMB200_ERR_INVALID;
+    sfmb200_ctx* ctx = P->ctx;
+    sfmb200_ba_options opt; if (opt_in) opt = *opt_in; else sfmb200_ba_default_options(&opt);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(sum, 0, sizeof *sum);
+    const auto t_start = std::chrono::steady_clock::now();
+    auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    const int64_t launches0 = ctx->launches;
+    int rc = compute_scaling(P, &opt); if (rc) return rc;
+
+    double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
+    int iter = 0, invalid_steps = 0;
+    bool new_point = true;          // gradient / cost of the current x not yet examined
+    double x_cost = 0, x_norm = 0, gmax = 0;
+    sum->termination_type = SFMB200_BA_NO_CONVERGENCE;
+    double* h = P->h_scal;
+
+    for (;;) {
+        // ---- one LM iteration on the device: pass at x, dense solve, candidate, evaluation -------------------
+        rc = schur_pass(P, &opt, radius, opt.profile != 0); if (rc) return rc;
+        sum->num_jacobian_passes++;
+        rc = dense_solve(P, &opt, radius); if (rc) return rc;
+        sum->num_linear_solves++;
+        const int nxt = P->cur ^ 1;
+        ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(P->cf[P->cur], P->y_cf, P->scale_cf, P->gcf, P->nc, P->cf[nxt], P->camd[nxt], P->locals,
+                                                         P->post, P->gmax_pt_bits, P->fail);
+        SFM_LAUNCH_CHECK(ctx);
+        if (P->np > 0 && P->nobs > 0) { BAView v = make_view(P, &opt); rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }
+        rc = sfmb200_allreduce_sum_f64(ctx, P->post, 8); if (rc) return rc;
+        rc = sfmb200_allreduce_max_f64(ctx, P->locals + 4, 1); if (rc) return rc;
+        // read back: sums[8] | post[8] locals[8] gmax fail[2]
+        SFM_CUDA(ctx, cudaMemcpyAsync(h, P->sums, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(h + 8, P->post, 8 * 20, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (opt.profile) { float ms = 0; if (cudaEventElapsedTime(&ms, P->ev0, P->ev1) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; } }
+        const double cost_x = 0.5 * h[0], xn2_pts = h[1];
+        const double cand_cost_raw = 0.5 * h[8], model_acc = h[9], dn2_pts = h[10], cn2_pts = h[11];
+        const double dn2_cf = h[16], xn2_cf = h[17], cn2_cf = h[18], gmax_cf = h[19];
+        const double gmax_pt = h[20];                                  // max over ranks
+        const double fails[2] = {h[12], h[13]};                        // summed over ranks
+        if (new_point) {
+            x_cost = cost_x; x_norm = std::sqrt(xn2_pts + xn2_cf); gmax = std::max(gmax_pt, gmax_cf);
+            if (iter == 0) {
+                sum->initial_cost = x_cost;
+                if (!std::isfinite(x_cost)) { sum->termination_type = SFMB200_BA_FAILURE; snprintf(sum->message, sizeof sum->message, "Residual and Jacobian evaluation failed."); break; }
+                if (opt.verbose) printf("iter %3d cost %.9e |g|max %.3e radius %.3e\n", 0, x_cost, gmax, radius);
+            }
+            if (iter == 0 && gmax <= opt.gradient_tolerance) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break; }
+            new_point = false;
+        }
+        // FinalizeIterationAndCheckIfMinimizerCanContinue of the previous iteration (Ceres' order: time, iterations, gradient, radius)
+        if (opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { snprintf(sum->message, sizeof sum->message, "Maximum solver time reached."); break; }
+        if (iter >= opt.max_num_iterations) { snprintf(sum->message, sizeof sum->message, "Maximum number of iterations reached."); break; }
+        if (iter > 0 && gmax <= opt.gradient_tolerance) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break; }
+        if (radius <= opt.min_trust_region_radius) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Minimum trust region radius reached."); break; }
+        ++iter;
+
+        const bool lin_ok = fails[0] == 0.0 && fails[1] == 0.0 && std::isfinite(model_acc) && std::isfinite(dn2_pts) && std::isfinite(dn2_cf);
+        const double model_cost_change = -model_acc;
+        if (!lin_ok || !(model_cost_change > 0.0)) {
+            sum->num_unsuccessful_steps++;
+            if (++invalid_steps >= opt.max_num_consecutive_invalid_steps) {
+                sum->termination_type = SFMB200_BA_FAILURE;
+                snprintf(sum->message, sizeof sum->message, "Number of consecutive invalid steps more than max_num_consecutive_invalid_steps: %d", opt.max_num_consecutive_invalid_steps);
+                break;
+            }
+            radius /= decrease_factor; decrease_factor *= 2.0;
+            if (opt.verbose) printf("iter %3d INVALID step radius %.3e\n", iter, radius);
+            continue;
+        }
+        invalid_steps = 0;
+        const double step_norm = std::sqrt(dn2_pts + dn2_cf);
+        const double cand_cost = std::isfinite(cand_cost_raw) ? cand_cost_raw : DBL_MAX;
+        if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+            sum->termination_type = SFMB200_BA_CONVERGENCE;
+            snprintf(sum->message, sizeof sum->message, "Parameter tolerance reached. Relative step_norm: %e <= %e.", step_norm / (x_norm + opt.parameter_tolerance), opt.parameter_tolerance);
+            break;
+        }
+        const double cost_change = x_cost - cand_cost;
+        if (std::fabs(cost_change) <= opt.function_tolerance * x_cost) {
+            sum->termination_type = SFMB200_BA_CONVERGENCE;
+            snprintf(sum->message, sizeof sum->message, "Function tolerance reached. |cost_change|/cost: %e <= %e", std::fabs(cost_change) / x_cost, opt.function_tolerance);
+            break;
+        }
+        const double relative_decrease = cost_change / model_cost_change;
+        if (relative_decrease > opt.min_relative_decrease) {
+            P->cur = nxt;                       // x <- candidate
+            x_norm = std::sqrt(cn2_pts + cn2_cf); new_point = true;
+            const double q = 2.0 * relative_decrease - 1.0;
+            radius = std::min(opt.max_trust_region_radius, radius / std::max(1.0 / 3.0, 1.0 - q * q * q));
+            decrease_factor = 2.0;
+            sum->num_successful_steps++;
+            x_cost = cand_cost;                 // refreshed from the pass at the new point next iteration
+        } else {
+            radius /= decrease_factor; decrease_factor *= 2.0;
+            sum->num_unsuccessful_steps++;
+        }
+        if (opt.verbose) printf("iter %3d cost %.9e |g|max %.3e radius %.3e rho %.3e %s\n", iter, x_cost, gmax, radius, relative_decrease, new_point ? "ok" : "rejected");
+    }
+    sum->num_iterations = iter; sum->final_cost = x_cost; sum->total_time_s = elapsed();
+    sum->kernel_launches = ctx->launches - launches0;
+    return SFMB200_OK;
+}
+
+int sfmb200_ba_solve(sfmb200_ctx* ctx, const sfmb200_ba_options* opt, int nc, int np, int nobs, double* cams6, double* pts3, double* focal,
+                     const float* obs_xy, const int32_t* obs_cam, const int32_t* pt_off, sfmb200_ba_summary* summary) {
+    if (!ctx || !focal || !summary) return SFMB200_ERR_INVALID;
+    sfmb200_ba_problem* P = nullptr;
+    int rc = sfmb200_ba_problem_create(ctx, nc, np, nobs, cams6, pts3, *focal, obs_xy, obs_cam, pt_off, &P);
+    if (rc) return rc;
+    rc = sfmb200_ba_problem_run(P, opt, summary);
+    if (!rc) rc = sfmb200_ba_problem_download(P, cams6, pts3, focal);
+    sfmb200_ba_problem_destroy(P);
+    return rc;
+}
+
+// ---- pose <-> parameter conversions of adjustBundle -------------------------------------------------------------
+// ceres::RotationMatrixToAngleAxis<float>(R.t().val, aa) (:126): float arithmetic through a quaternion.
+void sfmb200_rotmat_to_angle_axis_f32(const float* R, float* aa) {
+    // R row-major; element (i,j) = R[3*i+j]
+    const float trace = R[0] + R[4] + R[8];
+    float q[4];
+    if (trace >= 0.0f) {
+        float t = sqrtf(trace + 1.0f);
+        q[0] = 0.5f * t; t = 0.5f / t;
+        q[1] = (R[7] - R[5]) * t; q[2] = (R[2] - R[6]) * t; q[3] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        float t = sqrtf(R[4 * i] - R[4 * j] - R[4 * k] + 1.0f);
+        q[i + 1] = 0.5f * t; t = 0.5f / t;
+        q[0] = (R[3 * k + j] - R[3 * j + k]) * t; q[j + 1] = (R[3 * j + i] + R[3 * i + j]) * t; q[k + 1] = (R[3 * k + i] + R[3 * i + k]) * t;
+    }
+    const float s2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (s2 > 0.0f) {
+        const float s = sqrtf(s2), c = q[0];
+        const float two_theta = 2.0f * (c < 0.0f ? atan2f(-s, -c) : atan2f(s, c));
+        const float kk = two_theta / s;
+        aa[0] = q[1] * kk; aa[1] = q[2] * kk; aa[2] = q[3] * kk;
+    } else { aa[0] = q[1] * 2.0f; aa[1] = q[2] * 2.0f; aa[2] = q[3] * 2.0f; }
+}
+
+// ceres::AngleAxisToRotationMatrix followed by the reference's transposing write-back (:203-209): row-major R.
+void sfmb200_angle_axis_to_rotmat(const double* aa, double* R) {
+    CamDerived d; const double cam[6] = {aa[0], aa[1], aa[2], 0, 0, 0};
+    cam_derive(cam, d);
+    for (int i = 0; i < 9; ++i) R[i] = d.R[i];
+}
+
+}  // extern "C"

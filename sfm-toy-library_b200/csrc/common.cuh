@@ -1,0 +1,94 @@
+// common.cuh -- context, error plumbing and device scratch shared by every stage of libsfmb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+
+#include "../../include/sfmb200.h"
+
+// One growable device buffer + one pinned host buffer per purpose, reused across calls (cudaMalloc/cudaFree are
+// milliseconds; the reference calls each stage many times per runSfM()).
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// bump allocator over a DevBuf: carve() after a single reserve()
+struct Carver {
+    char* base; size_t off = 0;
+    explicit Carver(void* b) : base((char*)b) {}
+    template <typename T> T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* r = (T*)(base + off); off += n * sizeof(T); return r;
+    }
+    static size_t pad(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+struct CommState;   // comm.cu
+
+struct sfmb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    std::mutex mu;              // matchFeatures is called from several host threads in the reference (SfM.cpp:173-211)
+    DevBuf scratch;             // per-call device scratch (kernel workspace)
+    DevBuf scratch2;            // per-call device scratch (stage outputs)
+    PinBuf pinned;              // per-call pinned staging (results read-back)
+    CommState* comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+int sfmb200_fail(sfmb200_ctx* ctx, int code, const char* fmt, ...);
+
+#define SFM_CUDA(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return sfmb200_fail((ctx), e_ == cudaErrorMemoryAllocation ? SFMB200_ERR_NOMEM : SFMB200_ERR_CUDA, \
+                                "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+    } while (0)
+
+#define SFM_LAUNCH_CHECK(ctx)                                                                            \
+    do {                                                                                                 \
+        (ctx)->launches++;                                                                               \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess)                                                                           \
+            return sfmb200_fail((ctx), SFMB200_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// multi-GPU (comm.cu): in-place sum over ranks of n doubles on the ctx stream; no-op when nranks == 1
+int sfmb200_allreduce_sum_f64(sfmb200_ctx* ctx, double* dbuf, size_t n);
+int sfmb200_allreduce_max_f64(sfmb200_ctx* ctx, double* dbuf, size_t n);
+void sfmb200_comm_destroy(sfmb200_ctx* ctx);

@@ -1,0 +1,449 @@
+// match.cu -- K1: brute-force 2-nearest-neighbour descriptor matching with fused ratio test.
+//
+// Replaces SfM2DFeatureUtilities::matchFeatures (reference SfMToyLib/SfM2DFeatureUtilities.cpp:53-71):
+//   cv::DescriptorMatcher("BruteForce-Hamming")->knnMatch(k=2)  (:59-60)  + ratio test d0 < (double)0.8f * d1 (:35, :65)
+// and, batched over image pairs, the thread fan-out of SfM::createFeatureMatchMatrix (SfM.cpp:157-212).
+//
+// Integer path (bit-exact): XOR + POPC on 32-bit words, distance in int, ordering lexicographic on
+// (distance, trainIdx) so that ties go to the lower train index like cv::batchDistance.
+//
+// Kernels
+//   knn2_hamming_kernel<WORDS>  grid (qblocks*splits, pairs): each thread owns QPT query rows in registers; train rows are
+//                               staged through shared memory in tiles (coalesced 16-byte loads, broadcast LDS.128 reads);
+//                               top-2 per (query, train split) -> partial[].  The Nq x Nt distance matrix never exists.
+//   merge_flag_scan_kernel      merges the splits in index order, applies the ratio test in double, block-scans the flags
+//   scan_sums_kernel            exclusive scan of the per-block survivor counts (single CTA, chained)
+//   scatter_kernel              order-preserving compaction into (queryIdx, trainIdx, distance) + per-pair counts
+#include "common.cuh"
+
+namespace {
+
+constexpr int KNN_THREADS = 128;
+constexpr int QPT = 2;                       // query rows per thread
+constexpr int QBLOCK = KNN_THREADS * QPT;    // query rows per CTA
+constexpr int TILE = 128;                    // train rows per shared-memory tile
+constexpr int SCAN_THREADS = 1024;
+
+struct PairDesc {          // one (left,right) image pair
+    int q_row, nq;         // rows of the left image inside the descriptor array
+    int t_row, nt;         // rows of the right image
+    int64_t out_row;       // first row of this pair in the flattened [sum nq] arrays
+};
+
+struct Top2 { int d0, i0, d1, i1; };
+
+__device__ __forceinline__ void top2_insert(Top2& b, int d, int j) {
+    if (d < b.d0) { b.d1 = b.d0; b.i1 = b.i0; b.d0 = d; b.i0 = j; }
+    else if (d < b.d1) { b.d1 = d; b.i1 = j; }
+}
+
+template <int WORDS>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn2_hamming_kernel(const uint32_t* __restrict__ desc, const PairDesc* __restrict__ pairs, int qblocks, int splits,
+                    int4* __restrict__ partial) {
+    __shared__ __align__(16) uint32_t tile[TILE * WORDS];
+    const PairDesc pd = pairs[blockIdx.y];
+    const int qb = blockIdx.x / splits, sp = blockIdx.x % splits;
+    if (qb * QBLOCK >= pd.nq) return;
+    // train rows of this split: [t_begin, t_end)
+    const int chunk = (pd.nt + splits - 1) / splits;
+    const int t_begin = sp * chunk, t_end = min(pd.nt, t_begin + chunk);
+
+    uint32_t q[QPT][WORDS];
+    Top2 best[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+        const int row = qb * QBLOCK + u * KNN_THREADS + threadIdx.x;
+        best[u] = {INT_MAX, -1, INT_MAX, -1};
+        const uint4* src = reinterpret_cast<const uint4*>(desc + (size_t)(pd.q_row + min(row, pd.nq - 1)) * WORDS);
+#pragma unroll
+        for (int w = 0; w < WORDS / 4; ++w) {
+            const uint4 v = __ldg(src + w);
+            q[u][4 * w] = v.x; q[u][4 * w + 1] = v.y; q[u][4 * w + 2] = v.z; q[u][4 * w + 3] = v.w;
+        }
+    }
+
+    for (int t0 = t_begin; t0 < t_end; t0 += TILE) {
+        const int rows = min(TILE, t_end - t0);
+        __syncthreads();
+        {   // stage `rows` train rows: rows*WORDS/4 uint4, coalesced
+            const uint4* src = reinterpret_cast<const uint4*>(desc + (size_t)(pd.t_row + t0) * WORDS);
+            uint4* dst = reinterpret_cast<uint4*>(tile);
+            for (int i = threadIdx.x; i < rows * (WORDS / 4); i += KNN_THREADS) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < rows; ++j) {
+            const uint4* tr = reinterpret_cast<const uint4*>(tile + j * WORDS);
+            int d[QPT];
+#pragma unroll
+            for (int u = 0; u < QPT; ++u) d[u] = 0;
+#pragma unroll
+            for (int w = 0; w < WORDS / 4; ++w) {
+                const uint4 v = tr[w];                  // same address for the whole warp: one broadcast wavefront
+#pragma unroll
+                for (int u = 0; u < QPT; ++u)
+                    d[u] += __popc(q[u][4 * w] ^ v.x) + __popc(q[u][4 * w + 1] ^ v.y) + __popc(q[u][4 * w + 2] ^ v.z) +
+                            __popc(q[u][4 * w + 3] ^ v.w);
+            }
+#pragma unroll
+            for (int u = 0; u < QPT; ++u) top2_insert(best[u], d[u], t0 + j);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+        const int row = qb * QBLOCK + u * KNN_THREADS + threadIdx.x;
+        if (row < pd.nq) partial[(size_t)(pd.out_row + row) * splits + sp] = make_int4(best[u].d0, best[u].i0, best[u].d1, best[u].i1);
+    }
+}
+
+// L2 (float) variant: one warp per query row, lanes split the dimension; squared distance accumulated in float32,
+// sqrt in float (cv::BFMatcher(NORM_L2)).  Exact for integer-valued descriptors (sums < 2^24).
+__global__ void __launch_bounds__(256)
+knn2_l2_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim, int splits, float4* __restrict__ partial) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int row = warp / splits, sp = warp % splits;
+    if (row >= nq) return;
+    const int chunk = (nt + splits - 1) / splits, t_begin = sp * chunk, t_end = min(nt, t_begin + chunk);
+    float d0 = 3.4e38f, d1 = 3.4e38f; int i0 = -1, i1 = -1;
+    for (int j = t_begin; j < t_end; ++j) {
+        float s = 0.f;
+        for (int k = lane; k < dim; k += 32) { const float e = q[(size_t)row * dim + k] - __ldg(t + (size_t)j * dim + k); s = fmaf(e, e, s); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (s < d0) { d1 = d0; i1 = i0; d0 = s; i0 = j; } else if (s < d1) { d1 = s; i1 = j; }
+    }
+    if (lane == 0) partial[(size_t)row * splits + sp] = make_float4(d0, __int_as_float(i0), d1, __int_as_float(i1));
+}
+
+// warp + block exclusive scan of one int per thread (SCAN_THREADS threads); returns exclusive prefix, total in *total
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+    __shared__ int warp_sums[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += n; }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int base = w > 0 ? warp_sums[w - 1] : 0;
+    *total = warp_sums[SCAN_THREADS / 32 - 1];
+    return base + inc - v;
+}
+
+// rows = flattened query rows of all pairs.  is_l2: partials are float4 (squared distances)
+__global__ void __launch_bounds__(SCAN_THREADS)
+merge_flag_scan_kernel(const int4* __restrict__ partial, int splits, int64_t rows, double ratio, int is_l2,
+                       int32_t* __restrict__ best_t, float* __restrict__ best_d, int32_t* __restrict__ rank,
+                       uint8_t* __restrict__ flag, int32_t* __restrict__ block_sums) {
+    const int64_t g = (int64_t)blockIdx.x * SCAN_THREADS + threadIdx.x;
+    int keep = 0;
+    if (g < rows) {
+        float fd0, fd1; int i0 = -1, i1 = -1;
+        if (!is_l2) {
+            Top2 b = {INT_MAX, -1, INT_MAX, -1};
+            for (int s = 0; s < splits; ++s) {
+                const int4 p = partial[(size_t)g * splits + s];
+                if (p.y >= 0) top2_insert(b, p.x, p.y);
+                if (p.w >= 0) top2_insert(b, p.z, p.w);
+            }
+            i0 = b.i0; i1 = b.i1; fd0 = (float)b.d0; fd1 = (float)b.d1;          // DMatch.distance is float
+        } else {
+            float d0 = 3.4e38f, d1 = 3.4e38f;
+            const float4* pf = reinterpret_cast<const float4*>(partial);
+            for (int s = 0; s < splits; ++s) {
+                const float4 p = pf[(size_t)g * splits + s];
+                const int a = __float_as_int(p.y), c = __float_as_int(p.w);
+                if (a >= 0) { if (p.x < d0) { d1 = d0; i1 = i0; d0 = p.x; i0 = a; } else if (p.x < d1) { d1 = p.x; i1 = a; } }
+                if (c >= 0) { if (p.z < d0) { d1 = d0; i1 = i0; d0 = p.z; i0 = c; } else if (p.z < d1) { d1 = p.z; i1 = c; } }
+            }
+            fd0 = sqrtf(d0); fd1 = sqrtf(d1);
+        }
+        // reference: initialMatching[i][0].distance < NN_MATCH_RATIO * initialMatching[i][1].distance, in double (:65)
+        keep = (i0 >= 0 && i1 >= 0) && ((double)fd0 < ratio * (double)fd1);
+        best_t[g] = i0; best_d[g] = fd0; flag[g] = (uint8_t)keep;
+    }
+    int total;
+    const int ex = block_exclusive_scan(keep, &total);
+    if (g < rows) rank[g] = ex;
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// in-place exclusive scan of block_sums[n] (single CTA, chained over chunks); total -> *grand_total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t* __restrict__ sums, int n, int64_t* __restrict__ grand_total) {
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += SCAN_THREADS) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? sums[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, &total);
+        const int carry = carry_s;
+        if (i < n) sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scatter_kernel(const PairDesc* __restrict__ pairs, int n_pairs, int64_t rows, const int32_t* __restrict__ best_t,
+               const float* __restrict__ best_d, const int32_t* __restrict__ rank, const uint8_t* __restrict__ flag,
+               const int32_t* __restrict__ block_off, int32_t* __restrict__ out_q, int32_t* __restrict__ out_t,
+               float* __restrict__ out_d, int32_t* __restrict__ pair_start /* [n_pairs+1] dense position of each pair's first survivor */) {
+    const int64_t g = (int64_t)blockIdx.x * SCAN_THREADS + threadIdx.x;
+    if (g >= rows) return;
+    const int pos = block_off[blockIdx.x] + rank[g];
+    // which pair does row g belong to?  binary search on out_row
+    int lo = 0, hi = n_pairs - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pairs[mid].out_row <= g) lo = mid; else hi = mid - 1; }
+    const int local = (int)(g - pairs[lo].out_row);
+    if (local == 0) pair_start[lo] = pos;
+    if (flag[g]) { out_q[pos] = local; out_t[pos] = best_t[g]; out_d[pos] = best_d[g]; }
+}
+
+int choose_splits(int sm_count, int64_t ctas_without_split, int nt_max) {
+    int s = 1;
+    while (ctas_without_split * s < 4LL * sm_count && s < 32 && nt_max / (s * 2) >= TILE) s *= 2;
+    return s;
+}
+
+}  // namespace
+
+struct sfmb200_descset {
+    sfmb200_ctx* ctx;
+    uint32_t* d_desc = nullptr;
+    std::vector<int32_t> img_off;
+    int n_img = 0, words = 0, max_rows = 0;
+};
+
+// core: pairs already on the host as PairDesc; descriptors on the device.  Leaves the dense compacted results in
+// d_out_* (device) and per-pair dense start positions in d_pair_start [n_pairs+1].
+static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, int words, const std::vector<PairDesc>& hp, int64_t rows, int nq_max, int nt_max,
+                      double ratio, int32_t* d_out_q, int32_t* d_out_t, float* d_out_d, int32_t* d_pair_start, int64_t* d_total, DevBuf& work) {
+    const int n_pairs = (int)hp.size();
+    const int qblocks = ceil_div(nq_max, QBLOCK);
+    const int splits = choose_splits(ctx->sm_count, (int64_t)qblocks * n_pairs, nt_max);
+    const int nblk = (int)ceil_div64(rows, SCAN_THREADS);
+    size_t bytes = Carver::pad(sizeof(PairDesc) * n_pairs) + Carver::pad(sizeof(int4) * rows * splits) + Carver::pad(4 * rows) * 3 +
+                   Carver::pad(rows) + Carver::pad(4 * (size_t)nblk) + 4096;
+    SFM_CUDA(ctx, work.reserve(bytes));
+    Carver cv(work.p);
+    PairDesc* d_pairs = cv.take<PairDesc>(n_pairs);
+    int4* d_partial = cv.take<int4>((size_t)rows * splits);
+    int32_t* d_best_t = cv.take<int32_t>(rows); float* d_best_d = cv.take<float>(rows); int32_t* d_rank = cv.take<int32_t>(rows);
+    uint8_t* d_flag = cv.take<uint8_t>(rows); int32_t* d_bsum = cv.take<int32_t>(nblk);
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_pairs, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid(qblocks * splits, n_pairs);
+    switch (words) {
+        case 4: knn2_hamming_kernel<4><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial); break;
+        case 8: knn2_hamming_kernel<8><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial); break;
+        case 16: knn2_hamming_kernel<16><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial); break;
+        case 32: knn2_hamming_kernel<32><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial); break;
+        default: return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "desc_bytes must be 16, 32, 64 or 128 (got %d)", words * 4);
+    }
+    SFM_LAUNCH_CHECK(ctx);
+    merge_flag_scan_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_partial, splits, rows, ratio, 0, d_best_t, d_best_d, d_rank, d_flag, d_bsum);
+    SFM_LAUNCH_CHECK(ctx);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_bsum, nblk, d_total);
+    SFM_LAUNCH_CHECK(ctx);
+    scatter_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_pairs, n_pairs, rows, d_best_t, d_best_d, d_rank, d_flag, d_bsum, d_out_q, d_out_t, d_out_d, d_pair_start);
+    SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
+
+static int build_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, std::vector<PairDesc>& hp,
+                       int64_t& rows, int& nq_max, int& nt_max) {
+    hp.resize(n_pairs); rows = 0; nq_max = 0; nt_max = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const int l = pairs[2 * p], r = pairs[2 * p + 1];
+        if (l < 0 || r < 0 || l >= set->n_img || r >= set->n_img) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "pair %d: image id out of range", p);
+        PairDesc d; d.q_row = set->img_off[l]; d.nq = set->img_off[l + 1] - d.q_row; d.t_row = set->img_off[r]; d.nt = set->img_off[r + 1] - d.t_row;
+        d.out_row = rows; rows += d.nq; hp[p] = d;
+        nq_max = std::max(nq_max, d.nq); nt_max = std::max(nt_max, d.nt);
+    }
+    return SFMB200_OK;
+}
+
+extern "C" {
+
+int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc, const int32_t* img_off, int n_img, int desc_bytes, sfmb200_descset** out) {
+    if (!ctx || !out || !img_off || n_img < 0) return SFMB200_ERR_INVALID;
+    *out = nullptr;
+    if (desc_bytes <= 0 || desc_bytes % 16) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "desc_bytes must be a multiple of 16 (got %d)", desc_bytes);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    sfmb200_descset* s = new sfmb200_descset();
+    s->ctx = ctx; s->n_img = n_img; s->words = desc_bytes / 4; s->img_off.assign(img_off, img_off + n_img + 1);
+    for (int i = 0; i < n_img; ++i) {
+        if (img_off[i + 1] < img_off[i]) { delete s; return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "img_off not monotone"); }
+        s->max_rows = std::max(s->max_rows, img_off[i + 1] - img_off[i]);
+    }
+    const size_t bytes = (size_t)img_off[n_img] * desc_bytes;
+    cudaError_t e = cudaMalloc(&s->d_desc, bytes + 16);
+    if (e != cudaSuccess) { delete s; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    if (bytes) {
+        e = cudaMemcpyAsync(s->d_desc, desc, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(s->d_desc); delete s; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e)); }
+    }
+    *out = s;
+    return SFMB200_OK;
+}
+
+void sfmb200_descset_destroy(sfmb200_descset* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_desc);
+    delete s;
+}
+
+int sfmb200_match_pairs_device(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, double ratio,
+                               int32_t* d_out_q, int32_t* d_out_t, float* d_out_d, int32_t* d_pair_start, int64_t* d_total) {
+    if (!ctx || !set || (n_pairs > 0 && !pairs) || !d_pair_start || !d_total) return SFMB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_pairs == 0) return SFMB200_OK;
+    std::vector<PairDesc> hp; int64_t rows; int nq_max, nt_max;
+    int rc = build_pairs(ctx, set, pairs, n_pairs, hp, rows, nq_max, nt_max);
+    if (rc) return rc;
+    if (rows == 0) return SFMB200_OK;
+    return match_core(ctx, set->d_desc, set->words, hp, rows, nq_max, nt_max, ratio, d_out_q, d_out_t, d_out_d, d_pair_start, d_total, ctx->scratch);
+}
+
+int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, double ratio,
+                        int32_t* out_q, int32_t* out_t, float* out_d, int64_t* out_off, int32_t* out_cnt) {
+    if (!ctx || !set || n_pairs < 0 || (n_pairs > 0 && (!pairs || !out_off || !out_cnt))) return SFMB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<PairDesc> hp; int64_t rows; int nq_max, nt_max;
+    int rc = build_pairs(ctx, set, pairs, n_pairs, hp, rows, nq_max, nt_max);
+    if (rc) return rc;
+    for (int p = 0; p < n_pairs; ++p) { out_off[p] = hp[p].out_row; out_cnt[p] = 0; }
+    if (n_pairs) out_off[n_pairs] = rows;
+    if (rows == 0) return SFMB200_OK;
+    if (nt_max < 2) return SFMB200_OK;   // every pair has < 2 train rows: undefined in the reference -> no matches
+    // device outputs (dense) + pair starts + total, behind the kernel workspace
+    DevBuf& outb = ctx->scratch;
+    DevBuf& dense = ctx->scratch2;       // separate from the kernel workspace, which match_core re-carves
+    size_t ob = Carver::pad(4 * rows) * 3 + Carver::pad(4 * (size_t)(n_pairs + 1)) + 512;
+    SFM_CUDA(ctx, dense.reserve(ob));
+    Carver cv(dense.p);
+    int32_t* d_q = cv.take<int32_t>(rows); int32_t* d_t = cv.take<int32_t>(rows); float* d_d = cv.take<float>(rows);
+    int32_t* d_start = cv.take<int32_t>(n_pairs + 1); int64_t* d_total = cv.take<int64_t>(1);
+    rc = match_core(ctx, set->d_desc, set->words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb);
+    if (rc) return rc;
+    // read back: pair starts + total, then only the survivors
+    SFM_CUDA(ctx, ctx->pinned.reserve(Carver::pad(sizeof(int32_t) * (n_pairs + 1)) + 512 + 12 * (size_t)rows));
+    int32_t* h_start = (int32_t*)ctx->pinned.p;
+    int64_t* h_total = (int64_t*)((char*)ctx->pinned.p + Carver::pad(sizeof(int32_t) * (n_pairs + 1)));
+    SFM_CUDA(ctx, cudaMemcpyAsync(h_start, d_start, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(h_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t total = *h_total;
+    char* stage = (char*)ctx->pinned.p + Carver::pad(sizeof(int32_t) * (n_pairs + 1)) + 256;
+    int32_t* hq = (int32_t*)stage; int32_t* ht = hq + total; float* hd = (float*)(ht + total);
+    if (total) {
+        SFM_CUDA(ctx, cudaMemcpyAsync(hq, d_q, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(ht, d_t, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(hd, d_d, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // pairs with zero query rows never wrote their start: fill from the right
+    std::vector<int64_t> start(n_pairs + 1);
+    start[n_pairs] = total;
+    for (int p = n_pairs - 1; p >= 0; --p) start[p] = hp[p].nq > 0 ? h_start[p] : start[p + 1];
+    for (int p = 0; p < n_pairs; ++p) {
+        const int64_t c = start[p + 1] - start[p];
+        out_cnt[p] = (int32_t)c;
+        if (c) {
+            memcpy(out_q + out_off[p], hq + start[p], 4 * c);
+            memcpy(out_t + out_off[p], ht + start[p], 4 * c);
+            memcpy(out_d + out_off[p], hd + start[p], 4 * c);
+        }
+    }
+    return SFMB200_OK;
+}
+
+int sfmb200_match_knn2_ratio(sfmb200_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int desc_bytes,
+                             double ratio, int32_t* out_q, int32_t* out_t, float* out_d, int* out_n) {
+    if (!ctx || !out_n || nq < 0 || nt < 0) return SFMB200_ERR_INVALID;
+    *out_n = 0;
+    if (nq == 0 || nt < 2) return SFMB200_OK;     // nt < 2: undefined behaviour in the reference (:65) -> empty
+    if (!q || !t || !out_q || !out_t || !out_d) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "null buffer");
+    // a two-image descriptor set; the per-call upload is part of the drop-in cost (the reference passes cv::Mat by ref)
+    std::vector<uint8_t> both((size_t)(nq + nt) * desc_bytes);
+    memcpy(both.data(), q, (size_t)nq * desc_bytes);
+    memcpy(both.data() + (size_t)nq * desc_bytes, t, (size_t)nt * desc_bytes);
+    const int32_t off[3] = {0, nq, nq + nt};
+    sfmb200_descset* set = nullptr;
+    int rc = sfmb200_descset_create(ctx, both.data(), off, 2, desc_bytes, &set);
+    if (rc) return rc;
+    const int32_t pair[2] = {0, 1};
+    int64_t ooff[2]; int32_t cnt[1];
+    rc = sfmb200_match_pairs(ctx, set, pair, 1, ratio, out_q, out_t, out_d, ooff, cnt);
+    sfmb200_descset_destroy(set);
+    if (rc) return rc;
+    *out_n = cnt[0];
+    return SFMB200_OK;
+}
+
+int sfmb200_match_knn2_ratio_l2(sfmb200_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                                double ratio, int32_t* out_q, int32_t* out_t, float* out_d, int* out_n) {
+    if (!ctx || !out_n || nq < 0 || nt < 0 || dim <= 0) return SFMB200_ERR_INVALID;
+    *out_n = 0;
+    if (nq == 0 || nt < 2) return SFMB200_OK;
+    if (!q || !t || !out_q || !out_t || !out_d) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "null buffer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t rows = nq;
+    int splits = 1;
+    while ((int64_t)nq * splits < 8LL * ctx->sm_count * 8 && splits < 32 && nt / (splits * 2) >= 64) splits *= 2;
+    const int nblk = (int)ceil_div64(rows, SCAN_THREADS);
+    size_t bytes = Carver::pad(4 * (size_t)nq * dim) + Carver::pad(4 * (size_t)nt * dim) + Carver::pad(sizeof(PairDesc)) +
+                   Carver::pad(16 * rows * splits) + Carver::pad(4 * rows) * 6 + Carver::pad(rows) + Carver::pad(4 * (size_t)nblk) + 4096;
+    SFM_CUDA(ctx, ctx->scratch.reserve(bytes));
+    Carver cv(ctx->scratch.p);
+    float* d_qf = cv.take<float>((size_t)nq * dim); float* d_tf = cv.take<float>((size_t)nt * dim);
+    PairDesc* d_pairs = cv.take<PairDesc>(1); float4* d_partial = cv.take<float4>((size_t)rows * splits);
+    int32_t* d_best_t = cv.take<int32_t>(rows); float* d_best_d = cv.take<float>(rows); int32_t* d_rank = cv.take<int32_t>(rows);
+    int32_t* d_q = cv.take<int32_t>(rows); int32_t* d_t = cv.take<int32_t>(rows); float* d_d = cv.take<float>(rows);
+    uint8_t* d_flag = cv.take<uint8_t>(rows); int32_t* d_bsum = cv.take<int32_t>(nblk);
+    int32_t* d_start = cv.take<int32_t>(2); int64_t* d_total = cv.take<int64_t>(1);
+    PairDesc hp = {0, nq, 0, nt, 0};
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_qf, q, 4 * (size_t)nq * dim, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_tf, t, 4 * (size_t)nt * dim, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_pairs, &hp, sizeof hp, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t warps = (int64_t)nq * splits;
+    knn2_l2_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, ctx->stream>>>(d_qf, nq, d_tf, nt, dim, splits, d_partial);
+    SFM_LAUNCH_CHECK(ctx);
+    merge_flag_scan_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>((const int4*)d_partial, splits, rows, ratio, 1, d_best_t, d_best_d, d_rank, d_flag, d_bsum);
+    SFM_LAUNCH_CHECK(ctx);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_bsum, nblk, d_total);
+    SFM_LAUNCH_CHECK(ctx);
+    scatter_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_pairs, 1, rows, d_best_t, d_best_d, d_rank, d_flag, d_bsum, d_q, d_t, d_d, d_start);
+    SFM_LAUNCH_CHECK(ctx);
+    SFM_CUDA(ctx, ctx->pinned.reserve(64 + 12 * (size_t)rows));
+    int64_t* h_total = (int64_t*)ctx->pinned.p;
+    SFM_CUDA(ctx, cudaMemcpyAsync(h_total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t total = *h_total;
+    if (total) {
+        SFM_CUDA(ctx, cudaMemcpyAsync(out_q, d_q, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(out_t, d_t, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(out_d, d_d, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out_n = (int)total;
+    return SFMB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+"""GPU parity: sfmb200_match_* (CUDA, through the C ABI) vs the oracle restatement of matchFeatures
+(SfM2DFeatureUtilities.cpp:53-71) and the cv2 golden vectors.  Integer path -> bit-exact indices AND distances."""
+import numpy as np
+import pytest
+
+from sfm_toy_library_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _same(a, b):
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d", "e"])
+def test_golden_cv2(ctx, golden, case):
+    g = golden("match_cv2.npz")
+    _same(ctx.match_knn2_ratio(g[f"{case}_q"], g[f"{case}_t"]), (g[f"{case}_mq"], g[f"{case}_mt"], g[f"{case}_md"]))
+
+
+def test_ratio_constant(ctx, golden):
+    g = golden("match_cv2.npz")
+    assert len(ctx.match_knn2_ratio(g["c_q"], g["c_t"])[0]) == 1            # (double)0.8f keeps d0=4, d1=5
+    assert len(ctx.match_knn2_ratio(g["c_q"], g["c_t"], ratio=0.8)[0]) == 0
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 2), (255, 257), (256, 128), (1000, 3), (5000, 5000), (4999, 5003), (37, 9000)])
+def test_vs_oracle_ragged_sizes(ctx, oracle, nq, nt):
+    t = synth.make_descriptors(nt % 97, nt); q = synth.make_descriptors(nq % 89 + 100, nq, prev=t)
+    _same(ctx.match_knn2_ratio(q, t), oracle.match_hamming(q, t))
+
+
+def test_edge_cases(ctx):
+    d = synth.make_descriptors(0, 10)
+    assert len(ctx.match_knn2_ratio(d, d[:1])[0]) == 0                      # nt < 2 (UB in the reference) -> empty
+    assert len(ctx.match_knn2_ratio(d[:0], d)[0]) == 0                      # empty query
+    q, t, dist = ctx.match_knn2_ratio(d, d)                                 # d0 = 0: kept iff 0 < 0.8f*d1, i.e. d1 > 0
+    assert np.all(dist == 0) and np.array_equal(q, t)
+
+
+def test_all_ties_go_to_lowest_train_index(ctx, oracle):
+    t = np.repeat(synth.make_descriptors(5, 8), 40, axis=0)                 # every row 40 times
+    q = synth.make_descriptors(6, 50)
+    q[:8] = t[::40]
+    _same(ctx.match_knn2_ratio(q, t, ratio=2.0), oracle.match_hamming(q, t, ratio=2.0))
+
+
+def test_64_byte_descriptors(ctx, oracle):
+    a = synth.make_descriptors(9, 700, nbytes=64); b = synth.make_descriptors(10, 650, nbytes=64, prev=a)
+    _same(ctx.match_knn2_ratio(b, a), oracle.match_hamming(b, a))
+
+
+def test_all_pairs_batched_equals_pairwise(ctx, oracle):
+    descs = synth.make_descriptor_set(5, n=1200)
+    descs[3] = descs[3][:700]                                                # ragged image sizes
+    pairs = [(i, j) for i in range(5) for j in range(i + 1, 5)]              # SfM::createFeatureMatchMatrix (SfM.cpp:166-172)
+    ds = ctx.descriptor_set(descs)
+    res = ds.match_pairs(pairs)
+    for (i, j), r in zip(pairs, res):
+        _same(r, oracle.match_hamming(descs[i], descs[j]))
+        assert len(r[0]) > 50
+    ds.close()
+
+
+def test_l2_sift_like(ctx, oracle, golden):
+    g = golden("match_cv2.npz")
+    _same(ctx.match_knn2_ratio_l2(g["l2_q"], g["l2_t"]), (g["l2_mq"], g["l2_mt"], g["l2_md"]))
+    a = synth.make_sift_like(3, 900); b = synth.make_sift_like(4, 800, prev=a)
+    _same(ctx.match_knn2_ratio_l2(b, a), oracle.match_l2(b, a))
+
+
+def test_config4_properties_full_size(ctx):
+    """BASELINE.json config 4 sizes (5000 x 5000 per pair): size-independent properties instead of the O(n^2) oracle:
+    planted near-duplicates are recovered, output is sorted by queryIdx, distances are integers in [0, 256]."""
+    a = synth.make_descriptors(20, 5000); b = synth.make_descriptors(21, 5000, prev=a)
+    q, t, d = ctx.match_knn2_ratio(b, a)
+    assert np.all(np.diff(q) > 0) and np.all(d == np.round(d)) and d.min() >= 0 and d.max() <= 256
+    x = np.unpackbits(b[q] ^ a[t], axis=1).sum(1)
+    np.testing.assert_array_equal(x.astype(np.float32), d)                   # reported distance is the true Hamming distance
+    assert 0.15 * 5000 < len(q) < 0.3 * 5000
