@@ -120,6 +120,7 @@ typedef struct {
     int max_num_consecutive_invalid_steps;  /* 5     */
     int verbose;                            /* 1: one line per LM iteration on stdout (minimizer_progress_to_stdout, :173) */
     int profile;                            /* 1: time the dominant kernel with CUDA events (summary.schur_ms_*) */
+    int l2_flush_mb;                        /* > 0: write a scratch buffer of this many MB between LM iterations (benchmark hygiene) */
 } sfmb200_ba_options;
 
 enum { SFMB200_BA_CONVERGENCE = 0, SFMB200_BA_NO_CONVERGENCE = 1, SFMB200_BA_FAILURE = 2 };

@@ -310,31 +310,54 @@ static int eval_jacobian(const ba_problem* P, const double* x, int mode, int nth
     return !(bad || !isfinite(sum));
 }
 
-/* gradient g = J^T r (unscaled J); layout like x */
+/* gradient g = J^T r (unscaled J); layout like x.  Parallel over points (observations of a point are contiguous);
+ * camera/focal entries go through per-thread accumulators. */
 static void eval_gradient(const ba_problem* P, const double* res, const double* Jc, const double* Jp, const double* Jf,
-                          double* g) {
-    const int n = 6 * P->nc + 3 * P->np + 1;
+                          double* g, int nthreads) {
+    const int n = 6 * P->nc + 3 * P->np + 1, ncf = 6 * P->nc + 1;
     memset(g, 0, sizeof(double) * n);
-    double* gc = g; double* gp = g + 6 * P->nc; double* gf = g + 6 * P->nc + 3 * P->np;
-    for (int o = 0; o < P->nobs; ++o) {
-        const double r0 = res[2 * o], r1 = res[2 * o + 1];
-        double* c = gc + 6 * P->obs_cam[o]; double* p = gp + 3 * P->obs_pt[o];
-        for (int k = 0; k < 6; ++k) c[k] += Jc[12 * o + k] * r0 + Jc[12 * o + 6 + k] * r1;
-        for (int k = 0; k < 3; ++k) p[k] += Jp[6 * o + k] * r0 + Jp[6 * o + 3 + k] * r1;
-        gf[0] += Jf[2 * o] * r0 + Jf[2 * o + 1] * r1;
+    double* gp = g + 6 * P->nc;
+    (void)nthreads;
+#pragma omp parallel num_threads(nthreads)
+    {
+        double* loc = (double*)calloc(ncf, sizeof(double));
+#pragma omp for schedule(static)
+        for (int p = 0; p < P->np; ++p) {
+            for (int o = P->pt_off[p]; o < P->pt_off[p + 1]; ++o) {
+                const double r0 = res[2 * o], r1 = res[2 * o + 1];
+                double* c = loc + 6 * P->obs_cam[o];
+                for (int k = 0; k < 6; ++k) c[k] += Jc[12 * o + k] * r0 + Jc[12 * o + 6 + k] * r1;
+                for (int k = 0; k < 3; ++k) gp[3 * p + k] += Jp[6 * o + k] * r0 + Jp[6 * o + 3 + k] * r1;
+                loc[ncf - 1] += Jf[2 * o] * r0 + Jf[2 * o + 1] * r1;
+            }
+        }
+#pragma omp critical
+        { for (int i = 0; i < 6 * P->nc; ++i) g[i] += loc[i]; g[n - 1] += loc[ncf - 1]; }
+        free(loc);
     }
 }
 
 /* squared column norms of the (already scaled) Jacobian; layout like x */
-static void squared_column_norms(const ba_problem* P, const double* Jc, const double* Jp, const double* Jf, double* d) {
-    const int n = 6 * P->nc + 3 * P->np + 1;
+static void squared_column_norms(const ba_problem* P, const double* Jc, const double* Jp, const double* Jf, double* d, int nthreads) {
+    const int n = 6 * P->nc + 3 * P->np + 1, ncf = 6 * P->nc + 1;
     memset(d, 0, sizeof(double) * n);
-    double* dc = d; double* dp = d + 6 * P->nc; double* df = d + 6 * P->nc + 3 * P->np;
-    for (int o = 0; o < P->nobs; ++o) {
-        double* c = dc + 6 * P->obs_cam[o]; double* p = dp + 3 * P->obs_pt[o];
-        for (int k = 0; k < 6; ++k) c[k] += Jc[12 * o + k] * Jc[12 * o + k] + Jc[12 * o + 6 + k] * Jc[12 * o + 6 + k];
-        for (int k = 0; k < 3; ++k) p[k] += Jp[6 * o + k] * Jp[6 * o + k] + Jp[6 * o + 3 + k] * Jp[6 * o + 3 + k];
-        df[0] += Jf[2 * o] * Jf[2 * o] + Jf[2 * o + 1] * Jf[2 * o + 1];
+    double* dp = d + 6 * P->nc;
+    (void)nthreads;
+#pragma omp parallel num_threads(nthreads)
+    {
+        double* loc = (double*)calloc(ncf, sizeof(double));
+#pragma omp for schedule(static)
+        for (int p = 0; p < P->np; ++p) {
+            for (int o = P->pt_off[p]; o < P->pt_off[p + 1]; ++o) {
+                double* c = loc + 6 * P->obs_cam[o];
+                for (int k = 0; k < 6; ++k) c[k] += Jc[12 * o + k] * Jc[12 * o + k] + Jc[12 * o + 6 + k] * Jc[12 * o + 6 + k];
+                for (int k = 0; k < 3; ++k) dp[3 * p + k] += Jp[6 * o + k] * Jp[6 * o + k] + Jp[6 * o + 3 + k] * Jp[6 * o + 3 + k];
+                loc[ncf - 1] += Jf[2 * o] * Jf[2 * o] + Jf[2 * o + 1] * Jf[2 * o + 1];
+            }
+        }
+#pragma omp critical
+        { for (int i = 0; i < 6 * P->nc; ++i) d[i] += loc[i]; d[n - 1] += loc[ncf - 1]; }
+        free(loc);
     }
 }
 
@@ -499,12 +522,12 @@ int sfm_oracle_ba_reduced_system(int nc, int np, int nobs, const double* cams, c
     double* Uinv = (double*)malloc(sizeof(double) * 6 * np); double* gpt = (double*)malloc(sizeof(double) * 3 * np);
     double cost;
     int ok = eval_jacobian(&P, x, mode, 1, res, Jc, Jp, Jf, &cost);
-    if (grad_out) eval_gradient(&P, res, Jc, Jp, Jf, grad_out);
+    if (grad_out) eval_gradient(&P, res, Jc, Jp, Jf, grad_out, 1);
     if (scale_in) memcpy(scale, scale_in, sizeof(double) * n);
-    else if (jacobi_scaling) { squared_column_norms(&P, Jc, Jp, Jf, scale); for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + sqrt(scale[i])); }
+    else if (jacobi_scaling) { squared_column_norms(&P, Jc, Jp, Jf, scale, 1); for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + sqrt(scale[i])); }
     else for (int i = 0; i < n; ++i) scale[i] = 1.0;
     scale_columns(&P, scale, Jc, Jp, Jf, 1);
-    squared_column_norms(&P, Jc, Jp, Jf, D);
+    squared_column_norms(&P, Jc, Jp, Jf, D, 1);
     for (int i = 0; i < n; ++i) { double d = D[i]; d = d < min_diag ? min_diag : d; d = d > max_diag ? max_diag : d; D[i] = sqrt(d / radius); }
     ok = build_reduced_system(&P, res, Jc, Jp, Jf, D, S, rhs, Uinv, gpt, 1) && ok;
     if (scale_out) memcpy(scale_out, scale, sizeof(double) * n);
@@ -568,7 +591,7 @@ int sfm_oracle_ba_solve(const sfm_oracle_ba_options* opt, int nc, int np, int no
         const double t0_ = now_s();                                                             \
         jac_ok = eval_jacobian(&P, x, opt->jacobian_mode, nthreads, res, Jc, Jp, Jf, &x_cost);  \
         sum->num_jacobian_evals++; sum->num_residual_evals++;                                   \
-        eval_gradient(&P, res, Jc, Jp, Jf, g);                                                  \
+        eval_gradient(&P, res, Jc, Jp, Jf, g, nthreads);                                        \
         gmax = 0; for (int i_ = 0; i_ < n; ++i_) { const double a_ = fabs(g[i_]); if (a_ > gmax) gmax = a_; } \
         sum->jacobian_time_s += now_s() - t0_;                                                  \
     } while (0)
@@ -577,7 +600,7 @@ int sfm_oracle_ba_solve(const sfm_oracle_ba_options* opt, int nc, int np, int no
     EVAL_JAC();
     if (!jac_ok) { sum->termination_type = 2; snprintf(sum->message, sizeof sum->message, "Residual and Jacobian evaluation failed."); goto done; }
     if (opt->jacobi_scaling) {
-        squared_column_norms(&P, Jc, Jp, Jf, scale);
+        squared_column_norms(&P, Jc, Jp, Jf, scale, nthreads);
         for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + sqrt(scale[i]));
     } else for (int i = 0; i < n; ++i) scale[i] = 1.0;
     scale_columns(&P, scale, Jc, Jp, Jf, nthreads);
@@ -609,7 +632,7 @@ int sfm_oracle_ba_solve(const sfm_oracle_ba_options* opt, int nc, int np, int no
         /* LevenbergMarquardtStrategy::ComputeStep */
         const double t0 = now_s();
         if (!reuse_diagonal) {
-            squared_column_norms(&P, Jc, Jp, Jf, diag);
+            squared_column_norms(&P, Jc, Jp, Jf, diag, nthreads);
             for (int i = 0; i < n; ++i) { double d = diag[i]; d = d < opt->min_lm_diagonal ? opt->min_lm_diagonal : d; d = d > opt->max_lm_diagonal ? opt->max_lm_diagonal : d; diag[i] = d; }
         }
         for (int i = 0; i < n; ++i) D[i] = sqrt(diag[i] / radius);
@@ -620,6 +643,7 @@ int sfm_oracle_ba_solve(const sfm_oracle_ba_options* opt, int nc, int np, int no
             const double* yc = rhs; const double yf = rhs[6 * nc];
             for (int i = 0; i < 6 * nc; ++i) step[i] = -yc[i];
             step[n - 1] = -yf;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
             for (int p = 0; p < np; ++p) {
                 double t[3] = {gpt[3 * p], gpt[3 * p + 1], gpt[3 * p + 2]};
                 for (int o = pt_off[p]; o < pt_off[p + 1]; ++o) {

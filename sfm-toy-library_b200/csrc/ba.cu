@@ -742,7 +742,7 @@ void sfmb200_ba_default_options(sfmb200_ba_options* o) {
     o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
     o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
     o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
-    o->jacobi_scaling = 1; o->max_num_consecutive_invalid_steps = 5; o->verbose = 0; o->profile = 0;
+    o->jacobi_scaling = 1; o->max_num_consecutive_invalid_steps = 5; o->verbose = 0; o->profile = 0; o->l2_flush_mb = 0;
 }
 
 int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const double* cams6, const double* pts3, double focal,
@@ -909,6 +909,17 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
     double* h = P->h_scal;
 
     for (;;) {
+        // FinalizeIterationAndCheckIfMinimizerCanContinue of the previous iteration, Ceres' order: time, iterations,
+        // gradient, radius.  The first two need no device data, so they are tested before any kernel is launched:
+        // max_num_iterations = K performs exactly K passes / solves / candidate evaluations.
+        if (iter > 0) {
+            if (opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { snprintf(sum->message, sizeof sum->message, "Maximum solver time reached."); break; }
+            if (iter >= opt.max_num_iterations) { snprintf(sum->message, sizeof sum->message, "Maximum number of iterations reached."); break; }
+        }
+        if (opt.l2_flush_mb > 0) {      // benchmark hygiene: evict the working set from L2 between iterations
+            SFM_CUDA(ctx, ctx->scratch2.reserve((size_t)opt.l2_flush_mb << 20));
+            SFM_CUDA(ctx, cudaMemsetAsync(ctx->scratch2.p, 0, (size_t)opt.l2_flush_mb << 20, ctx->stream));
+        }
         // ---- one LM iteration on the device: pass at x, dense solve, candidate, evaluation -------------------
         rc = schur_pass(P, &opt, radius, opt.profile != 0); if (rc) return rc;
         sum->num_jacobian_passes++;
@@ -921,30 +932,28 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
         if (P->np > 0 && P->nobs > 0) { BAView v = make_view(P, &opt); rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }
         rc = sfmb200_allreduce_sum_f64(ctx, P->post, 8); if (rc) return rc;
         rc = sfmb200_allreduce_max_f64(ctx, P->locals + 4, 1); if (rc) return rc;
-        // read back: sums[8] | post[8] locals[8] gmax fail[2]
+        // read back: sums[8] | post[8] locals[8]
         SFM_CUDA(ctx, cudaMemcpyAsync(h, P->sums, 64, cudaMemcpyDeviceToHost, ctx->stream));
-        SFM_CUDA(ctx, cudaMemcpyAsync(h + 8, P->post, 8 * 20, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(h + 8, P->post, 8 * 16, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (opt.profile) { float ms = 0; if (cudaEventElapsedTime(&ms, P->ev0, P->ev1) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; } }
         const double cost_x = 0.5 * h[0], xn2_pts = h[1];
         const double cand_cost_raw = 0.5 * h[8], model_acc = h[9], dn2_pts = h[10], cn2_pts = h[11];
-        const double dn2_cf = h[16], xn2_cf = h[17], cn2_cf = h[18], gmax_cf = h[19];
-        const double gmax_pt = h[20];                                  // max over ranks
         const double fails[2] = {h[12], h[13]};                        // summed over ranks
+        const double dn2_cf = h[16], xn2_cf = h[17], cn2_cf = h[18], gmax_cf = h[19], gmax_pt = h[20];   // gmax_pt: max over ranks
         if (new_point) {
             x_cost = cost_x; x_norm = std::sqrt(xn2_pts + xn2_cf); gmax = std::max(gmax_pt, gmax_cf);
+            new_point = false;
             if (iter == 0) {
                 sum->initial_cost = x_cost;
                 if (!std::isfinite(x_cost)) { sum->termination_type = SFMB200_BA_FAILURE; snprintf(sum->message, sizeof sum->message, "Residual and Jacobian evaluation failed."); break; }
                 if (opt.verbose) printf("iter %3d cost %.9e |g|max %.3e radius %.3e\n", 0, x_cost, gmax, radius);
+                if (gmax <= opt.gradient_tolerance) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break; }
+                if (opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { snprintf(sum->message, sizeof sum->message, "Maximum solver time reached."); break; }
+                if (iter >= opt.max_num_iterations) { snprintf(sum->message, sizeof sum->message, "Maximum number of iterations reached."); break; }
             }
-            if (iter == 0 && gmax <= opt.gradient_tolerance) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break; }
-            new_point = false;
         }
-        // FinalizeIterationAndCheckIfMinimizerCanContinue of the previous iteration (Ceres' order: time, iterations, gradient, radius)
-        if (opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { snprintf(sum->message, sizeof sum->message, "Maximum solver time reached."); break; }
-        if (iter >= opt.max_num_iterations) { snprintf(sum->message, sizeof sum->message, "Maximum number of iterations reached."); break; }
-        if (iter > 0 && gmax <= opt.gradient_tolerance) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break; }
+        if (gmax <= opt.gradient_tolerance) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break; }
         if (radius <= opt.min_trust_region_radius) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Minimum trust region radius reached."); break; }
         ++iter;
 
