@@ -426,19 +426,27 @@ static void cholesky_solve(const double* L, int n, double* b) {
  * Returns 0 when a point block is not SPD.
  */
 static int build_reduced_system(const ba_problem* P, const double* res, const double* Jc, const double* Jp, const double* Jf,
-                                const double* D, double* S, double* rhs, double* Uinv, double* gpt, int nthreads) {
+                                const double* D, double* S, double* rhs, double* Uinv, double* gpt, int nthreads,
+                                double* pool /* nthreads * (n*n + n) doubles of per-thread accumulators, or NULL */) {
     const int nc = P->nc, np = P->np, n = 6 * nc + 1, fidx = 6 * nc;
     const double* Dp = D + 6 * nc;
     int ok = 1;
     memset(S, 0, sizeof(double) * (size_t)n * n);
     memset(rhs, 0, sizeof(double) * n);
     (void)nthreads;
+    const size_t stride = (size_t)n * n + n;
+    int used_threads = 1;
 #pragma omp parallel num_threads(nthreads)
     {
         double* Sl = S; double* rl = rhs; int own = 0;
 #ifdef _OPENMP
-        if (omp_get_num_threads() > 1) {
-            Sl = (double*)calloc((size_t)n * n, sizeof(double)); rl = (double*)calloc(n, sizeof(double)); own = 1;
+        if (omp_get_num_threads() > 1 && pool) {
+            Sl = pool + stride * omp_get_thread_num(); rl = Sl + (size_t)n * n; own = 1;
+            memset(Sl, 0, sizeof(double) * stride);
+#pragma omp single
+            used_threads = omp_get_num_threads();
+        } else if (omp_get_num_threads() > 1) {
+            Sl = (double*)calloc((size_t)n * n, sizeof(double)); rl = (double*)calloc(n, sizeof(double)); own = 2;
         }
 #endif
         double (*W)[21] = NULL; int wcap = 0;
@@ -493,10 +501,18 @@ static int build_reduced_system(const ba_problem* P, const double* res, const do
             }
         }
         free(W);
-        if (own) {
+        if (own == 2) {
 #pragma omp critical
             { for (size_t i = 0; i < (size_t)n * n; ++i) S[i] += Sl[i]; for (int i = 0; i < n; ++i) rhs[i] += rl[i]; }
             free(Sl); free(rl);
+        }
+    }
+    if (pool && used_threads > 1) {      /* parallel merge of the per-thread accumulators */
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+        for (long i = 0; i < (long)stride; ++i) {
+            double a = 0;
+            for (int t = 0; t < used_threads; ++t) a += pool[stride * t + i];
+            if (i < (long)n * n) S[i] += a; else rhs[i - (long)n * n] += a;
         }
     }
     for (int i = 0; i < n; ++i) { const double d = i < 6 * nc ? D[i] : D[6 * nc + 3 * np]; S[(size_t)i * n + i] += d * d; }
@@ -529,7 +545,7 @@ int sfm_oracle_ba_reduced_system(int nc, int np, int nobs, const double* cams, c
     scale_columns(&P, scale, Jc, Jp, Jf, 1);
     squared_column_norms(&P, Jc, Jp, Jf, D, 1);
     for (int i = 0; i < n; ++i) { double d = D[i]; d = d < min_diag ? min_diag : d; d = d > max_diag ? max_diag : d; D[i] = sqrt(d / radius); }
-    ok = build_reduced_system(&P, res, Jc, Jp, Jf, D, S, rhs, Uinv, gpt, 1) && ok;
+    ok = build_reduced_system(&P, res, Jc, Jp, Jf, D, S, rhs, Uinv, gpt, 1, NULL) && ok;
     if (scale_out) memcpy(scale_out, scale, sizeof(double) * n);
     if (cost_out) *cost_out = cost;
     free(P.obs_pt); free(x); free(res); free(Jc); free(Jp); free(Jf); free(scale); free(D); free(Uinv); free(gpt);
@@ -579,6 +595,7 @@ int sfm_oracle_ba_solve(const sfm_oracle_ba_options* opt, int nc, int np, int no
     double* step = (double*)malloc(sizeof(double) * n);
     double* S = (double*)malloc(sizeof(double) * (size_t)nr * nr); double* rhs = (double*)malloc(sizeof(double) * nr);
     double* Uinv = (double*)malloc(sizeof(double) * 6 * (size_t)np); double* gpt = (double*)malloc(sizeof(double) * 3 * (size_t)np);
+    double* pool = nthreads > 1 ? (double*)malloc(sizeof(double) * (size_t)nthreads * ((size_t)nr * nr + nr)) : NULL;
     memcpy(x, cams, sizeof(double) * 6 * nc); memcpy(x + 6 * nc, pts, sizeof(double) * 3 * np); x[n - 1] = *focal;
 
     double radius = opt->initial_trust_region_radius, decrease_factor = 2.0;
@@ -636,7 +653,7 @@ int sfm_oracle_ba_solve(const sfm_oracle_ba_options* opt, int nc, int np, int no
             for (int i = 0; i < n; ++i) { double d = diag[i]; d = d < opt->min_lm_diagonal ? opt->min_lm_diagonal : d; d = d > opt->max_lm_diagonal ? opt->max_lm_diagonal : d; diag[i] = d; }
         }
         for (int i = 0; i < n; ++i) D[i] = sqrt(diag[i] / radius);
-        int lin_ok = build_reduced_system(&P, res, Jc, Jp, Jf, D, S, rhs, Uinv, gpt, nthreads);
+        int lin_ok = build_reduced_system(&P, res, Jc, Jp, Jf, D, S, rhs, Uinv, gpt, nthreads, pool);
         if (lin_ok) lin_ok = dense_cholesky(S, nr, nthreads);
         if (lin_ok) {
             cholesky_solve(S, nr, rhs);               /* rhs := y_f */
@@ -740,7 +757,7 @@ done:
     sum->num_iterations = iter; sum->final_cost = x_cost;
     memcpy(cams, x, sizeof(double) * 6 * nc); memcpy(pts, x + 6 * nc, sizeof(double) * 3 * np); *focal = x[n - 1];
     free(P.obs_pt); free(x); free(xc); free(res); free(Jc); free(Jp); free(Jf); free(scale); free(diag); free(D); free(g);
-    free(step); free(S); free(rhs); free(Uinv); free(gpt);
+    free(step); free(S); free(rhs); free(Uinv); free(gpt); free(pool);
     sum->total_time_s = now_s() - t_start;
     return sum->termination_type;
 #undef EVAL_JAC

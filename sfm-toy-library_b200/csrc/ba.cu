@@ -386,42 +386,55 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
     A[(size_t)r * npad + c] = val;
 }
 
-// Panel step k: every CTA (block row i >= k) factors the 32x32 diagonal tile redundantly in shared memory; CTA i == k
-// writes it back, the others solve their tile against it: A[i][k] <- A[i][k] L_kk^-T.  Pivots with global index >= n
-// are forced to 1 (augmented / padding rows).  blockDim = (32, 32).
-__global__ void __launch_bounds__(1024) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int* __restrict__ fail) {
-    __shared__ double L[NB][NB + 1], B[NB][NB + 1];
-    const int r = threadIdx.y, c = threadIdx.x, i = k + blockIdx.x;
-    L[r][c] = A[(size_t)(k * NB + r) * npad + k * NB + c];
-    if (i != k) B[r][c] = A[(size_t)(i * NB + r) * npad + k * NB + c];
-    __syncthreads();
+// Panel step k, warp-level: one WARP per tile row i >= k, lane r holds row r of a 32x32 tile in registers.
+// Every warp factors the diagonal tile redundantly (496 shuffle-broadcasts + 496 DFMA, no block barrier, no shared
+// memory); warp i == k writes it back, the others solve their own tile against it in registers:
+// A[i][k] <- A[i][k] L_kk^-T.  Pivots with global index >= n are forced to 1 (augmented rhs row / padding rows).
+__global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk, int* __restrict__ fail) {
+    const int lane = threadIdx.x & 31;
+    const int i = k + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= nbk) return;
+    double a[NB];
+    {
+        const double* src = A + (size_t)(k * NB + lane) * npad + k * NB;
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); a[c] = v.x; a[c + 1] = v.y; }
+    }
+    bool bad = false;
+#pragma unroll
     for (int j = 0; j < NB; ++j) {
         const int gj = k * NB + j;
-        if (r == j && c == j) {
-            double d = L[j][j];
-            if (gj >= n) d = 1.0;
-            else if (!(d > 0.0) || !isfinite(d)) { if (i == k) atomicAdd(fail, 1); d = 1.0; }
-            else d = sqrt(d);
-            L[j][j] = d;
-        }
-        __syncthreads();
-        if (c == j && r > j) L[r][j] = (gj >= n) ? 0.0 : L[r][j] / L[j][j];
-        __syncthreads();
-        if (c > j && r >= c) L[r][c] -= L[r][j] * L[c][j];
-        __syncthreads();
+        double d = __shfl_sync(0xffffffffu, a[j], j);
+        double inv;
+        if (gj >= n) { d = 1.0; inv = 0.0; }                       // padding pivot: L_jj = 1, column below = 0
+        else if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; inv = 1.0; }
+        else { d = sqrt(d); inv = 1.0 / d; }
+        const double lrj = lane == j ? d : a[j] * inv;             // rows above the diagonal hold garbage: never read
+        a[j] = lrj;
+#pragma unroll
+        for (int c = j + 1; c < NB; ++c) { const double lcj = __shfl_sync(0xffffffffu, lrj, c); a[c] = fma(-lrj, lcj, a[c]); }
     }
     if (i == k) {
-        if (c <= r) A[(size_t)(k * NB + r) * npad + k * NB + c] = L[r][c];
+        if (bad && lane == 0) atomicAdd(fail, 1);
+        double* dst = A + (size_t)(k * NB + lane) * npad + k * NB;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (c <= lane) dst[c] = a[c];
         return;
     }
-    // X L^T = B  ->  column by column
+    // X L^T = B, row `lane` of B in registers; L[c][j] = register j of lane c
+    double x[NB];
+    double* tile = A + (size_t)(i * NB + lane) * npad + k * NB;
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(tile + c); x[c] = v.x; x[c + 1] = v.y; }
+#pragma unroll
     for (int j = 0; j < NB; ++j) {
-        if (c == j) B[r][j] = B[r][j] / L[j][j];
-        __syncthreads();
-        if (c > j) B[r][c] -= B[r][j] * L[c][j];
-        __syncthreads();
+        const double ljj = __shfl_sync(0xffffffffu, a[j], j);
+        x[j] = x[j] / ljj;
+#pragma unroll
+        for (int c = j + 1; c < NB; ++c) { const double lcj = __shfl_sync(0xffffffffu, a[j], c); x[c] = fma(-x[j], lcj, x[c]); }
     }
-    A[(size_t)(i * NB + r) * npad + k * NB + c] = B[r][c];
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(tile + c) = make_double2(x[c], x[c + 1]);
 }
 
 // Trailing update step k: tile (i, j), k < j <= i:  A[i][j] -= A[i][k] A[j][k]^T.  blockDim = (32, 32), grid = T(T+1)/2.
@@ -442,38 +455,53 @@ __global__ void __launch_bounds__(1024) chol_update_kernel(double* __restrict__ 
     if (i != j || c <= r) A[(size_t)(i * NB + r) * npad + j * NB + c] -= s;
 }
 
-// Back substitution L^T x = y with y = row n of the factored matrix.  Single CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) chol_backsolve_kernel(const double* __restrict__ A, int npad, int n, double* __restrict__ x) {
+// Back substitution L^T x = y with y = row n of the factored matrix.  Single CTA of 640 threads (warp 0 + 608 workers).
+// Per 32-block (descending): warp 0 holds the diagonal tile COLUMN-wise in registers (lane c = column c) and solves it with
+// one shuffle-broadcast per unknown, while all other threads already have the loads of their part of the block row in
+// flight; then  y[c] -= sum_m L[kb*32+m][c] x_m  for the columns to the left.
+__global__ void __launch_bounds__(640) chol_backsolve_kernel(const double* __restrict__ A, int npad, int n, double* __restrict__ x) {
     extern __shared__ double y[];                 // [npad]
-    __shared__ double T[NB][NB + 1];
-    const int tid = threadIdx.x, nbk = npad / NB;
+    const int tid = threadIdx.x, lane = tid & 31, nworkers = blockDim.x - 32;
     for (int i = tid; i < npad; i += blockDim.x) y[i] = i < n ? A[(size_t)n * npad + i] : 0.0;
     __syncthreads();
     for (int kb = (n - 1) / NB; kb >= 0; --kb) {
-        for (int e = tid; e < NB * NB; e += blockDim.x) { const int r = e / NB, c = e % NB; T[r][c] = A[(size_t)(kb * NB + r) * npad + kb * NB + c]; }
-        __syncthreads();
-        if (tid < 32) {     // solve the 32x32 upper system T^T x = y_kb with one warp
-            double yi = y[kb * NB + tid];
-            for (int j = NB - 1; j >= 0; --j) {
-                const int gj = kb * NB + j;
-                double xj = 0.0;
-                if (tid == j) { xj = gj < n ? yi / T[j][j] : 0.0; yi = xj; }
+        const int ncols = kb * NB;                // columns to the left of the diagonal tile
+        const int c0 = tid - 32;
+        const bool solver = tid < 32, has = !solver && c0 < ncols;
+        // one register array, two roles: warp 0 holds the diagonal tile column-wise (reg[r] = L[r][lane]); worker c0 holds
+        // its column of the block row (reg[m] = L[kb*32+m][c0]) -- these loads are in flight while warp 0 solves.
+        double reg[NB];
+        const double* src = A + (size_t)(kb * NB) * npad + (solver ? kb * NB + lane : (has ? c0 : 0));
+#pragma unroll
+        for (int m = 0; m < NB; ++m) reg[m] = src[(size_t)m * npad];
+        if (solver) {
+            double yc = y[kb * NB + lane];
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj) {
+                const int j = NB - 1 - jj, gj = kb * NB + j;
+                double xj = (lane == j) ? (gj < n ? yc / reg[j] : 0.0) : 0.0;
                 xj = __shfl_sync(0xffffffffu, xj, j);
-                if (tid < j) yi -= T[j][tid] * xj;
+                if (lane == j) yc = xj; else if (lane < j) yc = fma(-reg[j], xj, yc);
             }
-            y[kb * NB + tid] = yi;
+            y[kb * NB + lane] = yc;
         }
         __syncthreads();
-        // y[0 .. kb*NB) -= L[kb block rows][cols]^T x_kb
-        for (int c = tid; c < kb * NB; c += blockDim.x) {
+        if (has) {
             double s = 0;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) s = fma(reg[m], y[kb * NB + m], s);
+            y[c0] -= s;
+        }
+        if (!solver) {
+            for (int c = c0 + nworkers; c < ncols; c += nworkers) {       // n > 640 only
+                double s = 0;
 #pragma unroll 8
-            for (int m = 0; m < NB; ++m) s += A[(size_t)(kb * NB + m) * npad + c] * y[kb * NB + m];
-            y[c] -= s;
+                for (int m = 0; m < NB; ++m) s = fma(A[(size_t)(kb * NB + m) * npad + c], y[kb * NB + m], s);
+                y[c] -= s;
+            }
         }
         __syncthreads();
     }
-    (void)nbk;
     for (int i = tid; i < n; i += blockDim.x) x[i] = y[i];
 }
 
@@ -584,10 +612,19 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, c
     }
 }
 
-// camera-major copy of the observation list: counting sort by camera (structure is fixed across LM iterations)
-__global__ void count_cams_kernel(const int32_t* __restrict__ obs_cam, int nobs, int* __restrict__ cnt) {
+// camera-major copy of the observation list: counting sort by camera (structure is fixed across LM iterations).
+// Shared-memory histograms per CTA keep the same-address global atomics down to (CTAs x cameras) instead of one per
+// observation (1.6M atomics on 100 counters took 300 us each way).
+constexpr int SORT_THREADS = 1024;
+__global__ void __launch_bounds__(SORT_THREADS) count_cams_kernel(const int32_t* __restrict__ obs_cam, int nobs, int nc, int use_smem, int* __restrict__ cnt) {
+    extern __shared__ int sh[];
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < nobs) atomicAdd(cnt + obs_cam[o], 1);
+    if (!use_smem) { if (o < nobs) atomicAdd(cnt + obs_cam[o], 1); return; }
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    if (o < nobs) atomicAdd(sh + obs_cam[o], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) if (sh[i]) atomicAdd(cnt + i, sh[i]);
 }
 __global__ void scan_small_kernel(const int* __restrict__ cnt, int n, int32_t* __restrict__ off, int* __restrict__ cursor) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { int s = 0; for (int i = 0; i < n; ++i) { off[i] = s; cursor[i] = s; s += cnt[i]; } off[n] = s; }
@@ -596,10 +633,23 @@ __global__ void expand_obs_pt_kernel(const int32_t* __restrict__ pt_off, int np,
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < np) for (int o = pt_off[p]; o < pt_off[p + 1]; ++o) obs_pt[o] = p;
 }
-__global__ void scatter_cm_kernel(const int32_t* __restrict__ obs_cam, const float2* __restrict__ obs_xy, const int32_t* __restrict__ obs_pt,
-                                  int nobs, int* __restrict__ cursor, float2* __restrict__ cm_xy, int32_t* __restrict__ cm_pt) {
+__global__ void __launch_bounds__(SORT_THREADS) scatter_cm_kernel(const int32_t* __restrict__ obs_cam, const float2* __restrict__ obs_xy,
+                                                                  const int32_t* __restrict__ obs_pt, int nobs, int nc, int use_smem,
+                                                                  int* __restrict__ cursor, float2* __restrict__ cm_xy, int32_t* __restrict__ cm_pt) {
+    extern __shared__ int sh[];          // [2*nc]: per-CTA count, then reserved base
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < nobs) { const int pos = atomicAdd(cursor + obs_cam[o], 1); cm_xy[pos] = obs_xy[o]; cm_pt[pos] = obs_pt[o]; }
+    if (!use_smem) {
+        if (o < nobs) { const int pos = atomicAdd(cursor + obs_cam[o], 1); cm_xy[pos] = obs_xy[o]; cm_pt[pos] = obs_pt[o]; }
+        return;
+    }
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    int c = 0, r = 0;
+    if (o < nobs) { c = obs_cam[o]; r = atomicAdd(sh + c, 1); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) if (sh[i]) sh[nc + i] = atomicAdd(cursor + i, sh[i]);
+    __syncthreads();
+    if (o < nobs) { const int pos = sh[nc + c] + r; cm_xy[pos] = obs_xy[o]; cm_pt[pos] = obs_pt[o]; }
 }
 
 }  // namespace
@@ -726,11 +776,11 @@ static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, dou
                                                                                  opt->min_lm_diagonal, opt->max_lm_diagonal, P->A);
     SFM_LAUNCH_CHECK(ctx);
     for (int k = 0; k < nbk; ++k) {
-        chol_panel_kernel<<<nbk - k, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, P->n, k, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
+        chol_panel_kernel<<<ceil_div(nbk - k, 4), 128, 0, ctx->stream>>>(P->A, npad, P->n, k, nbk, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
         const int T = nbk - k - 1;
         if (T > 0) { chol_update_kernel<<<T * (T + 1) / 2, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, k, nbk); SFM_LAUNCH_CHECK(ctx); }
     }
-    chol_backsolve_kernel<<<1, 1024, sizeof(double) * npad, ctx->stream>>>(P->A, npad, P->n, P->y_cf); SFM_LAUNCH_CHECK(ctx);
+    chol_backsolve_kernel<<<1, 640, sizeof(double) * npad, ctx->stream>>>(P->A, npad, P->n, P->y_cf); SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
 
@@ -808,10 +858,11 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     // camera-major copy (device counting sort)
     CRT(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * (nc + 1), st));
     if (nobs) {
-        count_cams_kernel<<<ceil_div(nobs, 256), 256, 0, st>>>(P->obs_cam, nobs, cnt);
+        const int use_smem = (size_t)nc * 8 <= 40 * 1024;
+        count_cams_kernel<<<ceil_div(nobs, SORT_THREADS), SORT_THREADS, use_smem ? nc * 4 : 0, st>>>(P->obs_cam, nobs, nc, use_smem, cnt);
         scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor);
         expand_obs_pt_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, np, obs_pt);
-        scatter_cm_kernel<<<ceil_div(nobs, 256), 256, 0, st>>>(P->obs_cam, P->obs_xy, obs_pt, nobs, cursor, P->cm_xy, P->cm_pt);
+        scatter_cm_kernel<<<ceil_div(nobs, SORT_THREADS), SORT_THREADS, use_smem ? nc * 8 : 0, st>>>(P->obs_cam, P->obs_xy, obs_pt, nobs, nc, use_smem, cursor, P->cm_xy, P->cm_pt);
         ctx->launches += 4;
     } else {
         scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor); ctx->launches += 1;

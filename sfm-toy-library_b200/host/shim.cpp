@@ -1,0 +1,154 @@
+// shim.cpp -- the three stage functions of the reference, re-implemented as thin marshalling over the C ABI
+// (include/sfmb200.h).  Linking this object instead of the bodies in the reference's
+//   SfMToyLib/SfM2DFeatureUtilities.cpp:53-71, SfMToyLib/SfMStereoUtilities.cpp:120-206,
+//   SfMToyLib/SfMBundleAdjustmentUtils.cpp:99-222
+// leaves SfM.cpp and main.cpp untouched.  No arithmetic happens here: only flattening of the
+// std::vector / std::map / cv::Mat containers into the plain arrays of the ABI and back.
+#ifdef SFMB200_WITH_REFERENCE_HEADERS
+#include "SfMToyLib/SfM2DFeatureUtilities.h"
+#include "SfMToyLib/SfMStereoUtilities.h"
+#include "SfMToyLib/SfMBundleAdjustmentUtils.h"
+#else
+#include "sfmtoylib_b200.h"
+#endif
+#include "../../include/sfmb200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <mutex>
+#include <stdexcept>
+
+namespace {
+
+// One context per process (device from SFMB200_DEVICE, default 0), created on first use.  The library serialises
+// concurrent calls internally, so the std::thread fan-out of SfM::createFeatureMatchMatrix (SfM.cpp:173-211) is safe.
+sfmb200_ctx* context() {
+    static sfmb200_ctx* ctx = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* dev = std::getenv("SFMB200_DEVICE");
+        if (sfmb200_create(dev ? std::atoi(dev) : 0, &ctx) != SFMB200_OK) {
+            std::cerr << "sfmb200: " << sfmb200_last_error(nullptr) << std::endl;
+            throw std::runtime_error("sfmb200_create failed (no CPU fallback)");
+        }
+    });
+    return ctx;
+}
+
+void check(int rc, const char* what) {
+    if (rc != SFMB200_OK) {
+        std::cerr << "sfmb200: " << what << ": " << sfmb200_last_error(context()) << std::endl;
+        throw std::runtime_error(what);
+    }
+}
+
+const double kNNMatchRatio = 0.8f;            // NN_MATCH_RATIO: the float literal widened to double
+const float kMaxReprojectionError = 10.0f;    // MIN_REPROJECTION_ERROR
+
+}  // namespace
+
+namespace sfmtoylib {
+
+Matching SfM2DFeatureUtilities::matchFeatures(const Features& featuresLeft, const Features& featuresRight) {
+    const cv::Mat& L = featuresLeft.descriptors;
+    const cv::Mat& R = featuresRight.descriptors;
+    Matching out;
+    if (L.rows == 0 || R.rows < 2) return out;
+    const int bytes = (int)(L.cols * L.elemSize());
+    std::vector<int32_t> q(L.rows), t(L.rows);
+    std::vector<float> d(L.rows);
+    int n = 0;
+    check(sfmb200_match_knn2_ratio(context(), L.ptr<uint8_t>(0), L.rows, R.ptr<uint8_t>(0), R.rows, bytes, kNNMatchRatio,
+                                   q.data(), t.data(), d.data(), &n), "sfmb200_match_knn2_ratio");
+    out.reserve(n);
+    for (int i = 0; i < n; ++i) out.push_back(cv::DMatch(q[i], t[i], 0, d[i]));      // knnMatch sets imgIdx = 0
+    return out;
+}
+
+bool SfMStereoUtilities::triangulateViews(const Intrinsics& intrinsics, const ImagePair imagePair, const Matching& matches,
+                                          const Features& featuresLeft, const Features& featuresRight, const cv::Matx34f& Pleft,
+                                          const cv::Matx34f& Pright, PointCloud& pointCloud) {
+    const int m = (int)matches.size();
+    if (m == 0) return true;
+    float K[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) K[3 * r + c] = intrinsics.K.at<float>(r, c);
+    std::vector<int32_t> mq(m), mt(m);
+    for (int i = 0; i < m; ++i) { mq[i] = matches[i].queryIdx; mt[i] = matches[i].trainIdx; }
+    std::vector<float> X(3 * (size_t)m);
+    std::vector<uint8_t> keep(m);
+    int nkeep = 0;
+    static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "Point2f must be two packed floats");
+    check(sfmb200_triangulate(context(), K, Pleft.val, Pright.val,
+                              reinterpret_cast<const float*>(featuresLeft.points.data()), (int)featuresLeft.points.size(),
+                              reinterpret_cast<const float*>(featuresRight.points.data()), (int)featuresRight.points.size(),
+                              mq.data(), mt.data(), m, kMaxReprojectionError, X.data(), keep.data(), &nkeep), "sfmb200_triangulate");
+    pointCloud.reserve(pointCloud.size() + nkeep);
+    for (int i = 0; i < m; ++i) {
+        if (!keep[i]) continue;
+        Point3DInMap p;
+        p.p = cv::Point3f(X[3 * i], X[3 * i + 1], X[3 * i + 2]);
+        p.originatingViews[(int)imagePair.left] = mq[i];
+        p.originatingViews[(int)imagePair.right] = mt[i];
+        pointCloud.push_back(p);
+    }
+    return true;
+}
+
+void SfMBundleAdjustmentUtils::adjustBundle(PointCloud& pointCloud, std::vector<Pose>& cameraPoses, Intrinsics& intrinsics,
+                                            const std::vector<Features>& image2dFeatures) {
+    // dense numbering of the views that are actually observed (Ceres only knows blocks that appear in a residual)
+    std::vector<int> dense(cameraPoses.size(), -1), used;
+    for (const Point3DInMap& p : pointCloud)
+        for (const auto& kv : p.originatingViews)
+            if (dense[kv.first] < 0) dense[kv.first] = 0;
+    for (size_t v = 0; v < cameraPoses.size(); ++v)
+        if (dense[v] == 0) { dense[v] = (int)used.size(); used.push_back((int)v); }
+    const int nc = (int)used.size(), np = (int)pointCloud.size();
+    std::vector<double> cams(6 * (size_t)nc), pts(3 * (size_t)np);
+    for (int i = 0; i < nc; ++i) {
+        const Pose& pose = cameraPoses[used[i]];
+        float R[9], aa[3];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[3 * r + c] = pose(r, c);
+        sfmb200_rotmat_to_angle_axis_f32(R, aa);                       // float conversion, then widened
+        for (int k = 0; k < 3; ++k) { cams[6 * i + k] = aa[k]; cams[6 * i + 3 + k] = pose(k, 3); }
+    }
+    double focal = intrinsics.K.at<float>(0, 0);
+    const float cx = intrinsics.K.at<float>(0, 2), cy = intrinsics.K.at<float>(1, 2);
+    std::vector<float> obs_xy;
+    std::vector<int32_t> obs_cam, pt_off(np + 1, 0);
+    for (int i = 0; i < np; ++i) {
+        const Point3DInMap& p = pointCloud[i];
+        pts[3 * i] = p.p.x; pts[3 * i + 1] = p.p.y; pts[3 * i + 2] = p.p.z;
+        for (const auto& kv : p.originatingViews) {                    // std::map: ascending view id
+            cv::Point2f p2d = image2dFeatures[kv.first].points[kv.second];
+            p2d.x -= cx; p2d.y -= cy;                                  // float subtraction
+            obs_xy.push_back(p2d.x); obs_xy.push_back(p2d.y);
+            obs_cam.push_back(dense[kv.first]);
+        }
+        pt_off[i + 1] = (int32_t)obs_cam.size();
+    }
+    sfmb200_ba_options opt;
+    sfmb200_ba_default_options(&opt);                                   // 500 iterations, 10 s, Ceres defaults
+    opt.verbose = 1;                                                    // minimizer_progress_to_stdout = true
+    sfmb200_ba_summary summary;
+    check(sfmb200_ba_solve(context(), &opt, nc, np, (int)obs_cam.size(), cams.data(), pts.data(), &focal, obs_xy.data(),
+                           obs_cam.data(), pt_off.data(), &summary), "sfmb200_ba_solve");
+    std::cout << "sfmb200 BA: " << summary.message << " iterations " << summary.num_iterations << " cost "
+              << summary.initial_cost << " -> " << summary.final_cost << "\n";
+    if (summary.termination_type != SFMB200_BA_CONVERGENCE) {
+        std::cerr << "Bundle adjustment failed." << std::endl;
+        return;                                                         // inputs untouched
+    }
+    intrinsics.K.at<float>(0, 0) = (float)focal;
+    intrinsics.K.at<float>(1, 1) = (float)focal;
+    for (int i = 0; i < nc; ++i) {
+        Pose& pose = cameraPoses[used[i]];
+        double R[9];
+        sfmb200_angle_axis_to_rotmat(&cams[6 * i], R);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) pose(r, c) = (float)R[3 * r + c]; pose(r, 3) = (float)cams[6 * i + 3 + r]; }
+    }
+    for (int i = 0; i < np; ++i) { pointCloud[i].p.x = (float)pts[3 * i]; pointCloud[i].p.y = (float)pts[3 * i + 1]; pointCloud[i].p.z = (float)pts[3 * i + 2]; }
+}
+
+}  // namespace sfmtoylib

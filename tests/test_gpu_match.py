@@ -66,7 +66,7 @@ def test_all_pairs_batched_equals_pairwise(ctx, oracle):
     res = ds.match_pairs(pairs)
     for (i, j), r in zip(pairs, res):
         _same(r, oracle.match_hamming(descs[i], descs[j]))
-        assert len(r[0]) > 30
+        assert len(r[0]) > (30 if j == i + 1 else 0)
     ds.close()
 
 
