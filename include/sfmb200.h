@@ -133,8 +133,10 @@ typedef struct {
     int num_linear_solves;
     double initial_cost, final_cost;        /* 1/2 sum r^2 over ALL ranks' observations */
     double total_time_s;                    /* host wall clock of the LM loop */
-    double schur_ms_total;                  /* profile=1: CUDA-event time of the point-elimination kernel, summed */
+    double schur_ms_total;                  /* profile=1: CUDA-event time of the point-elimination kernel (K3a), summed */
     int schur_launches;
+    double pair_ms_total;                   /* profile=1: CUDA-event time of the camera-pair block kernel (K3c), summed */
+    int pair_launches;
     int64_t kernel_launches;                /* kernels launched by this solve */
     char message[160];
 } sfmb200_ba_summary;

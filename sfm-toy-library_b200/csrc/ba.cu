@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -42,6 +43,7 @@ struct BAView {
     const CamDerived* camd;                                           // derived per camera at x
     const double* scale_cf; const double* scale_pt;                   // Jacobi scaling
     double* ptblk;                                                    // [np*12] M(6) zg(3) zf(3)
+    double* Zbuf;                                                     // [nobs*18] Z_o = Jc^T Jp M^T (gather mode), point-major
     // reduced system (block layout) + sums
     double* Sblk; double* Scf; double* Sff; double* rhs; double* gcf; double* dcf; double* sums;
     unsigned long long* gmax_pt_bits;                                 // max |g_p| (bit pattern of a non-negative double)
@@ -162,23 +164,25 @@ __global__ void fill_kernel(double* __restrict__ p, size_t n, double v) {
 // whole warp then sweeps the pair blocks of each of its points so that 32 consecutive doubles go out per RED.
 // Shared memory per group: Z [maxk][18] + camera ids [maxk]; pair table shared by the CTA.
 // ---------------------------------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool GATHER>
 __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double inv_radius) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GB = PT_THREADS / G, GW = 32 / G;
     const int maxk = v.maxk;
-    double* Zall = reinterpret_cast<double*>(smem_raw);                           // [GB][maxk][18]
+    double* Zall = reinterpret_cast<double*>(smem_raw);                           // [GB][maxk][18]   (RED mode only)
     int* camall = reinterpret_cast<int*>(Zall + (size_t)GB * maxk * 18);          // [GB][maxk]
     unsigned short* pair_tab = reinterpret_cast<unsigned short*>(camall + GB * maxk);   // [maxk*(maxk-1)/2]  (i | j<<8)
-    for (int j = 1 + threadIdx.x / 32; j < maxk; j += PT_THREADS / 32)
-        for (int i = threadIdx.x & 31; i < j; i += 32) pair_tab[j * (j - 1) / 2 + i] = (unsigned short)(i | (j << 8));
-    __syncthreads();
+    if (!GATHER) {
+        for (int j = 1 + threadIdx.x / 32; j < maxk; j += PT_THREADS / 32)
+            for (int i = threadIdx.x & 31; i < j; i += 32) pair_tab[j * (j - 1) / 2 + i] = (unsigned short)(i | (j << 8));
+        __syncthreads();
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G, gi = lane / G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
     const int group_in_block = warp * GW + gi;
-    double* Zg = Zall + (size_t)group_in_block * maxk * 18;
-    int* camg = camall + group_in_block * maxk;
+    double* Zg = GATHER ? nullptr : Zall + (size_t)group_in_block * maxk * 18;
+    int* camg = GATHER ? nullptr : camall + group_in_block * maxk;
     const double f = *v.focal, sf = v.scale_cf[6 * v.nc];
     const int nb = v.nc;
 
@@ -205,12 +209,12 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
 #pragma unroll
             for (int a = 0; a < 3; ++a) { g[a] += e[a] * J.r[0] + e[3 + a] * J.r[1]; wf[a] += e[a] * J.Jf[0] + e[3 + a] * J.Jf[1]; }
             cost += J.r[0] * J.r[0] + J.r[1] * J.r[1];
-            double* W = Zg + j * 18;              // W = Jc^T Jp (6x3), turned into Z below
+            double* W = GATHER ? v.Zbuf + (size_t)o * 18 : Zg + j * 18;     // W = Jc^T Jp (6x3), turned into Z below
 #pragma unroll
             for (int a = 0; a < 6; ++a)
 #pragma unroll
                 for (int b = 0; b < 3; ++b) W[a * 3 + b] = J.Jc[a] * e[b] + J.Jc[6 + a] * e[3 + b];
-            camg[j] = c;
+            if (!GATHER) camg[j] = c;
         }
 #pragma unroll
         for (int a = 0; a < 6; ++a) U[a] = group_sum<G>(U[a], gmask);
@@ -243,13 +247,14 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
         }
         // Z = W M^T  (own rows; same thread wrote W)
         for (int j = gl; j < k; j += G) {
-            double* W = Zg + j * 18;
+            double* W = GATHER ? v.Zbuf + (size_t)(o0 + j) * 18 : Zg + j * 18;
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
                 const double w0 = W[a * 3], w1 = W[a * 3 + 1], w2 = W[a * 3 + 2];
                 W[a * 3] = w0 * M[0]; W[a * 3 + 1] = w0 * M[1] + w1 * M[2]; W[a * 3 + 2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
             }
         }
+        if (GATHER) continue;           // off-diagonal blocks are accumulated by ba_pair_kernel from Zbuf
         __syncwarp();
         // pair sweep: the whole warp handles the points of its GW groups one after the other
 #pragma unroll 1
@@ -281,6 +286,102 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
         red_add(v.Sff, -t2); red_add(v.rhs + 6 * v.nc, -t3);
         atomicMax(v.gmax_pt_bits, (unsigned long long)__double_as_longlong(t4));
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3c (gather mode): off-diagonal blocks without atomics.  For every camera pair (ci < cj) the list of (obs_i, obs_j)
+// index pairs of the points both cameras see is built once per problem (the structure is fixed across LM iterations).
+// One warp per (pair, split): lanes stride over the list, each accumulating a full 6x6 block  sum Z_i Z_j^T  in 36
+// registers from two 144-byte reads, then a warp shuffle reduction and 36 REDs per warp (instead of 36 per entry).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_WARPS = 4;
+__global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
+                                                                   const uint2* __restrict__ pair_ent, int nblk_off, int splits,
+                                                                   const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);       // index into the list of non-empty pairs
+    if (q >= nblk_off) return;
+    const int start = pair_off[q], len = pair_off[q + 1] - start;
+    const int sp = blockIdx.y;
+    const int b0 = start + (int)((long long)len * sp / splits), b1 = start + (int)((long long)len * (sp + 1) / splits);
+    double acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+    for (int e = b0 + lane; e < b1; e += 32) {
+        const uint2 ent = pair_ent[e];
+        const double2* pi = reinterpret_cast<const double2*>(Zbuf + (size_t)ent.x * 18);
+        const double2* pj = reinterpret_cast<const double2*>(Zbuf + (size_t)ent.y * 18);
+        double zi[18], zj[18];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { const double2 a = pi[t], b = pj[t]; zi[2 * t] = a.x; zi[2 * t + 1] = a.y; zj[2 * t] = b.x; zj[2 * t + 1] = b.y; }
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b < 6; ++b)
+                acc[a * 6 + b] = fma(zi[a * 3], zj[b * 3], fma(zi[a * 3 + 1], zj[b * 3 + 1], fma(zi[a * 3 + 2], zj[b * 3 + 2], acc[a * 6 + b])));
+    }
+    if (b1 <= b0) return;
+    double* dst = Sblk + (size_t)pair_blk[q] * 36;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+        const double sum = warp_sum(acc[i]);
+        if (lane == (i & 31)) red_add(dst + i, -sum);
+    }
+}
+
+// pair-list construction (once per problem): thread per point
+__device__ __forceinline__ void hist_add(int* sh, int* glob, bool use_smem, int idx) { atomicAdd((use_smem ? sh : glob) + idx, 1); }
+__global__ void __launch_bounds__(256) pair_count_kernel(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ obs_cam, int np, int nb,
+                                                         int nblk, int use_smem, int* __restrict__ cnt) {
+    extern __shared__ int sh[];
+    if (use_smem) { for (int i = threadIdx.x; i < nblk; i += blockDim.x) sh[i] = 0; __syncthreads(); }
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < np) {
+        const int o0 = pt_off[p], o1 = pt_off[p + 1];
+        for (int i = o0; i < o1; ++i) for (int j = i + 1; j < o1; ++j) hist_add(sh, cnt, use_smem, (int)blk_index(obs_cam[i], obs_cam[j], nb));
+    }
+    if (use_smem) { __syncthreads(); for (int i = threadIdx.x; i < nblk; i += blockDim.x) if (sh[i]) atomicAdd(cnt + i, sh[i]); }
+}
+// compact the non-empty pairs: pair_blk[q] = block id, pair_off[q] = start; single CTA (nblk is small: nc(nc+1)/2)
+__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ cnt, int nblk, int32_t* __restrict__ pair_off, int32_t* __restrict__ pair_blk,
+                                                         int* __restrict__ cursor, int* __restrict__ n_nonempty) {
+    __shared__ int wsum[32], wcnt[32], carry_s, carry_q;
+    if (threadIdx.x == 0) { carry_s = 0; carry_q = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < nblk; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int c = i < nblk ? cnt[i] : 0, f = c > 0;
+        int s = c, q = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, s, o), b = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) { s += a; q += b; } }
+        if (lane == 31) { wsum[w] = s; wcnt[w] = q; }
+        __syncthreads();
+        if (w == 0) {
+            int a = wsum[lane], b = wcnt[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b, o); if (lane >= o) { a += x; b += y; } }
+            wsum[lane] = a; wcnt[lane] = b;
+        }
+        __syncthreads();
+        const int ex_s = carry_s + (w ? wsum[w - 1] : 0) + s - c, ex_q = carry_q + (w ? wcnt[w - 1] : 0) + q - f;
+        if (i < nblk) { cursor[i] = ex_s; if (f) { pair_off[ex_q] = ex_s; pair_blk[ex_q] = i; } }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry_s += wsum[31]; carry_q += wcnt[31]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { pair_off[carry_q] = carry_s; *n_nonempty = carry_q; }
+}
+__global__ void __launch_bounds__(256) pair_fill_kernel(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ obs_cam, int np, int nb,
+                                                        int* __restrict__ cursor, uint2* __restrict__ ent) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const int o0 = pt_off[p], o1 = pt_off[p + 1];
+    for (int i = o0; i < o1; ++i)
+        for (int j = i + 1; j < o1; ++j) {
+            const int pos = atomicAdd(cursor + (int)blk_index(obs_cam[i], obs_cam[j], nb), 1);
+            ent[pos] = make_uint2((unsigned)i, (unsigned)j);
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -673,7 +774,12 @@ struct sfmb200_ba_problem {
     double* A; double* y_cf;
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
     bool have_scale = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    // gather mode (K3c): Z per observation + per-camera-pair entry lists
+    bool gather = true;
+    double* Zbuf = nullptr; int32_t* pair_off = nullptr; int32_t* pair_blk = nullptr; uint2* pair_ent = nullptr;
+    int n_pairs_nonempty = 0, pair_splits = 1;
+    DevBuf gmem;
 };
 
 static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* opt) {
@@ -681,7 +787,7 @@ static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* o
     v.nc = P->nc; v.np = P->np; v.nobs = P->nobs; v.maxk = P->maxk;
     v.obs_xy = P->obs_xy; v.obs_cam = P->obs_cam; v.pt_off = P->pt_off; v.cm_off = P->cm_off; v.cm_xy = P->cm_xy; v.cm_pt = P->cm_pt;
     v.cams = P->cf[P->cur]; v.focal = P->cf[P->cur] + 6 * P->nc; v.pts = P->pts[P->cur]; v.camd = P->camd[P->cur];
-    v.scale_cf = P->scale_cf; v.scale_pt = P->scale_pt; v.ptblk = P->ptblk;
+    v.scale_cf = P->scale_cf; v.scale_pt = P->scale_pt; v.ptblk = P->ptblk; v.Zbuf = P->Zbuf;
     v.Sblk = P->Sblk; v.Scf = P->Scf; v.Sff = P->Sff; v.rhs = P->rhs; v.gcf = P->gcf; v.dcf = P->dcf; v.sums = P->sums;
     v.gmax_pt_bits = P->gmax_pt_bits; v.fail = P->fail;
     v.min_diag = opt->min_lm_diagonal; v.max_diag = opt->max_lm_diagonal;
@@ -695,11 +801,17 @@ static size_t point_smem_bytes(int G, int maxk) {
 
 template <int G> static int launch_point_pass(sfmb200_ba_problem* P, const BAView& v, double inv_radius) {
     sfmb200_ctx* ctx = P->ctx;
-    const size_t smem = point_smem_bytes(G, P->maxk);
-    if (smem > 48 * 1024) SFM_CUDA(ctx, cudaFuncSetAttribute(ba_point_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int GB = PT_THREADS / G;
+    if (P->gather) {
+        const int blocks = std::max(1, std::min(ceil_div(P->np, GB), ctx->sm_count * 16));
+        ba_point_kernel<G, true><<<blocks, PT_THREADS, 0, ctx->stream>>>(v, inv_radius);
+        SFM_LAUNCH_CHECK(ctx);
+        return SFMB200_OK;
+    }
+    const size_t smem = point_smem_bytes(G, P->maxk);
+    if (smem > 48 * 1024) SFM_CUDA(ctx, cudaFuncSetAttribute(ba_point_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = std::max(1, std::min(ceil_div(P->np, GB), ctx->sm_count * 8));
-    ba_point_kernel<G><<<blocks, PT_THREADS, smem, ctx->stream>>>(v, inv_radius);
+    ba_point_kernel<G, false><<<blocks, PT_THREADS, smem, ctx->stream>>>(v, inv_radius);
     SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
@@ -764,6 +876,13 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
         if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev0, ctx->stream));
         int rc = DISPATCH_G(P, launch_point_pass)(P, v, 1.0 / radius); if (rc) return rc;
         if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev1, ctx->stream));
+        if (P->gather && P->n_pairs_nonempty > 0) {
+            if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev2, ctx->stream));
+            ba_pair_kernel<<<dim3(ceil_div(P->n_pairs_nonempty, PAIR_WARPS), P->pair_splits), PAIR_WARPS * 32, 0, ctx->stream>>>(
+                P->Zbuf, P->pair_off, P->pair_ent, P->n_pairs_nonempty, P->pair_splits, P->pair_blk, P->Sblk);
+            SFM_LAUNCH_CHECK(ctx);
+            if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev3, ctx->stream));
+        }
         ba_camera_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v); SFM_LAUNCH_CHECK(ctx);
     }
     return sfmb200_allreduce_sum_f64(ctx, P->red, P->red_n);
@@ -849,7 +968,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     int32_t* obs_pt = cv.take<int32_t>(nobs); int* cnt = cv.take<int>(2 * (size_t)(nc + 1)); int* cursor = cnt + nc + 1;
 
     cudaStream_t st = ctx->stream;
-#define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { P->mem.release(); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
+#define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { P->mem.release(); P->gmem.release(); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
     if (nobs) { CRT(cudaMemcpyAsync(P->obs_xy, obs_xy, 8 * (size_t)nobs, cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->obs_cam, obs_cam, 4 * (size_t)nobs, cudaMemcpyHostToDevice, st)); }
     if (np) { CRT(cudaMemcpyAsync(P->pt_off, pt_off, 4 * (size_t)(np + 1), cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->pts0, pts3, 24 * (size_t)np, cudaMemcpyHostToDevice, st)); }
     if (nc) CRT(cudaMemcpyAsync(P->cf0, cams6, 48 * (size_t)nc, cudaMemcpyHostToDevice, st));
@@ -869,7 +988,38 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     }
     CRT(cudaGetLastError());
     CRT(cudaMallocHost((void**)&P->h_scal, sizeof(double) * 32));
-    CRT(cudaEventCreate(&P->ev0)); CRT(cudaEventCreate(&P->ev1));
+    CRT(cudaEventCreate(&P->ev0)); CRT(cudaEventCreate(&P->ev1)); CRT(cudaEventCreate(&P->ev2)); CRT(cudaEventCreate(&P->ev3));
+    {   // off-diagonal Schur blocks: "gather" (default; per-camera-pair lists, no atomics in the hot loop) or "red"
+        const char* mode = getenv("SFMB200_BA_SCHUR");
+        P->gather = !(mode && strcmp(mode, "red") == 0);
+        long long E = 0;
+        for (int p = 0; p < np; ++p) { const long long k = pt_off[p + 1] - pt_off[p]; E += k * (k - 1) / 2; }
+        if (E >= (1LL << 31) - 1024) P->gather = false;          // int32 offsets
+        if (P->gather && E > 0) {
+            const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + Carver::pad(4 * (nblk + 1)) * 2 + Carver::pad(8 * (size_t)E) + Carver::pad(4 * nblk) * 2 + 4096;
+            CRT(P->gmem.reserve(gb));
+            Carver gc(P->gmem.p);
+            P->Zbuf = gc.take<double>(18 * (size_t)nobs); P->pair_off = gc.take<int32_t>(nblk + 1); P->pair_blk = gc.take<int32_t>(nblk + 1);
+            P->pair_ent = gc.take<uint2>((size_t)E);
+            int* pcnt = gc.take<int>(nblk); int* pcur = gc.take<int>(nblk); int* d_nne = gc.take<int>(4);
+            const int use_smem = nblk * 4 <= 40 * 1024;
+            CRT(cudaMemsetAsync(pcnt, 0, 4 * nblk, st));
+            pair_count_kernel<<<ceil_div(np, 256), 256, use_smem ? nblk * 4 : 0, st>>>(P->pt_off, P->obs_cam, np, nc, (int)nblk, use_smem, pcnt);
+            pair_scan_kernel<<<1, 1024, 0, st>>>(pcnt, (int)nblk, P->pair_off, P->pair_blk, pcur, d_nne);
+            pair_fill_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, P->obs_cam, np, nc, pcur, P->pair_ent);
+            ctx->launches += 3;
+            CRT(cudaGetLastError());
+            int nne = 0;
+            CRT(cudaMemcpyAsync(&nne, d_nne, 4, cudaMemcpyDeviceToHost, st));
+            CRT(cudaStreamSynchronize(st));
+            P->n_pairs_nonempty = nne;
+            P->pair_splits = std::max(1, std::min(64, ceil_div(16 * ctx->sm_count, std::max(1, nne))));
+        } else if (P->gather) {
+            P->gather = E > 0 ? P->gather : true;    // no pairs at all: nothing to accumulate off the diagonal
+            CRT(P->gmem.reserve(Carver::pad(8 * 18 * (size_t)std::max(nobs, 1)) + 256));
+            P->Zbuf = (double*)P->gmem.p;
+        }
+    }
 #undef CRT
     *out = P;
     SFM_CUDA(ctx, cudaMemcpyAsync(P->cf[0], P->cf0, 8 * n, cudaMemcpyDeviceToDevice, st));
@@ -886,6 +1036,9 @@ void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     if (P->h_scal) cudaFreeHost(P->h_scal);
     if (P->ev0) cudaEventDestroy(P->ev0);
     if (P->ev1) cudaEventDestroy(P->ev1);
+    if (P->ev2) cudaEventDestroy(P->ev2);
+    if (P->ev3) cudaEventDestroy(P->ev3);
+    P->gmem.release();
     P->mem.release();
     delete P;
 }
@@ -987,7 +1140,11 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
         SFM_CUDA(ctx, cudaMemcpyAsync(h, P->sums, 64, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaMemcpyAsync(h + 8, P->post, 8 * 16, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (opt.profile) { float ms = 0; if (cudaEventElapsedTime(&ms, P->ev0, P->ev1) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; } }
+        if (opt.profile && P->np > 0 && P->nobs > 0) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, P->ev0, P->ev1) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; }
+            if (P->gather && P->n_pairs_nonempty > 0 && cudaEventElapsedTime(&ms, P->ev2, P->ev3) == cudaSuccess) { sum->pair_ms_total += ms; sum->pair_launches++; }
+        }
         const double cost_x = 0.5 * h[0], xn2_pts = h[1];
         const double cand_cost_raw = 0.5 * h[8], model_acc = h[9], dn2_pts = h[10], cn2_pts = h[11];
         const double fails[2] = {h[12], h[13]};                        // summed over ranks

@@ -59,7 +59,7 @@ static void test_triangulate_from_2_views() {
         EXPECT(cloud[i].originatingViews.at(0) == (int)i && cloud[i].originatingViews.at(1) == (int)i, "back references");
     }
     // appends, never clears (SfMStereoUtilities.cpp:202); a gross outlier is filtered
-    right.points[3].x += 80;
+    right.points[3].y += 80;   // off the epipolar line (an x shift would only change the depth)
     SfMStereoUtilities::triangulateViews(intr, ImagePair{0, 1}, matching, left, right, Pl, Pr, cloud);
     EXPECT(cloud.size() == 23, "appended 11 more (one outlier dropped)");
 }

@@ -157,3 +157,41 @@ def test_config3_properties_full_size(ctx, oracle):
     s2 = ctx.ba_solve(cams, pts, f, p["obs_xy"], p["obs_cam"], p["pt_off"])[3]
     assert s2["termination_type"] == capi.CONVERGENCE and s2["num_iterations"] <= 2
     prob.close()
+
+
+def test_red_and_gather_schur_modes_agree(ctx, oracle, monkeypatch):
+    """The two implementations of the off-diagonal Schur blocks (atomics-free per-camera-pair gather, default, and the
+    per-point RED sweep) give the same reduced system and the same solve."""
+    p = synth.make_ba_problem(n_cams=12, n_pts=1500, obs_per_pt=5, seed=13)
+    out = {}
+    for mode in ("gather", "red"):
+        monkeypatch.setenv("SFMB200_BA_SCHUR", mode)
+        prob = ctx.ba_problem(*_args(p))
+        out[mode] = (prob.reduced_system(1e4), prob.run(), prob.download())
+        prob.close()
+    o = oracle.ba_reduced_system(*_args(p), radius=1e4)
+    for mode in ("gather", "red"):
+        np.testing.assert_allclose(out[mode][0]["S"], o["S"], rtol=0, atol=2e-11 * np.abs(o["S"]).max())
+    assert out["gather"][1]["num_iterations"] == out["red"][1]["num_iterations"]
+    assert abs(out["gather"][1]["final_cost"] - out["red"][1]["final_cost"]) < 1e-10 * out["red"][1]["final_cost"]
+    np.testing.assert_allclose(out["gather"][2][1], out["red"][2][1], rtol=0, atol=1e-8)
+
+
+def test_many_observations_per_point_and_ragged_tracks(ctx, oracle):
+    """Track lengths 2..40 in one problem (G = 32 groups, multi-chunk points, long pair lists)."""
+    rs = np.random.RandomState(5)
+    base = synth.make_ba_problem(n_cams=40, n_pts=300, obs_per_pt=40, seed=6)
+    keep = np.zeros(base["nobs"], bool); off = [0]
+    for i in range(base["np"]):
+        k = int(rs.randint(2, 41))
+        sel = np.sort(rs.choice(40, k, replace=False)) + base["pt_off"][i]
+        keep[sel] = True; off.append(off[-1] + k)
+    args = (base["cams"], base["pts"], base["focal"], base["obs_xy"][keep], base["obs_cam"][keep], np.asarray(off, np.int32))
+    prob = ctx.ba_problem(*args)
+    g = prob.reduced_system(1e4); o = oracle.ba_reduced_system(*args, radius=1e4)
+    np.testing.assert_allclose(g["S"], o["S"], rtol=0, atol=2e-11 * np.abs(o["S"]).max())
+    np.testing.assert_allclose(g["rhs"], o["rhs"], rtol=0, atol=1e-10 * np.abs(o["rhs"]).max())
+    s = prob.run(); so = oracle.ba_solve(*args, oracle.ba_default_options(jacobian_mode=1))[3]
+    assert s["termination_type"] == so["termination_type"] and s["num_iterations"] == so["num_iterations"]
+    assert abs(s["final_cost"] - so["final_cost"]) < 1e-9 * so["final_cost"]
+    prob.close()
