@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
             sp[0] = v.scale_pt[3 * p]; sp[1] = v.scale_pt[3 * p + 1]; sp[2] = v.scale_pt[3 * p + 2];
         }
         double U[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, wf[3] = {0, 0, 0}, cost = 0;
+        double Wreg[18];                  // gather mode: W of this lane's first observation stays in registers
         for (int j = gl; j < k; j += G) {
             const int o = o0 + j, c = v.obs_cam[o];
             ObsJ J;
@@ -209,11 +210,19 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
 #pragma unroll
             for (int a = 0; a < 3; ++a) { g[a] += e[a] * J.r[0] + e[3 + a] * J.r[1]; wf[a] += e[a] * J.Jf[0] + e[3 + a] * J.Jf[1]; }
             cost += J.r[0] * J.r[0] + J.r[1] * J.r[1];
-            double* W = GATHER ? v.Zbuf + (size_t)o * 18 : Zg + j * 18;     // W = Jc^T Jp (6x3), turned into Z below
+            // W = Jc^T Jp (6x3), turned into Z = W M^T below
+            if (GATHER && j == gl) {
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
+                for (int a = 0; a < 6; ++a)
 #pragma unroll
-                for (int b = 0; b < 3; ++b) W[a * 3 + b] = J.Jc[a] * e[b] + J.Jc[6 + a] * e[3 + b];
+                    for (int b = 0; b < 3; ++b) Wreg[a * 3 + b] = J.Jc[a] * e[b] + J.Jc[6 + a] * e[3 + b];
+            } else {
+                double* W = GATHER ? v.Zbuf + (size_t)o * 18 : Zg + j * 18;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) W[a * 3 + b] = J.Jc[a] * e[b] + J.Jc[6 + a] * e[3 + b];
+            }
             if (!GATHER) camg[j] = c;
         }
 #pragma unroll
@@ -246,7 +255,20 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
             }
         }
         // Z = W M^T  (own rows; same thread wrote W)
-        for (int j = gl; j < k; j += G) {
+        if (GATHER && gl < k) {
+            double2* dst = reinterpret_cast<double2*>(v.Zbuf + (size_t)(o0 + gl) * 18);
+#pragma unroll
+            for (int a = 0; a < 6; a += 2) {      // two rows = six doubles = three 16-byte stores
+                double z[6];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double w0 = Wreg[(a + h) * 3], w1 = Wreg[(a + h) * 3 + 1], w2 = Wreg[(a + h) * 3 + 2];
+                    z[3 * h] = w0 * M[0]; z[3 * h + 1] = w0 * M[1] + w1 * M[2]; z[3 * h + 2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
+                }
+                dst[a / 2 * 3] = make_double2(z[0], z[1]); dst[a / 2 * 3 + 1] = make_double2(z[2], z[3]); dst[a / 2 * 3 + 2] = make_double2(z[4], z[5]);
+            }
+        }
+        for (int j = gl + (GATHER ? G : 0); j < k; j += G) {
             double* W = GATHER ? v.Zbuf + (size_t)(o0 + j) * 18 : Zg + j * 18;
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
@@ -295,15 +317,20 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
 // registers from two 144-byte reads, then a warp shuffle reduction and 36 REDs per warp (instead of 36 per entry).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PAIR_WARPS = 4;
+// pair_off is indexed by key = blk * nseg + seg (seg = point-range segment): the grid walks the segments in the slow
+// (y) dimension, LAST segment first, so that all resident warps read the same ~24 MB slice of Zbuf -- which then lives
+// in L2 (the tail of Zbuf is still L2-resident from the point kernel that just wrote it).
 __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
-                                                                   const uint2* __restrict__ pair_ent, int nblk_off, int splits,
+                                                                   const uint2* __restrict__ pair_ent, int n_nonempty, int nseg, int splits,
                                                                    const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);       // index into the list of non-empty pairs
-    if (q >= nblk_off) return;
-    const int start = pair_off[q], len = pair_off[q + 1] - start;
-    const int sp = blockIdx.y;
+    if (q >= n_nonempty) return;
+    const int seg = nseg - 1 - (int)(blockIdx.y / splits), sp = blockIdx.y % splits;
+    const int blk = pair_blk[q];
+    const int start = pair_off[(size_t)blk * nseg + seg], len = pair_off[(size_t)blk * nseg + seg + 1] - start;
     const int b0 = start + (int)((long long)len * sp / splits), b1 = start + (int)((long long)len * (sp + 1) / splits);
+    if (b1 <= b0) return;
     double acc[36];
 #pragma unroll
     for (int i = 0; i < 36; ++i) acc[i] = 0.0;
@@ -320,8 +347,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* 
             for (int b = 0; b < 6; ++b)
                 acc[a * 6 + b] = fma(zi[a * 3], zj[b * 3], fma(zi[a * 3 + 1], zj[b * 3 + 1], fma(zi[a * 3 + 2], zj[b * 3 + 2], acc[a * 6 + b])));
     }
-    if (b1 <= b0) return;
-    double* dst = Sblk + (size_t)pair_blk[q] * 36;
+    double* dst = Sblk + (size_t)blk * 36;
 #pragma unroll
     for (int i = 0; i < 36; ++i) {
         const double sum = warp_sum(acc[i]);
@@ -329,57 +355,82 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* 
     }
 }
 
-// pair-list construction (once per problem): thread per point
-__device__ __forceinline__ void hist_add(int* sh, int* glob, bool use_smem, int idx) { atomicAdd((use_smem ? sh : glob) + idx, 1); }
+// pair-list construction (once per problem): thread per point; key = blk * nseg + seg(point)
+__device__ __forceinline__ int point_segment(int p, int np, int nseg) { return (int)((long long)p * nseg / np); }
 __global__ void __launch_bounds__(256) pair_count_kernel(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ obs_cam, int np, int nb,
-                                                         int nblk, int use_smem, int* __restrict__ cnt) {
-    extern __shared__ int sh[];
-    if (use_smem) { for (int i = threadIdx.x; i < nblk; i += blockDim.x) sh[i] = 0; __syncthreads(); }
+                                                         int nseg, int* __restrict__ cnt) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < np) {
-        const int o0 = pt_off[p], o1 = pt_off[p + 1];
-        for (int i = o0; i < o1; ++i) for (int j = i + 1; j < o1; ++j) hist_add(sh, cnt, use_smem, (int)blk_index(obs_cam[i], obs_cam[j], nb));
-    }
-    if (use_smem) { __syncthreads(); for (int i = threadIdx.x; i < nblk; i += blockDim.x) if (sh[i]) atomicAdd(cnt + i, sh[i]); }
+    if (p >= np) return;
+    const int o0 = pt_off[p], o1 = pt_off[p + 1], seg = point_segment(p, np, nseg);
+    for (int i = o0; i < o1; ++i)
+        for (int j = i + 1; j < o1; ++j) atomicAdd(cnt + (size_t)blk_index(obs_cam[i], obs_cam[j], nb) * nseg + seg, 1);
 }
-// compact the non-empty pairs: pair_blk[q] = block id, pair_off[q] = start; single CTA (nblk is small: nc(nc+1)/2)
-__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ cnt, int nblk, int32_t* __restrict__ pair_off, int32_t* __restrict__ pair_blk,
-                                                         int* __restrict__ cursor, int* __restrict__ n_nonempty) {
-    __shared__ int wsum[32], wcnt[32], carry_s, carry_q;
-    if (threadIdx.x == 0) { carry_s = 0; carry_q = 0; }
+// exclusive scan of cnt[nkeys] -> pair_off[nkeys+1] and cursor[nkeys]; single CTA, chained over 1024-element chunks
+__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ cnt, int nkeys, int32_t* __restrict__ pair_off, int* __restrict__ cursor) {
+    __shared__ int wsum[32], carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < nkeys; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int c = i < nkeys ? cnt[i] : 0;
+        int s = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += a; }
+        if (lane == 31) wsum[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            int a = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a += x; }
+            wsum[lane] = a;
+        }
+        __syncthreads();
+        const int ex = carry_s + (w ? wsum[w - 1] : 0) + s - c;
+        if (i < nkeys) { cursor[i] = ex; pair_off[i] = ex; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += wsum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pair_off[nkeys] = carry_s;
+}
+// list of camera pairs that have at least one entry; single CTA (nblk = nc(nc+1)/2 is small)
+__global__ void __launch_bounds__(1024) pair_compact_kernel(const int32_t* __restrict__ pair_off, int nblk, int nseg, int32_t* __restrict__ pair_blk,
+                                                            int* __restrict__ n_nonempty) {
+    __shared__ int wcnt[32], carry_q;
+    if (threadIdx.x == 0) carry_q = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int base = 0; base < nblk; base += 1024) {
         const int i = base + threadIdx.x;
-        const int c = i < nblk ? cnt[i] : 0, f = c > 0;
-        int s = c, q = f;
+        const int f = i < nblk ? (pair_off[(size_t)(i + 1) * nseg] > pair_off[(size_t)i * nseg]) : 0;
+        int q = f;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, s, o), b = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) { s += a; q += b; } }
-        if (lane == 31) { wsum[w] = s; wcnt[w] = q; }
+        for (int o = 1; o < 32; o <<= 1) { const int b = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) q += b; }
+        if (lane == 31) wcnt[w] = q;
         __syncthreads();
         if (w == 0) {
-            int a = wsum[lane], b = wcnt[lane];
+            int b = wcnt[lane];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b, o); if (lane >= o) { a += x; b += y; } }
-            wsum[lane] = a; wcnt[lane] = b;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, b, o); if (lane >= o) b += y; }
+            wcnt[lane] = b;
         }
         __syncthreads();
-        const int ex_s = carry_s + (w ? wsum[w - 1] : 0) + s - c, ex_q = carry_q + (w ? wcnt[w - 1] : 0) + q - f;
-        if (i < nblk) { cursor[i] = ex_s; if (f) { pair_off[ex_q] = ex_s; pair_blk[ex_q] = i; } }
+        if (f) pair_blk[carry_q + (w ? wcnt[w - 1] : 0) + q - 1] = i;
         __syncthreads();
-        if (threadIdx.x == 0) { carry_s += wsum[31]; carry_q += wcnt[31]; }
+        if (threadIdx.x == 0) carry_q += wcnt[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) { pair_off[carry_q] = carry_s; *n_nonempty = carry_q; }
+    if (threadIdx.x == 0) *n_nonempty = carry_q;
 }
 __global__ void __launch_bounds__(256) pair_fill_kernel(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ obs_cam, int np, int nb,
-                                                        int* __restrict__ cursor, uint2* __restrict__ ent) {
+                                                        int nseg, int* __restrict__ cursor, uint2* __restrict__ ent) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
-    const int o0 = pt_off[p], o1 = pt_off[p + 1];
+    const int o0 = pt_off[p], o1 = pt_off[p + 1], seg = point_segment(p, np, nseg);
     for (int i = o0; i < o1; ++i)
         for (int j = i + 1; j < o1; ++j) {
-            const int pos = atomicAdd(cursor + (int)blk_index(obs_cam[i], obs_cam[j], nb), 1);
+            const int pos = atomicAdd(cursor + (size_t)blk_index(obs_cam[i], obs_cam[j], nb) * nseg + seg, 1);
             ent[pos] = make_uint2((unsigned)i, (unsigned)j);
         }
 }
@@ -487,55 +538,58 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
     A[(size_t)r * npad + c] = val;
 }
 
-// Panel step k, warp-level: one WARP per tile row i >= k, lane r holds row r of a 32x32 tile in registers.
-// Every warp factors the diagonal tile redundantly (496 shuffle-broadcasts + 496 DFMA, no block barrier, no shared
-// memory); warp i == k writes it back, the others solve their own tile against it in registers:
-// A[i][k] <- A[i][k] L_kk^-T.  Pivots with global index >= n are forced to 1 (augmented rhs row / padding rows).
-__global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk, int* __restrict__ fail) {
-    const int lane = threadIdx.x & 31;
-    const int i = k + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= nbk) return;
-    double a[NB];
-    {
-        const double* src = A + (size_t)(k * NB + lane) * npad + k * NB;
-#pragma unroll
-        for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); a[c] = v.x; a[c + 1] = v.y; }
+// Panel step k.  CTA = 4 warps: warp 0 factors the 32x32 diagonal tile in shared memory (lane r owns row r; compact
+// loops -- a fully unrolled register version is ~100 KB of straight-line code and instruction-fetch bound), every warp
+// then solves one sub-diagonal tile against it, A[i][k] <- A[i][k] L_kk^-T, row-per-lane, no barrier in the solve.
+// Every CTA factors the diagonal tile redundantly (11 k FMA) instead of waiting on another CTA; CTA 0 writes it back
+// together with the reciprocal pivots (dinv) the back-substitution uses.  Pivots with global index >= n are forced to 1
+// (augmented rhs row / padding rows).
+constexpr int PANEL_WARPS = 4;
+__global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk,
+                                                                      double* __restrict__ dinv, int* __restrict__ fail) {
+    __shared__ double L[NB][NB + 1];
+    __shared__ double B[PANEL_WARPS][NB][NB + 1];
+    __shared__ double invd[NB];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = k + 1 + blockIdx.x * PANEL_WARPS + w;
+    const bool has_tile = i < nbk;
+    for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; L[r][c] = A[(size_t)(k * NB + r) * npad + k * NB + c]; }
+    if (has_tile)
+        for (int r = 0; r < NB; ++r) B[w][r][lane] = A[(size_t)(i * NB + r) * npad + k * NB + lane];
+    __syncthreads();
+    if (w == 0) {
+        bool bad = false;
+        for (int j = 0; j < NB; ++j) {
+            const int gj = k * NB + j;
+            const double d = L[j][j];
+            double ljj, inv;
+            if (gj >= n) { ljj = 1.0; inv = 0.0; }
+            else if (!(d > 0.0) || !isfinite(d)) { bad = true; ljj = 1.0; inv = 1.0; }
+            else { inv = rsqrt(d); ljj = d * inv; }
+            double lrj = 0.0;
+            if (lane > j) { lrj = L[lane][j] * inv; L[lane][j] = lrj; }
+            else if (lane == j) { L[j][j] = ljj; invd[j] = inv; }
+            __syncwarp();
+            for (int c = j + 1; c <= lane; ++c) L[lane][c] = fma(-lrj, L[c][j], L[lane][c]);
+            __syncwarp();
+        }
+        if (bad && lane == 0 && blockIdx.x == 0) atomicAdd(fail, 1);
     }
-    bool bad = false;
-#pragma unroll
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; if (c <= r) A[(size_t)(k * NB + r) * npad + k * NB + c] = L[r][c]; }
+        if (threadIdx.x < NB) dinv[k * NB + threadIdx.x] = invd[threadIdx.x];
+    }
+    if (!has_tile) return;
+    // X L^T = B for row `lane` of this warp's tile
     for (int j = 0; j < NB; ++j) {
-        const int gj = k * NB + j;
-        double d = __shfl_sync(0xffffffffu, a[j], j);
-        double inv;
-        if (gj >= n) { d = 1.0; inv = 0.0; }                       // padding pivot: L_jj = 1, column below = 0
-        else if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; inv = 1.0; }
-        else { d = sqrt(d); inv = 1.0 / d; }
-        const double lrj = lane == j ? d : a[j] * inv;             // rows above the diagonal hold garbage: never read
-        a[j] = lrj;
-#pragma unroll
-        for (int c = j + 1; c < NB; ++c) { const double lcj = __shfl_sync(0xffffffffu, lrj, c); a[c] = fma(-lrj, lcj, a[c]); }
+        const double x = B[w][lane][j] * invd[j];
+        B[w][lane][j] = x;
+#pragma unroll 4
+        for (int c = j + 1; c < NB; ++c) B[w][lane][c] = fma(-x, L[c][j], B[w][lane][c]);
     }
-    if (i == k) {
-        if (bad && lane == 0) atomicAdd(fail, 1);
-        double* dst = A + (size_t)(k * NB + lane) * npad + k * NB;
-#pragma unroll
-        for (int c = 0; c < NB; ++c) if (c <= lane) dst[c] = a[c];
-        return;
-    }
-    // X L^T = B, row `lane` of B in registers; L[c][j] = register j of lane c
-    double x[NB];
-    double* tile = A + (size_t)(i * NB + lane) * npad + k * NB;
-#pragma unroll
-    for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(tile + c); x[c] = v.x; x[c + 1] = v.y; }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        const double ljj = __shfl_sync(0xffffffffu, a[j], j);
-        x[j] = x[j] / ljj;
-#pragma unroll
-        for (int c = j + 1; c < NB; ++c) { const double lcj = __shfl_sync(0xffffffffu, a[j], c); x[c] = fma(-x[j], lcj, x[c]); }
-    }
-#pragma unroll
-    for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(tile + c) = make_double2(x[c], x[c + 1]);
+    __syncwarp();
+    for (int r = 0; r < NB; ++r) A[(size_t)(i * NB + r) * npad + k * NB + lane] = B[w][r][lane];
 }
 
 // Trailing update step k: tile (i, j), k < j <= i:  A[i][j] -= A[i][k] A[j][k]^T.  blockDim = (32, 32), grid = T(T+1)/2.
@@ -560,7 +614,7 @@ __global__ void __launch_bounds__(1024) chol_update_kernel(double* __restrict__ 
 // Per 32-block (descending): warp 0 holds the diagonal tile COLUMN-wise in registers (lane c = column c) and solves it with
 // one shuffle-broadcast per unknown, while all other threads already have the loads of their part of the block row in
 // flight; then  y[c] -= sum_m L[kb*32+m][c] x_m  for the columns to the left.
-__global__ void __launch_bounds__(640) chol_backsolve_kernel(const double* __restrict__ A, int npad, int n, double* __restrict__ x) {
+__global__ void __launch_bounds__(640) chol_backsolve_kernel(const double* __restrict__ A, const double* __restrict__ dinv, int npad, int n, double* __restrict__ x) {
     extern __shared__ double y[];                 // [npad]
     const int tid = threadIdx.x, lane = tid & 31, nworkers = blockDim.x - 32;
     for (int i = tid; i < npad; i += blockDim.x) y[i] = i < n ? A[(size_t)n * npad + i] : 0.0;
@@ -577,10 +631,11 @@ __global__ void __launch_bounds__(640) chol_backsolve_kernel(const double* __res
         for (int m = 0; m < NB; ++m) reg[m] = src[(size_t)m * npad];
         if (solver) {
             double yc = y[kb * NB + lane];
+            const double di = dinv[kb * NB + lane];          // reciprocal pivot (0 for padding rows)
 #pragma unroll
             for (int jj = 0; jj < NB; ++jj) {
-                const int j = NB - 1 - jj, gj = kb * NB + j;
-                double xj = (lane == j) ? (gj < n ? yc / reg[j] : 0.0) : 0.0;
+                const int j = NB - 1 - jj;
+                double xj = (lane == j) ? yc * di : 0.0;
                 xj = __shfl_sync(0xffffffffu, xj, j);
                 if (lane == j) yc = xj; else if (lane < j) yc = fma(-reg[j], xj, yc);
             }
@@ -771,14 +826,14 @@ struct sfmb200_ba_problem {
     double* post;                     // [8] summed over ranks
     double* locals;                   // [8] identical on every rank
     unsigned long long* gmax_pt_bits; int* fail;   // fail[0] point blocks, fail[1] dense Cholesky
-    double* A; double* y_cf;
+    double* A; double* y_cf; double* dinv;
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
     bool have_scale = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // gather mode (K3c): Z per observation + per-camera-pair entry lists
     bool gather = true;
     double* Zbuf = nullptr; int32_t* pair_off = nullptr; int32_t* pair_blk = nullptr; uint2* pair_ent = nullptr;
-    int n_pairs_nonempty = 0, pair_splits = 1;
+    int n_pairs_nonempty = 0, pair_splits = 1, pair_nseg = 1;
     DevBuf gmem;
 };
 
@@ -878,8 +933,8 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
         if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev1, ctx->stream));
         if (P->gather && P->n_pairs_nonempty > 0) {
             if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev2, ctx->stream));
-            ba_pair_kernel<<<dim3(ceil_div(P->n_pairs_nonempty, PAIR_WARPS), P->pair_splits), PAIR_WARPS * 32, 0, ctx->stream>>>(
-                P->Zbuf, P->pair_off, P->pair_ent, P->n_pairs_nonempty, P->pair_splits, P->pair_blk, P->Sblk);
+            ba_pair_kernel<<<dim3(ceil_div(P->n_pairs_nonempty, PAIR_WARPS), P->pair_nseg * P->pair_splits), PAIR_WARPS * 32, 0, ctx->stream>>>(
+                P->Zbuf, P->pair_off, P->pair_ent, P->n_pairs_nonempty, P->pair_nseg, P->pair_splits, P->pair_blk, P->Sblk);
             SFM_LAUNCH_CHECK(ctx);
             if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev3, ctx->stream));
         }
@@ -895,11 +950,11 @@ static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, dou
                                                                                  opt->min_lm_diagonal, opt->max_lm_diagonal, P->A);
     SFM_LAUNCH_CHECK(ctx);
     for (int k = 0; k < nbk; ++k) {
-        chol_panel_kernel<<<ceil_div(nbk - k, 4), 128, 0, ctx->stream>>>(P->A, npad, P->n, k, nbk, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
+        chol_panel_kernel<<<std::max(1, ceil_div(nbk - k - 1, PANEL_WARPS)), PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, k, nbk, P->dinv, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
         const int T = nbk - k - 1;
         if (T > 0) { chol_update_kernel<<<T * (T + 1) / 2, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, k, nbk); SFM_LAUNCH_CHECK(ctx); }
     }
-    chol_backsolve_kernel<<<1, 640, sizeof(double) * npad, ctx->stream>>>(P->A, npad, P->n, P->y_cf); SFM_LAUNCH_CHECK(ctx);
+    chol_backsolve_kernel<<<1, 640, sizeof(double) * npad, ctx->stream>>>(P->A, P->dinv, npad, P->n, P->y_cf); SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
 
@@ -951,7 +1006,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     for (int i = 0; i < 3; ++i) { add(8 * n); add(24 * (size_t)np); }
     add(sizeof(CamDerived) * (size_t)nc); add(sizeof(CamDerived) * (size_t)nc);
     add(8 * n); add(24 * (size_t)np); add(96 * (size_t)np); add(8 * P->red_n); add(64 + 64 + 16 + 16);
-    add(8 * (size_t)P->npad * P->npad); add(8 * n); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
+    add(8 * (size_t)P->npad * P->npad); add(8 * n); add(8 * (size_t)P->npad); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
     cudaError_t e = P->mem.reserve(bytes);
     if (e != cudaSuccess) { delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
     Carver cv(P->mem.p);
@@ -964,7 +1019,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->red = cv.take<double>(P->red_n);
     P->Sblk = P->red; P->Scf = P->Sblk + 36 * nblk; P->Sff = P->Scf + 6 * (size_t)nc; P->rhs = P->Sff + 1; P->gcf = P->rhs + n; P->dcf = P->gcf + n; P->sums = P->dcf + n;
     P->post = cv.take<double>(8 + 8 + 2 + 2); P->locals = P->post + 8; P->gmax_pt_bits = (unsigned long long*)(P->locals + 8); P->fail = (int*)(P->locals + 10);
-    P->A = cv.take<double>((size_t)P->npad * P->npad); P->y_cf = cv.take<double>(n);
+    P->A = cv.take<double>((size_t)P->npad * P->npad); P->y_cf = cv.take<double>(n); P->dinv = cv.take<double>(P->npad);
     int32_t* obs_pt = cv.take<int32_t>(nobs); int* cnt = cv.take<int>(2 * (size_t)(nc + 1)); int* cursor = cnt + nc + 1;
 
     cudaStream_t st = ctx->stream;
@@ -996,26 +1051,29 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         for (int p = 0; p < np; ++p) { const long long k = pt_off[p + 1] - pt_off[p]; E += k * (k - 1) / 2; }
         if (E >= (1LL << 31) - 1024) P->gather = false;          // int32 offsets
         if (P->gather && E > 0) {
-            const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + Carver::pad(4 * (nblk + 1)) * 2 + Carver::pad(8 * (size_t)E) + Carver::pad(4 * nblk) * 2 + 4096;
+            // point-range segments: ~24 MB of Zbuf each, so that one segment stays L2-resident while it is read ~7 times
+            const int nseg = (int)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (24LL << 20) - 1) / (24LL << 20)));
+            const size_t nkeys = nblk * (size_t)nseg;
+            const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + Carver::pad(4 * (nkeys + 1)) + Carver::pad(4 * (nblk + 1)) + Carver::pad(8 * (size_t)E) +
+                              Carver::pad(4 * nkeys) * 2 + 4096;
             CRT(P->gmem.reserve(gb));
             Carver gc(P->gmem.p);
-            P->Zbuf = gc.take<double>(18 * (size_t)nobs); P->pair_off = gc.take<int32_t>(nblk + 1); P->pair_blk = gc.take<int32_t>(nblk + 1);
+            P->Zbuf = gc.take<double>(18 * (size_t)nobs); P->pair_off = gc.take<int32_t>(nkeys + 1); P->pair_blk = gc.take<int32_t>(nblk + 1);
             P->pair_ent = gc.take<uint2>((size_t)E);
-            int* pcnt = gc.take<int>(nblk); int* pcur = gc.take<int>(nblk); int* d_nne = gc.take<int>(4);
-            const int use_smem = nblk * 4 <= 40 * 1024;
-            CRT(cudaMemsetAsync(pcnt, 0, 4 * nblk, st));
-            pair_count_kernel<<<ceil_div(np, 256), 256, use_smem ? nblk * 4 : 0, st>>>(P->pt_off, P->obs_cam, np, nc, (int)nblk, use_smem, pcnt);
-            pair_scan_kernel<<<1, 1024, 0, st>>>(pcnt, (int)nblk, P->pair_off, P->pair_blk, pcur, d_nne);
-            pair_fill_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, P->obs_cam, np, nc, pcur, P->pair_ent);
-            ctx->launches += 3;
+            int* pcnt = gc.take<int>(nkeys); int* pcur = gc.take<int>(nkeys); int* d_nne = gc.take<int>(4);
+            CRT(cudaMemsetAsync(pcnt, 0, 4 * nkeys, st));
+            pair_count_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, P->obs_cam, np, nc, nseg, pcnt);
+            pair_scan_kernel<<<1, 1024, 0, st>>>(pcnt, (int)nkeys, P->pair_off, pcur);
+            pair_compact_kernel<<<1, 1024, 0, st>>>(P->pair_off, (int)nblk, nseg, P->pair_blk, d_nne);
+            pair_fill_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, P->obs_cam, np, nc, nseg, pcur, P->pair_ent);
+            ctx->launches += 4;
             CRT(cudaGetLastError());
             int nne = 0;
             CRT(cudaMemcpyAsync(&nne, d_nne, 4, cudaMemcpyDeviceToHost, st));
             CRT(cudaStreamSynchronize(st));
-            P->n_pairs_nonempty = nne;
+            P->n_pairs_nonempty = nne; P->pair_nseg = nseg;
             P->pair_splits = std::max(1, std::min(64, ceil_div(16 * ctx->sm_count, std::max(1, nne))));
         } else if (P->gather) {
-            P->gather = E > 0 ? P->gather : true;    // no pairs at all: nothing to accumulate off the diagonal
             CRT(P->gmem.reserve(Carver::pad(8 * 18 * (size_t)std::max(nobs, 1)) + 256));
             P->Zbuf = (double*)P->gmem.p;
         }
