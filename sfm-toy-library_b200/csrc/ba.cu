@@ -320,6 +320,15 @@ constexpr int PAIR_WARPS = 4;
 // pair_off is indexed by key = blk * nseg + seg (seg = point-range segment): the grid walks the segments in the slow
 // (y) dimension, LAST segment first, so that all resident warps read the same ~24 MB slice of Zbuf -- which then lives
 // in L2 (the tail of Zbuf is still L2-resident from the point kernel that just wrote it).
+// The accumulation  S[ci,cj] -= sum_e Z_i(e) Z_j(e)^T  is a (6 x 3E)(3E x 6) product in fp64: it runs on the FP64
+// tensor pipe as one  mma.sync.m8n8k4.f64  per entry (6x6x3 padded to 8x8x4).  The operand fragments want lane l to hold
+// element (l>>2, l&3) of the 8x4 tile, i.e. double number (l>>2)*3 + (l&3) of the 18-double Z record: one coalesced
+// 8-byte load per lane per operand (18 of 32 lanes active, one 144-byte record = at most two 128-byte lines), instead
+// of 18 uncoalesced 16-byte loads per lane in a lane-per-entry SIMT formulation (which was L1-wavefront bound).
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+constexpr int PAIR_UNROLL = 8;
 __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
                                                                    const uint2* __restrict__ pair_ent, int n_nonempty, int nseg, int splits,
                                                                    const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk) {
@@ -331,27 +340,37 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* 
     const int start = pair_off[(size_t)blk * nseg + seg], len = pair_off[(size_t)blk * nseg + seg + 1] - start;
     const int b0 = start + (int)((long long)len * sp / splits), b1 = start + (int)((long long)len * (sp + 1) / splits);
     if (b1 <= b0) return;
-    double acc[36];
+    const int fr = lane >> 2, fc = lane & 3;
+    const bool valid = fr < 6 && fc < 3;
+    const int fidx = valid ? fr * 3 + fc : 0;
+    double c0[PAIR_UNROLL], c1[PAIR_UNROLL];
 #pragma unroll
-    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-    for (int e = b0 + lane; e < b1; e += 32) {
-        const uint2 ent = pair_ent[e];
-        const double2* pi = reinterpret_cast<const double2*>(Zbuf + (size_t)ent.x * 18);
-        const double2* pj = reinterpret_cast<const double2*>(Zbuf + (size_t)ent.y * 18);
-        double zi[18], zj[18];
+    for (int u = 0; u < PAIR_UNROLL; ++u) { c0[u] = 0.0; c1[u] = 0.0; }
+    int e = b0;
+    for (; e + PAIR_UNROLL <= b1; e += PAIR_UNROLL) {
+        double a[PAIR_UNROLL], b[PAIR_UNROLL];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) { const double2 a = pi[t], b = pj[t]; zi[2 * t] = a.x; zi[2 * t + 1] = a.y; zj[2 * t] = b.x; zj[2 * t + 1] = b.y; }
+        for (int u = 0; u < PAIR_UNROLL; ++u) {
+            const uint2 ent = __ldg(pair_ent + e + u);                // same address in every lane: one broadcast transaction
+            const double va = __ldg(Zbuf + (size_t)ent.x * 18 + fidx), vb = __ldg(Zbuf + (size_t)ent.y * 18 + fidx);
+            a[u] = valid ? va : 0.0; b[u] = valid ? vb : 0.0;
+        }
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = 0; b < 6; ++b)
-                acc[a * 6 + b] = fma(zi[a * 3], zj[b * 3], fma(zi[a * 3 + 1], zj[b * 3 + 1], fma(zi[a * 3 + 2], zj[b * 3 + 2], acc[a * 6 + b])));
+        for (int u = 0; u < PAIR_UNROLL; ++u) dmma_m8n8k4(c0[u], c1[u], a[u], b[u]);
     }
-    double* dst = Sblk + (size_t)blk * 36;
+    for (; e < b1; ++e) {
+        const uint2 ent = __ldg(pair_ent + e);
+        const double va = __ldg(Zbuf + (size_t)ent.x * 18 + fidx), vb = __ldg(Zbuf + (size_t)ent.y * 18 + fidx);
+        dmma_m8n8k4(c0[0], c1[0], valid ? va : 0.0, valid ? vb : 0.0);
+    }
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 36; ++i) {
-        const double sum = warp_sum(acc[i]);
-        if (lane == (i & 31)) red_add(dst + i, -sum);
+    for (int u = 0; u < PAIR_UNROLL; ++u) { s0 += c0[u]; s1 += c1[u]; }
+    // accumulator fragment: row = lane>>2, columns 2*(lane&3) and 2*(lane&3)+1
+    const int cc = 2 * fc;
+    if (fr < 6 && cc < 6) {
+        double* dst = Sblk + (size_t)blk * 36 + fr * 6 + cc;
+        red_add(dst, -s0); red_add(dst + 1, -s1);
     }
 }
 
@@ -538,40 +557,56 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
     A[(size_t)r * npad + c] = val;
 }
 
-// Panel step k.  CTA = 4 warps: warp 0 factors the 32x32 diagonal tile in shared memory (lane r owns row r; compact
-// loops -- a fully unrolled register version is ~100 KB of straight-line code and instruction-fetch bound), every warp
-// then solves one sub-diagonal tile against it, A[i][k] <- A[i][k] L_kk^-T, row-per-lane, no barrier in the solve.
+// Panel step k.  CTA = 4 warps.  Warp 0 factors the 32x32 diagonal tile with lane r holding row r in 32 registers.
+// The pivot loop stays ROLLED (a fully unrolled version is ~100 KB of straight-line code and instruction-fetch bound;
+// a shared-memory version is a chain of dependent LDS->DFMA->STS steps): after every pivot the register row is rotated
+// by one, so the current column is always a[0] and every access is statically indexed, while the 31 trailing updates of
+// a pivot are independent shuffle+FMA pairs.  The factor goes to shared memory; every warp then solves one sub-diagonal
+// tile against it, A[i][k] <- A[i][k] L_kk^-T, with the same rotation trick (row per lane, L[c][j] as LDS broadcasts).
 // Every CTA factors the diagonal tile redundantly (11 k FMA) instead of waiting on another CTA; CTA 0 writes it back
-// together with the reciprocal pivots (dinv) the back-substitution uses.  Pivots with global index >= n are forced to 1
+// together with the reciprocal pivots (dinv) for the back-substitution.  Pivots with global index >= n are forced to 1
 // (augmented rhs row / padding rows).
 constexpr int PANEL_WARPS = 4;
 __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk,
                                                                       double* __restrict__ dinv, int* __restrict__ fail) {
     __shared__ double L[NB][NB + 1];
-    __shared__ double B[PANEL_WARPS][NB][NB + 1];
     __shared__ double invd[NB];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = k + 1 + blockIdx.x * PANEL_WARPS + w;
     const bool has_tile = i < nbk;
-    for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; L[r][c] = A[(size_t)(k * NB + r) * npad + k * NB + c]; }
-    if (has_tile)
-        for (int r = 0; r < NB; ++r) B[w][r][lane] = A[(size_t)(i * NB + r) * npad + k * NB + lane];
-    __syncthreads();
+    double x[NB];                                     // this warp's sub-diagonal tile, row `lane`
+    if (has_tile) {
+        const double* src = A + (size_t)(i * NB + lane) * npad + k * NB;
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); x[c] = v.x; x[c + 1] = v.y; }
+    }
     if (w == 0) {
+        double a[NB];
+        const double* src = A + (size_t)(k * NB + lane) * npad + k * NB;
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); a[c] = v.x; a[c + 1] = v.y; }
         bool bad = false;
+#pragma unroll 1
         for (int j = 0; j < NB; ++j) {
             const int gj = k * NB + j;
-            const double d = L[j][j];
+            const double d = __shfl_sync(0xffffffffu, a[0], j);        // a[0] == element (lane, j)
             double ljj, inv;
             if (gj >= n) { ljj = 1.0; inv = 0.0; }
             else if (!(d > 0.0) || !isfinite(d)) { bad = true; ljj = 1.0; inv = 1.0; }
             else { inv = rsqrt(d); ljj = d * inv; }
-            double lrj = 0.0;
-            if (lane > j) { lrj = L[lane][j] * inv; L[lane][j] = lrj; }
-            else if (lane == j) { L[j][j] = ljj; invd[j] = inv; }
-            __syncwarp();
-            for (int c = j + 1; c <= lane; ++c) L[lane][c] = fma(-lrj, L[c][j], L[lane][c]);
-            __syncwarp();
+            const double lrj = lane == j ? ljj : a[0] * inv;           // rows above the diagonal hold garbage: never read
+            if (lane == j) invd[j] = inv;
+            if (lane >= j) L[lane][j] = lrj;
+            a[0] = lrj;
+#pragma unroll
+            for (int p = 1; p < NB; ++p) {                             // position p == column j+p (wraps to finished columns)
+                const double lcj = __shfl_sync(0xffffffffu, lrj, (j + p) & 31);
+                if (j + p < NB) a[p] = fma(-lrj, lcj, a[p]);
+            }
+            const double t = a[0];
+#pragma unroll
+            for (int p = 0; p < NB - 1; ++p) a[p] = a[p + 1];
+            a[NB - 1] = t;
         }
         if (bad && lane == 0 && blockIdx.x == 0) atomicAdd(fail, 1);
     }
@@ -581,15 +616,20 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __
         if (threadIdx.x < NB) dinv[k * NB + threadIdx.x] = invd[threadIdx.x];
     }
     if (!has_tile) return;
-    // X L^T = B for row `lane` of this warp's tile
+    // X L^T = B for row `lane`: x[0] is the current column
+#pragma unroll 1
     for (int j = 0; j < NB; ++j) {
-        const double x = B[w][lane][j] * invd[j];
-        B[w][lane][j] = x;
-#pragma unroll 4
-        for (int c = j + 1; c < NB; ++c) B[w][lane][c] = fma(-x, L[c][j], B[w][lane][c]);
+        const double xj = x[0] * invd[j];
+#pragma unroll
+        for (int p = 1; p < NB; ++p)
+            if (j + p < NB) x[p] = fma(-xj, L[j + p][j], x[p]);
+#pragma unroll
+        for (int p = 0; p < NB - 1; ++p) x[p] = x[p + 1];
+        x[NB - 1] = xj;
     }
-    __syncwarp();
-    for (int r = 0; r < NB; ++r) A[(size_t)(i * NB + r) * npad + k * NB + lane] = B[w][r][lane];
+    double* dst = A + (size_t)(i * NB + lane) * npad + k * NB;
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(x[c], x[c + 1]);
 }
 
 // Trailing update step k: tile (i, j), k < j <= i:  A[i][j] -= A[i][k] A[j][k]^T.  blockDim = (32, 32), grid = T(T+1)/2.
