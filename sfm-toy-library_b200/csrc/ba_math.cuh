@@ -109,17 +109,24 @@ SFM_HD void obs_eval(const CamDerived& d, const double* X, double f, double ox, 
 
 // Cholesky U = C C^T of a symmetric 3x3 (xx xy xz yy yz zz) and M = C^-1 (lower: m00 m10 m11 m20 m21 m22).
 // Returns false when U is not positive definite.
+SFM_HD double sfm_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);                // one MUFU + Newton steps instead of a sqrt followed by a division
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 SFM_HD bool chol3_inverse(const double* U, double* M) {
     if (!(U[0] > 0.0)) return false;
-    const double l00 = sqrt(U[0]), i00 = 1.0 / l00;
+    const double i00 = sfm_rsqrt(U[0]);
     const double l10 = U[1] * i00, l20 = U[2] * i00;
     const double d1 = U[3] - l10 * l10;
     if (!(d1 > 0.0)) return false;
-    const double l11 = sqrt(d1), i11 = 1.0 / l11;
+    const double i11 = sfm_rsqrt(d1);
     const double l21 = (U[4] - l20 * l10) * i11;
     const double d2 = U[5] - l20 * l20 - l21 * l21;
     if (!(d2 > 0.0)) return false;
-    const double i22 = 1.0 / sqrt(d2);
+    const double i22 = sfm_rsqrt(d2);
     M[0] = i00;
     M[1] = -l10 * i00 * i11; M[2] = i11;
     M[3] = -(l20 * i00 + l21 * M[1]) * i22; M[4] = -l21 * i11 * i22; M[5] = i22;
