@@ -567,6 +567,7 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
 // together with the reciprocal pivots (dinv) for the back-substitution.  Pivots with global index >= n are forced to 1
 // (augmented rhs row / padding rows).
 constexpr int PANEL_WARPS = 4;
+constexpr int PANEL_ROT = 4;      // pivots per rotation of the register row
 __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk,
                                                                       double* __restrict__ dinv, int* __restrict__ fail) {
     __shared__ double L[NB][NB + 1];
@@ -587,26 +588,32 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __
         for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); a[c] = v.x; a[c + 1] = v.y; }
         bool bad = false;
 #pragma unroll 1
-        for (int j = 0; j < NB; ++j) {
-            const int gj = k * NB + j;
-            const double d = __shfl_sync(0xffffffffu, a[0], j);        // a[0] == element (lane, j)
-            double ljj, inv;
-            if (gj >= n) { ljj = 1.0; inv = 0.0; }
-            else if (!(d > 0.0) || !isfinite(d)) { bad = true; ljj = 1.0; inv = 1.0; }
-            else { inv = rsqrt(d); ljj = d * inv; }
-            const double lrj = lane == j ? ljj : a[0] * inv;           // rows above the diagonal hold garbage: never read
-            if (lane == j) invd[j] = inv;
-            if (lane >= j) L[lane][j] = lrj;
-            a[0] = lrj;
+        for (int jb = 0; jb < NB; jb += PANEL_ROT) {
 #pragma unroll
-            for (int p = 1; p < NB; ++p) {                             // position p == column j+p (wraps to finished columns)
-                const double lcj = __shfl_sync(0xffffffffu, lrj, (j + p) & 31);
-                if (j + p < NB) a[p] = fma(-lrj, lcj, a[p]);
+            for (int u = 0; u < PANEL_ROT; ++u) {                      // pivot j = jb + u, its column sits in a[u]
+                const int j = jb + u, gj = k * NB + j;
+                const double d = __shfl_sync(0xffffffffu, a[u], j);
+                double ljj, inv;
+                if (gj >= n) { ljj = 1.0; inv = 0.0; }
+                else if (!(d > 0.0) || !isfinite(d)) { bad = true; ljj = 1.0; inv = 1.0; }
+                else { inv = rsqrt(d); ljj = d * inv; }
+                const double lrj = lane == j ? ljj : a[u] * inv;       // rows above the diagonal hold garbage: never read
+                if (lane == j) invd[j] = inv;
+                if (lane >= j) L[lane][j] = lrj;
+                a[u] = lrj;
+#pragma unroll
+                for (int p = u + 1; p < NB; ++p) {                     // position p == column jb+p (wraps to finished columns)
+                    const double lcj = __shfl_sync(0xffffffffu, lrj, (jb + p) & 31);
+                    if (jb + p < NB) a[p] = fma(-lrj, lcj, a[p]);
+                }
             }
-            const double t = a[0];
+            double t[PANEL_ROT];
 #pragma unroll
-            for (int p = 0; p < NB - 1; ++p) a[p] = a[p + 1];
-            a[NB - 1] = t;
+            for (int u = 0; u < PANEL_ROT; ++u) t[u] = a[u];
+#pragma unroll
+            for (int p = 0; p < NB - PANEL_ROT; ++p) a[p] = a[p + PANEL_ROT];
+#pragma unroll
+            for (int u = 0; u < PANEL_ROT; ++u) a[NB - PANEL_ROT + u] = t[u];
         }
         if (bad && lane == 0 && blockIdx.x == 0) atomicAdd(fail, 1);
     }
@@ -618,14 +625,23 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __
     if (!has_tile) return;
     // X L^T = B for row `lane`: x[0] is the current column
 #pragma unroll 1
-    for (int j = 0; j < NB; ++j) {
-        const double xj = x[0] * invd[j];
+    for (int jb = 0; jb < NB; jb += PANEL_ROT) {
 #pragma unroll
-        for (int p = 1; p < NB; ++p)
-            if (j + p < NB) x[p] = fma(-xj, L[j + p][j], x[p]);
+        for (int u = 0; u < PANEL_ROT; ++u) {
+            const int j = jb + u;
+            const double xj = x[u] * invd[j];
+            x[u] = xj;
 #pragma unroll
-        for (int p = 0; p < NB - 1; ++p) x[p] = x[p + 1];
-        x[NB - 1] = xj;
+            for (int p = u + 1; p < NB; ++p)
+                if (jb + p < NB) x[p] = fma(-xj, L[jb + p][j], x[p]);
+        }
+        double t[PANEL_ROT];
+#pragma unroll
+        for (int u = 0; u < PANEL_ROT; ++u) t[u] = x[u];
+#pragma unroll
+        for (int p = 0; p < NB - PANEL_ROT; ++p) x[p] = x[p + PANEL_ROT];
+#pragma unroll
+        for (int u = 0; u < PANEL_ROT; ++u) x[NB - PANEL_ROT + u] = t[u];
     }
     double* dst = A + (size_t)(i * NB + lane) * npad + k * NB;
 #pragma unroll
@@ -755,8 +771,10 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, c
         const double* pb = v.ptblk + (size_t)p * 12;
         const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
         const double zg[3] = {pb[6], pb[7], pb[8]};
-        // pass 1: t = sum_o Jp^T (Jc y_c + Jf y_f)
+        // pass 1: t = sum_o Jp^T (Jc y_c + Jf y_f).  For the lane's first observation the pieces pass 2 needs
+        // (m' = Jc y_c + Jf y_f, Jp, r) stay in registers, so the Jacobian is evaluated once per observation.
         double t[3] = {0, 0, 0};
+        double k_m0 = 0, k_m1 = 0, k_r0 = 0, k_r1 = 0, k_Jp[6] = {0, 0, 0, 0, 0, 0};
         for (int j = gl; j < k; j += G) {
             const int o = o0 + j, c = v.obs_cam[o];
             ObsJ J;
@@ -766,6 +784,11 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, c
             for (int a = 0; a < 6; ++a) { const double yc = y_cf[6 * c + a]; m0 += J.Jc[a] * yc; m1 += J.Jc[6 + a] * yc; }
 #pragma unroll
             for (int a = 0; a < 3; ++a) t[a] += J.Jp[a] * m0 + J.Jp[3 + a] * m1;
+            if (j == gl) {
+                k_m0 = m0; k_m1 = m1; k_r0 = J.r[0]; k_r1 = J.r[1];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) k_Jp[a] = J.Jp[a];
+            }
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) t[a] = group_sum<G>(t[a], gmask);
@@ -783,15 +806,22 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, c
         for (int j = gl; j < k; j += G) {
             const int o = o0 + j, c = v.obs_cam[o];
             const float2 xy = v.obs_xy[o];
-            ObsJ J;
-            eval_scaled(v.camd[c], X, f, xy, v.scale_cf + 6 * c, sp, sf, J);
-            double m0 = J.Jf[0] * yf, m1 = J.Jf[1] * yf;
+            double m0, m1, r0, r1;
+            if (j == gl) {
+                m0 = k_m0; m1 = k_m1; r0 = k_r0; r1 = k_r1;
 #pragma unroll
-            for (int a = 0; a < 6; ++a) { const double yc = y_cf[6 * c + a]; m0 += J.Jc[a] * yc; m1 += J.Jc[6 + a] * yc; }
+                for (int a = 0; a < 3; ++a) { m0 += k_Jp[a] * yp[a]; m1 += k_Jp[3 + a] * yp[a]; }
+            } else {
+                ObsJ J;
+                eval_scaled(v.camd[c], X, f, xy, v.scale_cf + 6 * c, sp, sf, J);
+                m0 = J.Jf[0] * yf; m1 = J.Jf[1] * yf; r0 = J.r[0]; r1 = J.r[1];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { m0 += J.Jp[a] * yp[a]; m1 += J.Jp[3 + a] * yp[a]; }
+                for (int a = 0; a < 6; ++a) { const double yc = y_cf[6 * c + a]; m0 += J.Jc[a] * yc; m1 += J.Jc[6 + a] * yc; }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { m0 += J.Jp[a] * yp[a]; m1 += J.Jp[3 + a] * yp[a]; }
+            }
             m0 = -m0; m1 = -m1;
-            acc_m += m0 * (J.r[0] + 0.5 * m0) + m1 * (J.r[1] + 0.5 * m1);
+            acc_m += m0 * (r0 + 0.5 * m0) + m1 * (r1 + 0.5 * m1);
             double rc[2];
             obs_residual(camd_c[c], Xc, fc, (double)xy.x, (double)xy.y, rc);
             acc_cc += rc[0] * rc[0] + rc[1] * rc[1];

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Secondary metrics of SURVEY.md section 8(d): all-pairs matching (BASELINE.json config 4, reference-faithful Hamming)
+and batched triangulation (config 5), each with resident-input device timing (CUDA events on the library stream),
+the host-buffer C-ABI call, a roofline object and a CPU baseline (cv2 = the OpenCV code the reference calls).
+Prints one JSON line per stage.  Usage: python tools/bench_stages.py [--images 50] [--features 5000] [--points 1000000]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=50)
+    ap.add_argument("--features", type=int, default=5000)
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    from sfm_toy_library_b200 import capi, synth
+    torch.cuda.set_device(0)
+    ctx = capi.Context(0)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    hbm, src = peaks()
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, reps):
+        ts = []
+        for _ in range(reps + 1):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            ctx.synchronize(); e0.record(stream); fn(); e1.record(stream); ctx.synchronize(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.mean(ts[1:]))
+
+    # ---------------------------------------------------------------- matching, config 4
+    descs = synth.make_descriptor_set(args.images, n=args.features)
+    pairs = [(i, j) for i in range(args.images) for j in range(i + 1, args.images)]
+    ds = ctx.descriptor_set(descs)
+    rows = args.features * len(pairs)
+    dq = torch.empty(rows, dtype=torch.int32, device="cuda"); dt_ = torch.empty(rows, dtype=torch.int32, device="cuda")
+    dd = torch.empty(rows, dtype=torch.float32, device="cuda"); dst = torch.empty(len(pairs) + 1, dtype=torch.int32, device="cuda")
+    dtot = torch.empty(1, dtype=torch.int64, device="cuda")
+    l0 = ctx.kernel_launches
+    ms = timed(lambda: ds.match_pairs_device(pairs, dq.data_ptr(), dt_.data_ptr(), dd.data_ptr(), dst.data_ptr(), dtot.data_ptr()), args.reps)
+    launches = (ctx.kernel_launches - l0) // (args.reps + 1)
+    t0 = time.perf_counter(); res = ds.match_pairs(pairs); e2e_s = time.perf_counter() - t0
+    n_matches = int(sum(len(r[0]) for r in res))
+    dist_evals = float(args.features) ** 2 * len(pairs)
+    import cv2
+    cpu = {}
+    for thr in (1, os.cpu_count() or 1):
+        cv2.setNumThreads(thr)
+        m = cv2.DescriptorMatcher_create("BruteForce-Hamming")
+        npairs_cpu = 2 if thr == 1 else 8
+        t0 = time.perf_counter()
+        for (i, j) in pairs[:npairs_cpu]:
+            m.knnMatch(descs[i], descs[j], 2)
+        cpu[thr] = npairs_cpu / (time.perf_counter() - t0)
+    print(json.dumps({"stage": "match", "metric": "image pairs matched per second (5000x5000 ORB-256, knn2 + ratio)", "value": len(pairs) / (ms * 1e-3),
+                      "unit": "pairs/s", "ms_per_step": ms, "pairs": len(pairs), "features": args.features, "matches": n_matches, "dtype": "u8/int",
+                      "descriptor_pairs_per_s": dist_evals / (ms * 1e-3), "gpu_launches": int(launches),
+                      "e2e": {"value": len(pairs) / e2e_s, "unit": "pairs/s", "note": "sfmb200_match_pairs, host result buffers, descriptors already resident"},
+                      "roofline": {"bound": "alu (POPC pipe)", "note": "bytes are negligible (8 MB of descriptors); the XOR/POPC kernel is bound by the 16 lanes/clk/SM POPC pipe",
+                                   "popc_per_s": dist_evals * 8 / (ms * 1e-3), "peak_popc_per_s": 148 * 16 * 1.965e9, "frac": dist_evals * 8 / (ms * 1e-3) / (148 * 16 * 1.965e9)},
+                      "cpu_baseline": {"value": cpu[max(cpu)], "unit": "pairs/s", "cores": max(cpu), "kind": "reference", "single_thread_pairs_per_s": cpu[1],
+                                       "sample": "cv2 BruteForce-Hamming knnMatch(k=2) on the first pairs of the same set"}}), flush=True)
+    ds.close()
+
+    # ---------------------------------------------------------------- triangulation, config 5
+    p = synth.make_triangulation_problem(args.points, seed=0)
+    m = args.points
+    dl = torch.from_numpy(p["ptsL"]).cuda(); dr = torch.from_numpy(p["ptsR"]).cuda()
+    dX = torch.empty(m * 3, dtype=torch.float32, device="cuda"); dk = torch.empty(m, dtype=torch.uint8, device="cuda"); dn = torch.empty(1, dtype=torch.int32, device="cuda")
+    ms = timed(lambda: ctx.triangulate_device(p["K"], p["Pl"], p["Pr"], dl.data_ptr(), dr.data_ptr(), None, None, m, dX.data_ptr(), dk.data_ptr(), dn.data_ptr()), args.reps)
+    t0 = time.perf_counter(); X, keep, nk = ctx.triangulate(p["K"], p["Pl"], p["Pr"], p["ptsL"], p["ptsR"]); e2e_s = time.perf_counter() - t0
+    from oracle import cv2_reference as ref
+    cv2.setNumThreads(os.cpu_count() or 1)
+    ns = min(m, 100_000)
+    t0 = time.perf_counter(); ref.triangulate_views(p["K"], p["Pl"], p["Pr"], p["ptsL"][:ns], p["ptsR"][:ns]); cpu_s = time.perf_counter() - t0
+    abytes = 29 * m
+    print(json.dumps({"stage": "triangulate", "metric": "point pairs triangulated per second (DLT + reprojection filter)", "value": m / (ms * 1e-3), "unit": "points/s",
+                      "ms_per_step": ms, "points": m, "kept": int(nk), "dtype": "f64 inside, f32 in/out", "gpu_launches": 1,
+                      "e2e": {"value": m / e2e_s, "unit": "points/s", "h2d_bytes_per_step": 16 * m, "d2h_bytes_per_step": 13 * m, "note": "sfmb200_triangulate with host buffers"},
+                      "roofline": {"bound": "hbm", "achieved": abytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": abytes / (ms * 1e-3) / 1e9 / hbm,
+                                   "peak_source": src, "algorithmic_bytes": abytes, "note": "fp64 SVD bound in practice"},
+                      "cpu_baseline": {"value": ns / cpu_s, "unit": "points/s", "cores": 1, "kind": "reference",
+                                       "sample": f"cv2 replay of triangulateViews on the first {ns} points (cv::triangulatePoints is serial)"}}), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
