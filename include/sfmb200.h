@@ -167,6 +167,14 @@ int sfmb200_ba_problem_download(sfmb200_ba_problem* prob, double* cams6, double*
 int sfmb200_ba_problem_reduced_system(sfmb200_ba_problem* prob, const sfmb200_ba_options* opt, double radius,
                                       double* S, double* rhs, double* grad_cf, double* cost);
 
+/* Multi-GPU exchange over PEER MEMORY instead of NCCL: every rank exports the CUDA-IPC handle of its problem's exchange
+ * buffer, the host all-gathers the handles (rank order) and every rank attaches them.  From then on the reduced camera
+ * system is summed by kernels that load the peers' partial buffers directly over NVLink.  Needs sfmb200_comm_init
+ * (rank / size) first; all ranks must create their problems before anyone attaches. */
+#define SFMB200_IPC_HANDLE_BYTES 64
+int sfmb200_ba_problem_ipc_handle(sfmb200_ba_problem* prob, uint8_t* handle /* [SFMB200_IPC_HANDLE_BYTES] */);
+int sfmb200_ba_problem_ipc_attach(sfmb200_ba_problem* prob, const uint8_t* handles /* [nranks * SFMB200_IPC_HANDLE_BYTES] */);
+
 /* one-shot: create + run + download + destroy (what the adjustBundle shim calls). cams6/pts3/focal are updated in
  * place with the final iterate whatever the termination type; the CONVERGENCE-only write-back rule is the caller's. */
 int sfmb200_ba_solve(sfmb200_ctx* ctx, const sfmb200_ba_options* opt, int nc, int np, int nobs,

@@ -274,6 +274,16 @@ class BAProblem:
         except Exception:
             pass
 
+    def ipc_handle(self):
+        buf = (C.c_uint8 * 64)()
+        self.ctx._check(lib().sfmb200_ba_problem_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def ipc_attach(self, handles):
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.ctx._check(lib().sfmb200_ba_problem_ipc_attach(self._h, buf))
+
     def reset(self):
         self.ctx._check(lib().sfmb200_ba_problem_reset(self._h))
 

@@ -557,95 +557,113 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
     A[(size_t)r * npad + c] = val;
 }
 
-// Panel step k.  CTA = 4 warps.  Warp 0 factors the 32x32 diagonal tile with lane r holding row r in 32 registers.
-// The pivot loop stays ROLLED (a fully unrolled version is ~100 KB of straight-line code and instruction-fetch bound;
-// a shared-memory version is a chain of dependent LDS->DFMA->STS steps): after every pivot the register row is rotated
-// by one, so the current column is always a[0] and every access is statically indexed, while the 31 trailing updates of
-// a pivot are independent shuffle+FMA pairs.  The factor goes to shared memory; every warp then solves one sub-diagonal
-// tile against it, A[i][k] <- A[i][k] L_kk^-T, with the same rotation trick (row per lane, L[c][j] as LDS broadcasts).
-// Every CTA factors the diagonal tile redundantly (11 k FMA) instead of waiting on another CTA; CTA 0 writes it back
-// together with the reciprocal pivots (dinv) for the back-substitution.  Pivots with global index >= n are forced to 1
-// (augmented rhs row / padding rows).
+// Panel step k.  CTA = 4 warps = 128 threads; every CTA factors the 32x32 diagonal tile itself (11 k FMA, cheaper than a
+// cross-CTA dependency) and solves up to four sub-diagonal tiles against it.  A single warp working through the tile is
+// issue-latency bound (measured: ~5 k dependent instructions at IPC 0.09 = 26 us), so the work is restructured:
+//   phase 1  factorisation, lane = row, the 32 columns dealt round-robin to the 4 warps (8 registers each).  Per pivot the
+//            owning warp produces the column (shuffle, rsqrt, scale) and publishes it in shared memory; after ONE barrier
+//            every warp applies it to its 8 columns (8 broadcast-LDS + FMA instead of 31 in one warp).  The register set is
+//            rotated every 4 pivots so that the loop stays rolled with static register indices.
+//   phase 2  warp 0 inverts the factor by forward substitution on the identity (lane = column of L^-1).
+//   phase 3  each warp: X = B L^-T as 32 dot products per row against broadcast rows of L^-1 -- no dependency chain,
+//            instead of a 32-step triangular solve.
+// CTA 0 writes the factor back together with the reciprocal pivots (dinv) the back-substitution uses.  Pivots with
+// global index >= n are forced to 1 with a zero column (augmented rhs row / padding rows).
 constexpr int PANEL_WARPS = 4;
-constexpr int PANEL_ROT = 4;      // pivots per rotation of the register row
 __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk,
                                                                       double* __restrict__ dinv, int* __restrict__ fail) {
-    __shared__ double L[NB][NB + 1];
+    __shared__ double Ls[NB][NB + 1];          // diagonal tile, then its factor (lower)
+    __shared__ double Li[NB][NB + 1];          // inverse of the factor (lower), also the staging tile for phase 3 output
+    __shared__ double colbuf[2][NB];
     __shared__ double invd[NB];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = k + 1 + blockIdx.x * PANEL_WARPS + w;
     const bool has_tile = i < nbk;
-    double x[NB];                                     // this warp's sub-diagonal tile, row `lane`
+    double b[NB];                               // this warp's sub-diagonal tile, row `lane`
     if (has_tile) {
         const double* src = A + (size_t)(i * NB + lane) * npad + k * NB;
 #pragma unroll
-        for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); x[c] = v.x; x[c + 1] = v.y; }
+        for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); b[c] = v.x; b[c + 1] = v.y; }
     }
-    if (w == 0) {
-        double a[NB];
-        const double* src = A + (size_t)(k * NB + lane) * npad + k * NB;
+    for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; Ls[r][c] = A[(size_t)(k * NB + r) * npad + k * NB + c]; }
+    __syncthreads();
+    // ---- phase 1: col[q] = column 4*(q + rot) + w of row `lane`  (rot = number of rotations so far)
+    double col[NB / PANEL_WARPS];
 #pragma unroll
-        for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); a[c] = v.x; a[c + 1] = v.y; }
-        bool bad = false;
+    for (int q = 0; q < NB / PANEL_WARPS; ++q) col[q] = Ls[lane][PANEL_WARPS * q + w];
+    bool bad = false;
 #pragma unroll 1
-        for (int jb = 0; jb < NB; jb += PANEL_ROT) {
+    for (int jb = 0; jb < NB; jb += PANEL_WARPS) {
 #pragma unroll
-            for (int u = 0; u < PANEL_ROT; ++u) {                      // pivot j = jb + u, its column sits in a[u]
-                const int j = jb + u, gj = k * NB + j;
-                const double d = __shfl_sync(0xffffffffu, a[u], j);
+        for (int ow = 0; ow < PANEL_WARPS; ++ow) {                    // pivot j = jb + ow is column col[0] of warp ow
+            const int j = jb + ow, gj = k * NB + j;
+            if (w == ow) {
+                const double d = __shfl_sync(0xffffffffu, col[0], j);
                 double ljj, inv;
                 if (gj >= n) { ljj = 1.0; inv = 0.0; }
                 else if (!(d > 0.0) || !isfinite(d)) { bad = true; ljj = 1.0; inv = 1.0; }
                 else { inv = rsqrt(d); ljj = d * inv; }
-                const double lrj = lane == j ? ljj : a[u] * inv;       // rows above the diagonal hold garbage: never read
+                const double lrj = lane == j ? ljj : (lane > j ? col[0] * inv : 0.0);
+                col[0] = lrj;
+                colbuf[j & 1][lane] = lrj;
                 if (lane == j) invd[j] = inv;
-                if (lane >= j) L[lane][j] = lrj;
-                a[u] = lrj;
-#pragma unroll
-                for (int p = u + 1; p < NB; ++p) {                     // position p == column jb+p (wraps to finished columns)
-                    const double lcj = __shfl_sync(0xffffffffu, lrj, (jb + p) & 31);
-                    if (jb + p < NB) a[p] = fma(-lrj, lcj, a[p]);
-                }
             }
-            double t[PANEL_ROT];
+            __syncthreads();
+            const double lrj = colbuf[j & 1][lane];
 #pragma unroll
-            for (int u = 0; u < PANEL_ROT; ++u) t[u] = a[u];
-#pragma unroll
-            for (int p = 0; p < NB - PANEL_ROT; ++p) a[p] = a[p + PANEL_ROT];
-#pragma unroll
-            for (int u = 0; u < PANEL_ROT; ++u) a[NB - PANEL_ROT + u] = t[u];
+            for (int q = 0; q < NB / PANEL_WARPS; ++q) {
+                const int c = jb + PANEL_WARPS * q + w;               // column held in col[q]; >= NB means wrapped (finished)
+                if (c > j && c < NB) col[q] = fma(-lrj, colbuf[j & 1][c], col[q]);
+            }
         }
-        if (bad && lane == 0 && blockIdx.x == 0) atomicAdd(fail, 1);
+        // the pivot columns of this group are final: store them, rotate the register set by one
+        if (lane >= jb + w) Ls[lane][jb + w] = col[0]; else Ls[lane][jb + w] = 0.0;
+        const double t = col[0];
+#pragma unroll
+        for (int q = 0; q < NB / PANEL_WARPS - 1; ++q) col[q] = col[q + 1];
+        col[NB / PANEL_WARPS - 1] = t;
     }
+    if (bad && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(fail, 1);
     __syncthreads();
     if (blockIdx.x == 0) {
-        for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; if (c <= r) A[(size_t)(k * NB + r) * npad + k * NB + c] = L[r][c]; }
+        for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; if (c <= r) A[(size_t)(k * NB + r) * npad + k * NB + c] = Ls[r][c]; }
         if (threadIdx.x < NB) dinv[k * NB + threadIdx.x] = invd[threadIdx.x];
     }
-    if (!has_tile) return;
-    // X L^T = B for row `lane`: x[0] is the current column
+    if (blockIdx.x * PANEL_WARPS + k + 1 >= nbk) return;              // no sub-diagonal tile in this CTA (uniform)
+    // ---- phase 2: Li = L^-1, lane = column
+    if (w == 0) {
+        double x[NB];
+#pragma unroll
+        for (int m = 0; m < NB; ++m) x[m] = 0.0;
 #pragma unroll 1
-    for (int jb = 0; jb < NB; jb += PANEL_ROT) {
+        for (int r = 0; r < NB; ++r) {
+            double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-        for (int u = 0; u < PANEL_ROT; ++u) {
-            const int j = jb + u;
-            const double xj = x[u] * invd[j];
-            x[u] = xj;
+            for (int m = 0; m < NB; m += 4) {                          // x[m] == 0 for m >= r, so the full row can be used
+                s0 = fma(-Ls[r][m], x[m], s0); s1 = fma(-Ls[r][m + 1], x[m + 1], s1);
+                s2 = fma(-Ls[r][m + 2], x[m + 2], s2); s3 = fma(-Ls[r][m + 3], x[m + 3], s3);
+            }
+            const double xr = ((s0 + s1) + (s2 + s3)) * invd[r];
 #pragma unroll
-            for (int p = u + 1; p < NB; ++p)
-                if (jb + p < NB) x[p] = fma(-xj, L[jb + p][j], x[p]);
+            for (int m = 0; m < NB; ++m) x[m] = (m == r) ? xr : x[m];
+            Li[r][lane] = xr;
         }
-        double t[PANEL_ROT];
-#pragma unroll
-        for (int u = 0; u < PANEL_ROT; ++u) t[u] = x[u];
-#pragma unroll
-        for (int p = 0; p < NB - PANEL_ROT; ++p) x[p] = x[p + PANEL_ROT];
-#pragma unroll
-        for (int u = 0; u < PANEL_ROT; ++u) x[NB - PANEL_ROT + u] = t[u];
     }
-    double* dst = A + (size_t)(i * NB + lane) * npad + k * NB;
+    __syncthreads();
+    // ---- phase 3: X[lane][c] = sum_{m<=c} B[lane][m] Li[c][m]   (Li is lower triangular: m > c contributes zeros)
+    if (has_tile) {
+        double* dst = A + (size_t)(i * NB + lane) * npad + k * NB;
+#pragma unroll 1
+        for (int c = 0; c < NB; c += 2) {
+            double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
 #pragma unroll
-    for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(x[c], x[c + 1]);
+            for (int m = 0; m < NB; m += 2) {
+                s0 = fma(b[m], Li[c][m], s0); s1 = fma(b[m + 1], Li[c][m + 1], s1);
+                u0 = fma(b[m], Li[c + 1][m], u0); u1 = fma(b[m + 1], Li[c + 1][m + 1], u1);
+            }
+            *reinterpret_cast<double2*>(dst + c) = make_double2(s0 + s1, u0 + u1);
+        }
+    }
 }
 
 // Trailing update step k: tile (i, j), k < j <= i:  A[i][j] -= A[i][k] A[j][k]^T.  blockDim = (32, 32), grid = T(T+1)/2.
@@ -718,7 +736,7 @@ __global__ void __launch_bounds__(640) chol_backsolve_kernel(const double* __res
 }
 
 // cameras + focal: candidate = x - y*scale ; derived table of the candidate ; norms.  Single CTA.
-// locals[0] = |delta_cf|^2, [1] = |x_cf|^2, [2] = |cand_cf|^2, [3] = max |g_cf| (unscaled), [4] = max |g_pts| (max-reduced over ranks)
+// locals[0] = |delta_cf|^2, [1] = |x_cf|^2, [2] = |cand_cf|^2, [3] = max |g_cf| (unscaled); post[7] = max |g_pts| (max-reduced over ranks)
 __global__ void __launch_bounds__(256) ba_cam_update_kernel(const double* __restrict__ x_cf, const double* __restrict__ y_cf,
                                                             const double* __restrict__ scale_cf, const double* __restrict__ gcf, int nc,
                                                             double* __restrict__ cand_cf, CamDerived* __restrict__ camd_c, double* __restrict__ locals,
@@ -742,7 +760,7 @@ __global__ void __launch_bounds__(256) ba_cam_update_kernel(const double* __rest
         for (int w = 0; w < 8; ++w) { s0 += red[w][0]; s1 += red[w][1]; s2 += red[w][2]; s3 = fmax(s3, red[w][3]); }
         locals[0] = s0; locals[1] = s1; locals[2] = s2; locals[3] = s3;
         // rank-local flags -> buffers that are reduced over ranks (sum / max) so that every rank takes the same decision
-        locals[4] = __longlong_as_double((long long)*gmax_pt_bits);
+        post[7] = __longlong_as_double((long long)*gmax_pt_bits);      // max-reduced over ranks
         post[4] = (double)fail[0]; post[5] = (double)fail[1];
     }
     __syncthreads();            // cand_cf complete
@@ -878,6 +896,51 @@ __global__ void __launch_bounds__(SORT_THREADS) scatter_cm_kernel(const int32_t*
     if (o < nobs) { const int pos = sh[nc + c] + r; cm_xy[pos] = obs_xy[o]; cm_pt[pos] = obs_pt[o]; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Cross-GPU sum over PEER MEMORY (one process per GPU, buffers mapped with CUDA IPC, loads travel over NVLink/NVSwitch).
+// Replaces ncclAllReduce for the reduced camera system: every rank reads the partial buffers of all ranks directly and
+// sums them in the same order (bitwise identical result on every rank), ~2 us of flag traffic instead of a collective
+// launch.  Protocol per call (epoch e, monotonically increasing, same sequence on every rank):
+//   peer_signal(A,e)  "my partial buffer is complete"      -> written into every peer's flag array
+//   peer_reduce       waits A>=e from all ranks, tmp[i] = sum_r buf_r[i]  (max for the tail range)
+//   peer_signal(B,e)  "I have finished reading everybody's buffer"
+//   peer_copyback     waits B>=e from all ranks, buf <- tmp   (nobody reads my partials any more)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MAX_PEERS = 16;
+struct PeerTable { double* buf[MAX_PEERS]; unsigned long long* flags[MAX_PEERS]; };   // flags: [2][MAX_PEERS] per rank
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void peer_signal_kernel(PeerTable t, int slot, int my_rank, int nranks, unsigned long long epoch) {
+    if ((int)threadIdx.x < nranks) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.flags[threadIdx.x] + slot * MAX_PEERS + my_rank), "l"(epoch) : "memory");
+    }
+}
+__device__ __forceinline__ void peer_wait(const unsigned long long* my_flags, int slot, int nranks, unsigned long long epoch) {
+    if ((int)threadIdx.x < nranks) { while (ld_flag(my_flags + slot * MAX_PEERS + threadIdx.x) < epoch) __nanosleep(64); }
+    __syncthreads();
+    __threadfence_system();
+}
+__global__ void __launch_bounds__(256) peer_reduce_kernel(PeerTable t, size_t offset, int my_rank, int nranks, unsigned long long epoch,
+                                                          size_t n_sum, size_t n_max, double* __restrict__ tmp) {
+    peer_wait(t.flags[my_rank], 0, nranks, epoch);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sum + n_max; i += (size_t)gridDim.x * blockDim.x) {
+        double acc = __ldcv(t.buf[0] + offset + i);
+        for (int r = 1; r < nranks; ++r) { const double v = __ldcv(t.buf[r] + offset + i); acc = i < n_sum ? acc + v : fmax(acc, v); }
+        tmp[i] = acc;
+    }
+}
+__global__ void __launch_bounds__(256) peer_copyback_kernel(PeerTable t, size_t offset, int my_rank, int nranks, unsigned long long epoch,
+                                                            size_t n, const double* __restrict__ tmp) {
+    peer_wait(t.flags[my_rank], 1, nranks, epoch);
+    double* dst = t.buf[my_rank] + offset;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = tmp[i];
+}
+
 }  // namespace
 
 // =================================================================================================================
@@ -905,6 +968,9 @@ struct sfmb200_ba_problem {
     double* Zbuf = nullptr; int32_t* pair_off = nullptr; int32_t* pair_blk = nullptr; uint2* pair_ent = nullptr;
     int n_pairs_nonempty = 0, pair_splits = 1, pair_nseg = 1;
     DevBuf gmem;
+    // exchange memory (its own cudaMalloc so that it can be exported with CUDA IPC): red | post.. | flags
+    void* xmem = nullptr; size_t xmem_doubles = 0; double* xtmp = nullptr; unsigned long long* xflags = nullptr;
+    bool peers = false; PeerTable ptab; void* peer_base[MAX_PEERS] = {nullptr}; unsigned long long epoch = 0;
 };
 
 static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* opt) {
@@ -966,6 +1032,24 @@ static dim3 camera_grid(const sfmb200_ba_problem* P) {
     return dim3(chunks, std::max(1, P->nc));
 }
 
+// In-place reduction over ranks of buf[0..n_sum) (sum) and buf[n_sum..n_sum+n_max) (max); buf lives in the exchange memory.
+static int ba_allreduce(sfmb200_ba_problem* P, double* buf, size_t n_sum, size_t n_max) {
+    sfmb200_ctx* ctx = P->ctx;
+    if (ctx->nranks <= 1) return SFMB200_OK;
+    if (!P->peers) {                     // NCCL fallback
+        int rc = sfmb200_allreduce_sum_f64(ctx, buf, n_sum); if (rc) return rc;
+        return n_max ? sfmb200_allreduce_max_f64(ctx, buf + n_sum, n_max) : SFMB200_OK;
+    }
+    const size_t offset = buf - (double*)P->xmem, n = n_sum + n_max;
+    const unsigned long long e = ++P->epoch;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 4));
+    peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(P->ptab, 0, ctx->rank, ctx->nranks, e); SFM_LAUNCH_CHECK(ctx);
+    peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n_sum, n_max, P->xtmp); SFM_LAUNCH_CHECK(ctx);
+    peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(P->ptab, 1, ctx->rank, ctx->nranks, e); SFM_LAUNCH_CHECK(ctx);
+    peer_copyback_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n, P->xtmp); SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
+
 // Jacobi scaling at the current x (iteration 0).  Multi-GPU: camera/focal column norms are summed over ranks.
 static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt) {
     sfmb200_ctx* ctx = P->ctx;
@@ -984,7 +1068,7 @@ static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt)
         int rc = DISPATCH_G(P, launch_point_norm)(P, v); if (rc) return rc;
         ba_camera_norm_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v, colnorm); SFM_LAUNCH_CHECK(ctx);
     }
-    int rc = sfmb200_allreduce_sum_f64(ctx, colnorm, n); if (rc) return rc;
+    int rc = ba_allreduce(P, colnorm, n, 0); if (rc) return rc;
     scale_from_norm_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(colnorm, n, P->scale_cf); SFM_LAUNCH_CHECK(ctx);
     P->have_scale = true;
     return SFMB200_OK;
@@ -995,7 +1079,7 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
     sfmb200_ctx* ctx = P->ctx;
     BAView v = make_view(P, opt);
     SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * P->red_n, ctx->stream));
-    SFM_CUDA(ctx, cudaMemsetAsync(P->post, 0, sizeof(double) * 8 + sizeof(double) * 8 + 16 + 16, ctx->stream));   // post, locals, gmax, fail
+    SFM_CUDA(ctx, cudaMemsetAsync(P->post, 0, sizeof(double) * 20, ctx->stream));   // post, locals, gmax, fail
     cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
     if (P->np > 0 && P->nobs > 0) {
         if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev0, ctx->stream));
@@ -1010,7 +1094,7 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
         }
         ba_camera_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v); SFM_LAUNCH_CHECK(ctx);
     }
-    return sfmb200_allreduce_sum_f64(ctx, P->red, P->red_n);
+    return ba_allreduce(P, P->red, P->red_n, 0);
 }
 
 static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius) {
@@ -1075,7 +1159,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     add(8 * (size_t)nobs); add(4 * (size_t)nobs); add(4 * (size_t)(np + 1)); add(4 * (size_t)(nc + 1)); add(8 * (size_t)nobs); add(4 * (size_t)nobs);
     for (int i = 0; i < 3; ++i) { add(8 * n); add(24 * (size_t)np); }
     add(sizeof(CamDerived) * (size_t)nc); add(sizeof(CamDerived) * (size_t)nc);
-    add(8 * n); add(24 * (size_t)np); add(96 * (size_t)np); add(8 * P->red_n); add(64 + 64 + 16 + 16);
+    add(8 * n); add(24 * (size_t)np); add(96 * (size_t)np); add(8 * (P->red_n + 32));
     add(8 * (size_t)P->npad * P->npad); add(8 * n); add(8 * (size_t)P->npad); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
     cudaError_t e = P->mem.reserve(bytes);
     if (e != cudaSuccess) { delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
@@ -1086,14 +1170,22 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->cf0 = cv.take<double>(n); P->pts0 = cv.take<double>(3 * (size_t)np);
     P->camd[0] = cv.take<CamDerived>(nc); P->camd[1] = cv.take<CamDerived>(nc);
     P->scale_cf = cv.take<double>(n); P->scale_pt = cv.take<double>(3 * (size_t)np); P->ptblk = cv.take<double>(12 * (size_t)np);
-    P->red = cv.take<double>(P->red_n);
+    // exchange memory: [red (red_n) | post 8 | locals 8 | gmax 1 | pad 1 | fail 1 | pad][flags 2*MAX_PEERS u64]
+    P->xmem_doubles = P->red_n + 24 + 2 * MAX_PEERS;
+    {
+        cudaError_t ex = cudaMalloc(&P->xmem, 8 * P->xmem_doubles + 256);
+        if (ex != cudaSuccess) { P->mem.release(); delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(exchange): %s", cudaGetErrorString(ex)); }
+        cudaMemsetAsync(P->xmem, 0, 8 * P->xmem_doubles + 256, ctx->stream);
+    }
+    P->red = (double*)P->xmem;
+    P->xtmp = cv.take<double>(P->red_n + 32);
     P->Sblk = P->red; P->Scf = P->Sblk + 36 * nblk; P->Sff = P->Scf + 6 * (size_t)nc; P->rhs = P->Sff + 1; P->gcf = P->rhs + n; P->dcf = P->gcf + n; P->sums = P->dcf + n;
-    P->post = cv.take<double>(8 + 8 + 2 + 2); P->locals = P->post + 8; P->gmax_pt_bits = (unsigned long long*)(P->locals + 8); P->fail = (int*)(P->locals + 10);
+    P->post = P->red + P->red_n; P->xflags = (unsigned long long*)(P->post + 24); P->locals = P->post + 8; P->gmax_pt_bits = (unsigned long long*)(P->locals + 8); P->fail = (int*)(P->locals + 10);
     P->A = cv.take<double>((size_t)P->npad * P->npad); P->y_cf = cv.take<double>(n); P->dinv = cv.take<double>(P->npad);
     int32_t* obs_pt = cv.take<int32_t>(nobs); int* cnt = cv.take<int>(2 * (size_t)(nc + 1)); int* cursor = cnt + nc + 1;
 
     cudaStream_t st = ctx->stream;
-#define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { P->mem.release(); P->gmem.release(); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
+#define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { P->mem.release(); P->gmem.release(); cudaFree(P->xmem); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
     if (nobs) { CRT(cudaMemcpyAsync(P->obs_xy, obs_xy, 8 * (size_t)nobs, cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->obs_cam, obs_cam, 4 * (size_t)nobs, cudaMemcpyHostToDevice, st)); }
     if (np) { CRT(cudaMemcpyAsync(P->pt_off, pt_off, 4 * (size_t)(np + 1), cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->pts0, pts3, 24 * (size_t)np, cudaMemcpyHostToDevice, st)); }
     if (nc) CRT(cudaMemcpyAsync(P->cf0, cams6, 48 * (size_t)nc, cudaMemcpyHostToDevice, st));
@@ -1166,8 +1258,10 @@ void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     if (P->ev1) cudaEventDestroy(P->ev1);
     if (P->ev2) cudaEventDestroy(P->ev2);
     if (P->ev3) cudaEventDestroy(P->ev3);
+    for (int r = 0; r < MAX_PEERS; ++r) if (P->peer_base[r]) cudaIpcCloseMemHandle(P->peer_base[r]);
     P->gmem.release();
     P->mem.release();
+    if (P->xmem) cudaFree(P->xmem);
     delete P;
 }
 
@@ -1191,6 +1285,41 @@ int sfmb200_ba_problem_download(sfmb200_ba_problem* P, double* cams6, double* pt
     if (focal) SFM_CUDA(ctx, cudaMemcpyAsync(focal, P->cf[P->cur] + 6 * P->nc, 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (pts3 && P->np) SFM_CUDA(ctx, cudaMemcpyAsync(pts3, P->pts[P->cur], 24 * (size_t)P->np, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFMB200_OK;
+}
+
+int sfmb200_ba_problem_ipc_handle(sfmb200_ba_problem* P, uint8_t* out) {
+    if (!P || !out) return SFMB200_ERR_INVALID;
+    sfmb200_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == SFMB200_IPC_HANDLE_BYTES, "IPC handle size");
+    SFM_CUDA(ctx, cudaIpcGetMemHandle(&h, P->xmem));
+    memcpy(out, &h, sizeof h);
+    return SFMB200_OK;
+}
+
+int sfmb200_ba_problem_ipc_attach(sfmb200_ba_problem* P, const uint8_t* handles) {
+    if (!P) return SFMB200_ERR_INVALID;
+    sfmb200_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->nranks <= 1) return SFMB200_OK;
+    if (!handles) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "handles required");
+    if (ctx->nranks > MAX_PEERS) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "at most %d ranks", MAX_PEERS);
+    for (int r = 0; r < ctx->nranks; ++r) {
+        void* base = P->xmem;
+        if (r != ctx->rank) {
+            cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)r * SFMB200_IPC_HANDLE_BYTES, sizeof h);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return sfmb200_fail(ctx, SFMB200_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+            P->peer_base[r] = base;
+        }
+        P->ptab.buf[r] = (double*)base;
+        P->ptab.flags[r] = (unsigned long long*)((double*)base + P->red_n + 24);
+    }
+    P->peers = true;
     return SFMB200_OK;
 }
 
@@ -1262,8 +1391,7 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
                                                          P->post, P->gmax_pt_bits, P->fail);
         SFM_LAUNCH_CHECK(ctx);
         if (P->np > 0 && P->nobs > 0) { BAView v = make_view(P, &opt); rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }
-        rc = sfmb200_allreduce_sum_f64(ctx, P->post, 8); if (rc) return rc;
-        rc = sfmb200_allreduce_max_f64(ctx, P->locals + 4, 1); if (rc) return rc;
+        rc = ba_allreduce(P, P->post, 7, 1); if (rc) return rc;   // sums: candidate cost, model, norms, failure counts; max: |g| of the points
         // read back: sums[8] | post[8] locals[8]
         SFM_CUDA(ctx, cudaMemcpyAsync(h, P->sums, 64, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaMemcpyAsync(h + 8, P->post, 8 * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1276,7 +1404,7 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
         const double cost_x = 0.5 * h[0], xn2_pts = h[1];
         const double cand_cost_raw = 0.5 * h[8], model_acc = h[9], dn2_pts = h[10], cn2_pts = h[11];
         const double fails[2] = {h[12], h[13]};                        // summed over ranks
-        const double dn2_cf = h[16], xn2_cf = h[17], cn2_cf = h[18], gmax_cf = h[19], gmax_pt = h[20];   // gmax_pt: max over ranks
+        const double dn2_cf = h[16], xn2_cf = h[17], cn2_cf = h[18], gmax_cf = h[19], gmax_pt = h[15];     // gmax_pt: max over ranks
         if (new_point) {
             x_cost = cost_x; x_norm = std::sqrt(xn2_pts + xn2_cf); gmax = std::max(gmax_pt, gmax_cf);
             new_point = false;

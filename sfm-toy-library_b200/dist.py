@@ -47,3 +47,18 @@ def init_comm(ctx, dist_module=None):
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(uid[0], rank, world)
     return world
+
+
+def attach_peers(prob, dist_module=None):
+    """Switch a BAProblem's cross-rank sums from NCCL to peer-memory kernels: all-gather the CUDA-IPC handles of the
+    exchange buffers (rank order) and attach them.  Collective: every rank must call it after creating its problem."""
+    dist = dist_module
+    if dist is None:
+        import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return False
+    handles = [None] * dist.get_world_size()
+    dist.all_gather_object(handles, prob.ipc_handle())
+    prob.ipc_attach(handles)
+    dist.barrier()
+    return True

@@ -14,7 +14,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, exchange):
     import torch.distributed as dist
     from sfm_toy_library_b200 import capi, synth
     from sfm_toy_library_b200 import dist as sdist
@@ -25,6 +25,8 @@ def _worker(rank, world, port, out_dir):
     p = synth.make_ba_problem(n_cams=16, n_pts=3001, obs_per_pt=6, seed=8)
     sh = sdist.shard_ba_problem(p, rank, world)
     prob = ctx.ba_problem(sh["cams"], sh["pts"], sh["focal"], sh["obs_xy"], sh["obs_cam"], sh["pt_off"])
+    if exchange == "peer":
+        assert sdist.attach_peers(prob, dist)                       # CUDA-IPC mapped buffers, sums by NVLink loads
     red = prob.reduced_system(1e4)
     s = prob.run()
     cams, pts, f = prob.download()
@@ -35,13 +37,14 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(600)
-def test_two_gpu_solve_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_two_gpu_solve_equals_single_gpu(tmp_path, exchange):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from sfm_toy_library_b200 import capi, synth
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), exchange), nprocs=2, join=True)
     r = [np.load(os.path.join(tmp_path, f"r{i}.npz")) for i in range(2)]
     p = synth.make_ba_problem(n_cams=16, n_pts=3001, obs_per_pt=6, seed=8)
     ctx = capi.Context(0)
