@@ -165,7 +165,7 @@ __global__ void fill_kernel(double* __restrict__ p, size_t n, double v) {
 // Shared memory per group: Z [maxk][18] + camera ids [maxk]; pair table shared by the CTA.
 // ---------------------------------------------------------------------------------------------------------------
 template <int G, bool GATHER>
-__global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double inv_radius) {
+__global__ void __launch_bounds__(PT_THREADS, GATHER ? 4 : 3) ba_point_kernel(BAView v, double inv_radius) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GB = PT_THREADS / G, GW = 32 / G;
     const int maxk = v.maxk;
@@ -564,16 +564,14 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
 //            owning warp produces the column (shuffle, rsqrt, scale) and publishes it in shared memory; after ONE barrier
 //            every warp applies it to its 8 columns (8 broadcast-LDS + FMA instead of 31 in one warp).  The register set is
 //            rotated every 4 pivots so that the loop stays rolled with static register indices.
-//   phase 2  warp 0 inverts the factor by forward substitution on the identity (lane = column of L^-1).
-//   phase 3  each warp: X = B L^-T as 32 dot products per row against broadcast rows of L^-1 -- no dependency chain,
-//            instead of a 32-step triangular solve.
+//   phase 2  each warp solves X L^T = B for its tile, row per lane in registers (rotated like phase 1), L[c][j] as
+//            broadcast LDS.  (An explicit 32x32 inverse + product was measured slower: 15 k + 7 k cycles vs ~5 k.)
 // CTA 0 writes the factor back together with the reciprocal pivots (dinv) the back-substitution uses.  Pivots with
 // global index >= n are forced to 1 with a zero column (augmented rhs row / padding rows).
 constexpr int PANEL_WARPS = 4;
 __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk,
                                                                       double* __restrict__ dinv, int* __restrict__ fail) {
     __shared__ double Ls[NB][NB + 1];          // diagonal tile, then its factor (lower)
-    __shared__ double Li[NB][NB + 1];          // inverse of the factor (lower), also the staging tile for phase 3 output
     __shared__ double colbuf[2][NB];
     __shared__ double invd[NB];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -585,7 +583,13 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __
 #pragma unroll
         for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); b[c] = v.x; b[c + 1] = v.y; }
     }
-    for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; Ls[r][c] = A[(size_t)(k * NB + r) * npad + k * NB + c]; }
+    {   // diagonal tile -> shared memory; all 8 loads of a thread are issued before the first store
+        double v[NB * NB / (PANEL_WARPS * 32)];
+#pragma unroll
+        for (int u = 0; u < NB * NB / (PANEL_WARPS * 32); ++u) { const int e = threadIdx.x + u * PANEL_WARPS * 32; v[u] = A[(size_t)(k * NB + (e >> 5)) * npad + k * NB + (e & 31)]; }
+#pragma unroll
+        for (int u = 0; u < NB * NB / (PANEL_WARPS * 32); ++u) { const int e = threadIdx.x + u * PANEL_WARPS * 32; Ls[e >> 5][e & 31] = v[u]; }
+    }
     __syncthreads();
     // ---- phase 1: col[q] = column 4*(q + rot) + w of row `lane`  (rot = number of rotations so far)
     double col[NB / PANEL_WARPS];
@@ -629,41 +633,31 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __
         for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; if (c <= r) A[(size_t)(k * NB + r) * npad + k * NB + c] = Ls[r][c]; }
         if (threadIdx.x < NB) dinv[k * NB + threadIdx.x] = invd[threadIdx.x];
     }
-    if (blockIdx.x * PANEL_WARPS + k + 1 >= nbk) return;              // no sub-diagonal tile in this CTA (uniform)
-    // ---- phase 2: Li = L^-1, lane = column
-    if (w == 0) {
-        double x[NB];
-#pragma unroll
-        for (int m = 0; m < NB; ++m) x[m] = 0.0;
+    if (!has_tile) return;
+    // ---- phase 2: X L^T = B for row `lane`, columns in registers.  The register row is rotated by PANEL_WARPS every
+    // PANEL_WARPS pivots so that the loop stays rolled with static indices; L[c][j] arrives as a broadcast LDS.
 #pragma unroll 1
-        for (int r = 0; r < NB; ++r) {
-            double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int jb = 0; jb < NB; jb += PANEL_WARPS) {
 #pragma unroll
-            for (int m = 0; m < NB; m += 4) {                          // x[m] == 0 for m >= r, so the full row can be used
-                s0 = fma(-Ls[r][m], x[m], s0); s1 = fma(-Ls[r][m + 1], x[m + 1], s1);
-                s2 = fma(-Ls[r][m + 2], x[m + 2], s2); s3 = fma(-Ls[r][m + 3], x[m + 3], s3);
-            }
-            const double xr = ((s0 + s1) + (s2 + s3)) * invd[r];
+        for (int u = 0; u < PANEL_WARPS; ++u) {
+            const int j = jb + u;
+            const double xj = b[u] * invd[j];
+            b[u] = xj;
 #pragma unroll
-            for (int m = 0; m < NB; ++m) x[m] = (m == r) ? xr : x[m];
-            Li[r][lane] = xr;
+            for (int p2 = u + 1; p2 < NB; ++p2)
+                if (jb + p2 < NB) b[p2] = fma(-xj, Ls[jb + p2][j], b[p2]);
         }
-    }
-    __syncthreads();
-    // ---- phase 3: X[lane][c] = sum_{m<=c} B[lane][m] Li[c][m]   (Li is lower triangular: m > c contributes zeros)
-    if (has_tile) {
-        double* dst = A + (size_t)(i * NB + lane) * npad + k * NB;
-#pragma unroll 1
-        for (int c = 0; c < NB; c += 2) {
-            double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
+        double t[PANEL_WARPS];
 #pragma unroll
-            for (int m = 0; m < NB; m += 2) {
-                s0 = fma(b[m], Li[c][m], s0); s1 = fma(b[m + 1], Li[c][m + 1], s1);
-                u0 = fma(b[m], Li[c + 1][m], u0); u1 = fma(b[m + 1], Li[c + 1][m + 1], u1);
-            }
-            *reinterpret_cast<double2*>(dst + c) = make_double2(s0 + s1, u0 + u1);
-        }
+        for (int u = 0; u < PANEL_WARPS; ++u) t[u] = b[u];
+#pragma unroll
+        for (int p2 = 0; p2 < NB - PANEL_WARPS; ++p2) b[p2] = b[p2 + PANEL_WARPS];
+#pragma unroll
+        for (int u = 0; u < PANEL_WARPS; ++u) b[NB - PANEL_WARPS + u] = t[u];
     }
+    double* dst = A + (size_t)(i * NB + lane) * npad + k * NB;
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(b[c], b[c + 1]);
 }
 
 // Trailing update step k: tile (i, j), k < j <= i:  A[i][j] -= A[i][k] A[j][k]^T.  blockDim = (32, 32), grid = T(T+1)/2.
@@ -774,7 +768,7 @@ __global__ void __launch_bounds__(256) ba_cam_update_kernel(const double* __rest
 // post[0] = sum r'^2, post[1] = sum m.(r+m/2), post[2] = |delta_pts|^2, post[3] = |cand_pts|^2
 // ---------------------------------------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, const double* __restrict__ y_cf, const double* __restrict__ cand_cf,
+__global__ void __launch_bounds__(PT_THREADS, 4) ba_backsub_eval_kernel(BAView v, const double* __restrict__ y_cf, const double* __restrict__ cand_cf,
                                                                      const CamDerived* __restrict__ camd_c, double* __restrict__ pts_c,
                                                                      double* __restrict__ post) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G;
