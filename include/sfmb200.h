@@ -137,6 +137,7 @@ typedef struct {
     int schur_launches;
     double pair_ms_total;                   /* profile=1: CUDA-event time of the camera-pair block kernel (K3c), summed */
     int pair_launches;
+    double camera_ms_total;                 /* profile=1: CUDA-event time of the camera-major kernel (K3b), summed (one launch per schur launch) */
     int64_t kernel_launches;                /* kernels launched by this solve */
     char message[160];
 } sfmb200_ba_summary;

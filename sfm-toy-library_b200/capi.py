@@ -36,7 +36,7 @@ class BASummary(C.Structure):
     _fields_ = [("termination_type", C.c_int), ("num_iterations", C.c_int), ("num_successful_steps", C.c_int),
                 ("num_unsuccessful_steps", C.c_int), ("num_jacobian_passes", C.c_int), ("num_linear_solves", C.c_int),
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("total_time_s", C.c_double),
-                ("schur_ms_total", C.c_double), ("schur_launches", C.c_int), ("pair_ms_total", C.c_double), ("pair_launches", C.c_int),
+                ("schur_ms_total", C.c_double), ("schur_launches", C.c_int), ("pair_ms_total", C.c_double), ("pair_launches", C.c_int), ("camera_ms_total", C.c_double),
                 ("kernel_launches", C.c_int64),
                 ("message", C.c_char * 160)]
 

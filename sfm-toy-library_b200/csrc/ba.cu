@@ -165,7 +165,7 @@ __global__ void fill_kernel(double* __restrict__ p, size_t n, double v) {
 // Shared memory per group: Z [maxk][18] + camera ids [maxk]; pair table shared by the CTA.
 // ---------------------------------------------------------------------------------------------------------------
 template <int G, bool GATHER>
-__global__ void __launch_bounds__(PT_THREADS, GATHER ? 4 : 3) ba_point_kernel(BAView v, double inv_radius) {
+__global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double inv_radius) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GB = PT_THREADS / G, GW = 32 / G;
     const int maxk = v.maxk;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(PT_THREADS, GATHER ? 4 : 3) ba_point_kernel(BA
 // One warp per (pair, split): lanes stride over the list, each accumulating a full 6x6 block  sum Z_i Z_j^T  in 36
 // registers from two 144-byte reads, then a warp shuffle reduction and 36 REDs per warp (instead of 36 per entry).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PAIR_WARPS = 4;
+constexpr int PAIR_WARPS = 8;
 // pair_off is indexed by key = blk * nseg + seg (seg = point-range segment): the grid walks the segments in the slow
 // (y) dimension, LAST segment first, so that all resident warps read the same ~24 MB slice of Zbuf -- which then lives
 // in L2 (the tail of Zbuf is still L2-resident from the point kernel that just wrote it).
@@ -328,7 +328,7 @@ constexpr int PAIR_WARPS = 4;
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-constexpr int PAIR_UNROLL = 8;
+constexpr int PAIR_UNROLL = 16;
 __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
                                                                    const uint2* __restrict__ pair_ent, int n_nonempty, int nseg, int splits,
                                                                    const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk) {
@@ -343,20 +343,22 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* 
     const int fr = lane >> 2, fc = lane & 3;
     const bool valid = fr < 6 && fc < 3;
     const int fidx = valid ? fr * 3 + fc : 0;
-    double c0[PAIR_UNROLL], c1[PAIR_UNROLL];
+    double c0[8], c1[8];               // 8 independent accumulator fragments
 #pragma unroll
-    for (int u = 0; u < PAIR_UNROLL; ++u) { c0[u] = 0.0; c1[u] = 0.0; }
+    for (int u = 0; u < 8; ++u) { c0[u] = 0.0; c1[u] = 0.0; }
     int e = b0;
     for (; e + PAIR_UNROLL <= b1; e += PAIR_UNROLL) {
+        // one coalesced request fetches the PAIR_UNROLL index pairs of this batch; they are handed out by shuffles
+        const uint2 mine = lane < PAIR_UNROLL ? __ldg(pair_ent + e + lane) : make_uint2(0u, 0u);
         double a[PAIR_UNROLL], b[PAIR_UNROLL];
 #pragma unroll
         for (int u = 0; u < PAIR_UNROLL; ++u) {
-            const uint2 ent = __ldg(pair_ent + e + u);                // same address in every lane: one broadcast transaction
-            const double va = __ldg(Zbuf + (size_t)ent.x * 18 + fidx), vb = __ldg(Zbuf + (size_t)ent.y * 18 + fidx);
+            const unsigned ex = __shfl_sync(0xffffffffu, mine.x, u), ey = __shfl_sync(0xffffffffu, mine.y, u);
+            const double va = __ldg(Zbuf + (size_t)ex * 18 + fidx), vb = __ldg(Zbuf + (size_t)ey * 18 + fidx);
             a[u] = valid ? va : 0.0; b[u] = valid ? vb : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < PAIR_UNROLL; ++u) dmma_m8n8k4(c0[u], c1[u], a[u], b[u]);
+        for (int u = 0; u < PAIR_UNROLL; ++u) dmma_m8n8k4(c0[u & 7], c1[u & 7], a[u], b[u]);
     }
     for (; e < b1; ++e) {
         const uint2 ent = __ldg(pair_ent + e);
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* 
     }
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int u = 0; u < PAIR_UNROLL; ++u) { s0 += c0[u]; s1 += c1[u]; }
+    for (int u = 0; u < 8; ++u) { s0 += c0[u]; s1 += c1[u]; }
     // accumulator fragment: row = lane>>2, columns 2*(lane&3) and 2*(lane&3)+1
     const int cc = 2 * fc;
     if (fr < 6 && cc < 6) {
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(256) ba_cam_update_kernel(const double* __rest
 // post[0] = sum r'^2, post[1] = sum m.(r+m/2), post[2] = |delta_pts|^2, post[3] = |cand_pts|^2
 // ---------------------------------------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(PT_THREADS, 4) ba_backsub_eval_kernel(BAView v, const double* __restrict__ y_cf, const double* __restrict__ cand_cf,
+__global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, const double* __restrict__ y_cf, const double* __restrict__ cand_cf,
                                                                      const CamDerived* __restrict__ camd_c, double* __restrict__ pts_c,
                                                                      double* __restrict__ post) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G;
@@ -956,7 +958,7 @@ struct sfmb200_ba_problem {
     double* A; double* y_cf; double* dinv;
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
     bool have_scale = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;
     // gather mode (K3c): Z per observation + per-camera-pair entry lists
     bool gather = true;
     double* Zbuf = nullptr; int32_t* pair_off = nullptr; int32_t* pair_blk = nullptr; uint2* pair_ent = nullptr;
@@ -1086,7 +1088,9 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
             SFM_LAUNCH_CHECK(ctx);
             if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev3, ctx->stream));
         }
+        if (profile && !(P->gather && P->n_pairs_nonempty > 0)) SFM_CUDA(ctx, cudaEventRecord(P->ev3, ctx->stream));
         ba_camera_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v); SFM_LAUNCH_CHECK(ctx);
+        if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev4, ctx->stream));
     }
     return ba_allreduce(P, P->red, P->red_n, 0);
 }
@@ -1199,7 +1203,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     }
     CRT(cudaGetLastError());
     CRT(cudaMallocHost((void**)&P->h_scal, sizeof(double) * 32));
-    CRT(cudaEventCreate(&P->ev0)); CRT(cudaEventCreate(&P->ev1)); CRT(cudaEventCreate(&P->ev2)); CRT(cudaEventCreate(&P->ev3));
+    CRT(cudaEventCreate(&P->ev0)); CRT(cudaEventCreate(&P->ev1)); CRT(cudaEventCreate(&P->ev2)); CRT(cudaEventCreate(&P->ev3)); CRT(cudaEventCreate(&P->ev4));
     {   // off-diagonal Schur blocks: "gather" (default; per-camera-pair lists, no atomics in the hot loop) or "red"
         const char* mode = getenv("SFMB200_BA_SCHUR");
         P->gather = !(mode && strcmp(mode, "red") == 0);
@@ -1207,8 +1211,8 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         for (int p = 0; p < np; ++p) { const long long k = pt_off[p + 1] - pt_off[p]; E += k * (k - 1) / 2; }
         if (E >= (1LL << 31) - 1024) P->gather = false;          // int32 offsets
         if (P->gather && E > 0) {
-            // point-range segments: ~24 MB of Zbuf each, so that one segment stays L2-resident while it is read ~7 times
-            const int nseg = (int)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (24LL << 20) - 1) / (24LL << 20)));
+            // point-range segments: ~32 MB of Zbuf each, so that one segment stays L2-resident while it is read ~7 times
+            const int nseg = (int)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (32LL << 20) - 1) / (32LL << 20)));
             const size_t nkeys = nblk * (size_t)nseg;
             const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + Carver::pad(4 * (nkeys + 1)) + Carver::pad(4 * (nblk + 1)) + Carver::pad(8 * (size_t)E) +
                               Carver::pad(4 * nkeys) * 2 + 4096;
@@ -1252,6 +1256,7 @@ void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     if (P->ev1) cudaEventDestroy(P->ev1);
     if (P->ev2) cudaEventDestroy(P->ev2);
     if (P->ev3) cudaEventDestroy(P->ev3);
+    if (P->ev4) cudaEventDestroy(P->ev4);
     for (int r = 0; r < MAX_PEERS; ++r) if (P->peer_base[r]) cudaIpcCloseMemHandle(P->peer_base[r]);
     P->gmem.release();
     P->mem.release();
@@ -1394,6 +1399,7 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
             float ms = 0;
             if (cudaEventElapsedTime(&ms, P->ev0, P->ev1) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; }
             if (P->gather && P->n_pairs_nonempty > 0 && cudaEventElapsedTime(&ms, P->ev2, P->ev3) == cudaSuccess) { sum->pair_ms_total += ms; sum->pair_launches++; }
+            if (cudaEventElapsedTime(&ms, P->ev3, P->ev4) == cudaSuccess) sum->camera_ms_total += ms;
         }
         const double cost_x = 0.5 * h[0], xn2_pts = h[1];
         const double cand_cost_raw = 0.5 * h[8], model_acc = h[9], dn2_pts = h[10], cn2_pts = h[11];
