@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
 // One warp per (pair, split): lanes stride over the list, each accumulating a full 6x6 block  sum Z_i Z_j^T  in 36
 // registers from two 144-byte reads, then a warp shuffle reduction and 36 REDs per warp (instead of 36 per entry).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PAIR_WARPS = 8;
+constexpr int PAIR_WARPS = 4;
 // pair_off is indexed by key = blk * nseg + seg (seg = point-range segment): the grid walks the segments in the slow
 // (y) dimension, LAST segment first, so that all resident warps read the same ~24 MB slice of Zbuf -- which then lives
 // in L2 (the tail of Zbuf is still L2-resident from the point kernel that just wrote it).
@@ -328,7 +328,7 @@ constexpr int PAIR_WARPS = 8;
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-constexpr int PAIR_UNROLL = 16;
+constexpr int PAIR_UNROLL = 8;
 __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
                                                                    const uint2* __restrict__ pair_ent, int n_nonempty, int nseg, int splits,
                                                                    const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk) {
@@ -348,13 +348,11 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* 
     for (int u = 0; u < 8; ++u) { c0[u] = 0.0; c1[u] = 0.0; }
     int e = b0;
     for (; e + PAIR_UNROLL <= b1; e += PAIR_UNROLL) {
-        // one coalesced request fetches the PAIR_UNROLL index pairs of this batch; they are handed out by shuffles
-        const uint2 mine = lane < PAIR_UNROLL ? __ldg(pair_ent + e + lane) : make_uint2(0u, 0u);
         double a[PAIR_UNROLL], b[PAIR_UNROLL];
 #pragma unroll
         for (int u = 0; u < PAIR_UNROLL; ++u) {
-            const unsigned ex = __shfl_sync(0xffffffffu, mine.x, u), ey = __shfl_sync(0xffffffffu, mine.y, u);
-            const double va = __ldg(Zbuf + (size_t)ex * 18 + fidx), vb = __ldg(Zbuf + (size_t)ey * 18 + fidx);
+            const uint2 ent = __ldg(pair_ent + e + u);                // same address in every lane: one broadcast transaction
+            const double va = __ldg(Zbuf + (size_t)ent.x * 18 + fidx), vb = __ldg(Zbuf + (size_t)ent.y * 18 + fidx);
             a[u] = valid ? va : 0.0; b[u] = valid ? vb : 0.0;
         }
 #pragma unroll
@@ -1211,8 +1209,8 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         for (int p = 0; p < np; ++p) { const long long k = pt_off[p + 1] - pt_off[p]; E += k * (k - 1) / 2; }
         if (E >= (1LL << 31) - 1024) P->gather = false;          // int32 offsets
         if (P->gather && E > 0) {
-            // point-range segments: ~32 MB of Zbuf each, so that one segment stays L2-resident while it is read ~7 times
-            const int nseg = (int)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (32LL << 20) - 1) / (32LL << 20)));
+            // point-range segments: ~24 MB of Zbuf each, so that one segment stays L2-resident while it is read ~7 times
+            const int nseg = (int)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (24LL << 20) - 1) / (24LL << 20)));
             const size_t nkeys = nblk * (size_t)nseg;
             const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + Carver::pad(4 * (nkeys + 1)) + Carver::pad(4 * (nblk + 1)) + Carver::pad(8 * (size_t)E) +
                               Carver::pad(4 * nkeys) * 2 + 4096;
