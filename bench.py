@@ -184,8 +184,12 @@ def run_ours(args):
     if world > 1:
         from sfm_toy_library_b200 import dist as sdist
         exchange = "nccl"
-        if os.environ.get("SFMB200_EXCHANGE", "peer") == "peer" and sdist.attach_peers(prob, dist):
-            exchange = "peer-memory kernels (CUDA IPC, NVLink loads)"
+        if os.environ.get("SFMB200_EXCHANGE", "peer") == "peer":
+            try:
+                if sdist.attach_peers(prob, dist):
+                    exchange = "peer-memory kernels (CUDA IPC, NVLink loads)"
+            except Exception as e:                      # e.g. no peer access between the devices: NCCL still works
+                sys.stderr.write(f"peer attach failed ({e}); using NCCL\n")
     flush = torch.empty(L2_FLUSH_MB << 20, dtype=torch.uint8, device="cuda")
 
     # ---- value: inputs resident in HBM; W warm-up iterations, then exactly K timed LM iterations -------------------

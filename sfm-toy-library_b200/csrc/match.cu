@@ -15,6 +15,8 @@
 //   scan_sums_kernel            exclusive scan of the per-block survivor counts (single CTA, chained)
 //   scatter_kernel              order-preserving compaction into (queryIdx, trainIdx, distance) + per-pair counts
 #include "common.cuh"
+#include "match_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -23,19 +25,6 @@ constexpr int QPT = 2;                       // query rows per thread
 constexpr int QBLOCK = KNN_THREADS * QPT;    // query rows per CTA
 constexpr int TILE = 128;                    // train rows per shared-memory tile
 constexpr int SCAN_THREADS = 1024;
-
-struct PairDesc {          // one (left,right) image pair
-    int q_row, nq;         // rows of the left image inside the descriptor array
-    int t_row, nt;         // rows of the right image
-    int64_t out_row;       // first row of this pair in the flattened [sum nq] arrays
-};
-
-struct Top2 { int d0, i0, d1, i1; };
-
-__device__ __forceinline__ void top2_insert(Top2& b, int d, int j) {
-    if (d < b.d0) { b.d1 = b.d0; b.i1 = b.i0; b.d0 = d; b.i0 = j; }
-    else if (d < b.d1) { b.d1 = d; b.i1 = j; }
-}
 
 template <int WORDS>
 __global__ void __launch_bounds__(KNN_THREADS)
@@ -228,29 +217,39 @@ struct sfmb200_descset {
 // core: pairs already on the host as PairDesc; descriptors on the device.  Leaves the dense compacted results in
 // d_out_* (device) and per-pair dense start positions in d_pair_start [n_pairs+1].
 static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, int words, const std::vector<PairDesc>& hp, int64_t rows, int nq_max, int nt_max,
-                      double ratio, int32_t* d_out_q, int32_t* d_out_t, float* d_out_d, int32_t* d_pair_start, int64_t* d_total, DevBuf& work) {
+                      double ratio, int32_t* d_out_q, int32_t* d_out_t, float* d_out_d, int32_t* d_pair_start, int64_t* d_total, DevBuf& work,
+                      int** d_tc_error = nullptr) {
     const int n_pairs = (int)hp.size();
     const int qblocks = ceil_div(nq_max, QBLOCK);
-    const int splits = choose_splits(ctx->sm_count, (int64_t)qblocks * n_pairs, nt_max);
+    // 32-byte descriptors (ORB, the reference's case): exact integer GEMM on the tensor cores (match_tc.cu);
+    // SFMB200_MATCH=popc forces the XOR/POPC kernel (other widths always use it)
+    const char* mode = getenv("SFMB200_MATCH");
+    const bool use_tc = words == 8 && !(mode && strcmp(mode, "popc") == 0);
+    const int splits = use_tc ? match_tc_splits(ctx->sm_count, n_pairs, nq_max, nt_max) : choose_splits(ctx->sm_count, (int64_t)qblocks * n_pairs, nt_max);
     const int nblk = (int)ceil_div64(rows, SCAN_THREADS);
     size_t bytes = Carver::pad(sizeof(PairDesc) * n_pairs) + Carver::pad(sizeof(int4) * rows * splits) + Carver::pad(4 * rows) * 3 +
-                   Carver::pad(rows) + Carver::pad(4 * (size_t)nblk) + 4096;
+                   Carver::pad(rows) + Carver::pad(4 * (size_t)nblk) + 8192;
     SFM_CUDA(ctx, work.reserve(bytes));
     Carver cv(work.p);
     PairDesc* d_pairs = cv.take<PairDesc>(n_pairs);
     int4* d_partial = cv.take<int4>((size_t)rows * splits);
     int32_t* d_best_t = cv.take<int32_t>(rows); float* d_best_d = cv.take<float>(rows); int32_t* d_rank = cv.take<int32_t>(rows);
-    uint8_t* d_flag = cv.take<uint8_t>(rows); int32_t* d_bsum = cv.take<int32_t>(nblk);
+    uint8_t* d_flag = cv.take<uint8_t>(rows); int32_t* d_bsum = cv.take<int32_t>(nblk); int* d_err = cv.take<int>(4);
     SFM_CUDA(ctx, cudaMemcpyAsync(d_pairs, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid(qblocks * splits, n_pairs);
-    switch (words) {
+    if (use_tc) {
+        SFM_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+        int rc = match_tc_launch(ctx, d_desc, d_pairs, n_pairs, nq_max, splits, d_partial, d_err);
+        if (rc) return rc;
+        if (d_tc_error) *d_tc_error = d_err;
+    } else switch (words) {
         case 4: knn2_hamming_kernel<4><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial); break;
         case 8: knn2_hamming_kernel<8><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial); break;
         case 16: knn2_hamming_kernel<16><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial); break;
         case 32: knn2_hamming_kernel<32><<<grid, KNN_THREADS, 0, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial); break;
         default: return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "desc_bytes must be 16, 32, 64 or 128 (got %d)", words * 4);
     }
-    SFM_LAUNCH_CHECK(ctx);
+    if (!use_tc) SFM_LAUNCH_CHECK(ctx);
     merge_flag_scan_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_partial, splits, rows, ratio, 0, d_best_t, d_best_d, d_rank, d_flag, d_bsum);
     SFM_LAUNCH_CHECK(ctx);
     scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_bsum, nblk, d_total);
@@ -339,7 +338,8 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     Carver cv(dense.p);
     int32_t* d_q = cv.take<int32_t>(rows); int32_t* d_t = cv.take<int32_t>(rows); float* d_d = cv.take<float>(rows);
     int32_t* d_start = cv.take<int32_t>(n_pairs + 1); int64_t* d_total = cv.take<int64_t>(1);
-    rc = match_core(ctx, set->d_desc, set->words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb);
+    int* d_tc_err = nullptr;
+    rc = match_core(ctx, set->d_desc, set->words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb, &d_tc_err);
     if (rc) return rc;
     // read back: pair starts + total, then only the survivors
     SFM_CUDA(ctx, ctx->pinned.reserve(Carver::pad(sizeof(int32_t) * (n_pairs + 1)) + 512 + 12 * (size_t)rows));
@@ -347,7 +347,10 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     int64_t* h_total = (int64_t*)((char*)ctx->pinned.p + Carver::pad(sizeof(int32_t) * (n_pairs + 1)));
     SFM_CUDA(ctx, cudaMemcpyAsync(h_start, d_start, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(ctx, cudaMemcpyAsync(h_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    int h_tc_err = 0;
+    if (d_tc_err) SFM_CUDA(ctx, cudaMemcpyAsync(&h_tc_err, d_tc_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_tc_err) return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "tcgen05 matcher: an MMA completion barrier timed out");
     const int64_t total = *h_total;
     char* stage = (char*)ctx->pinned.p + Carver::pad(sizeof(int32_t) * (n_pairs + 1)) + 256;
     int32_t* hq = (int32_t*)stage; int32_t* ht = hq + total; float* hd = (float*)(ht + total);

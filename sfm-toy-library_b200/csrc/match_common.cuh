@@ -1,0 +1,23 @@
+// match_common.cuh -- types shared by the two Hamming knn2 kernels (match.cu: XOR/POPC, match_tc.cu: tcgen05) and their epilogue.
+#pragma once
+#include "common.cuh"
+#include <climits>
+
+struct PairDesc {          // one (left,right) image pair
+    int q_row, nq;         // rows of the left image inside the descriptor array
+    int t_row, nt;         // rows of the right image
+    int64_t out_row;       // first row of this pair in the flattened [sum nq] arrays
+};
+
+struct Top2 { int d0, i0, d1, i1; };
+
+// ordering of cv::batchDistance (K=2): lexicographic on (distance, trainIdx) when candidates arrive in ascending index
+__device__ __forceinline__ void top2_insert(Top2& b, int d, int j) {
+    if (d < b.d0) { b.d1 = b.d0; b.i1 = b.i0; b.d0 = d; b.i0 = j; }
+    else if (d < b.d1) { b.d1 = d; b.i1 = j; }
+}
+
+// tcgen05 path (match_tc.cu), 32-byte descriptors only
+int match_tc_splits(int sm_count, int n_pairs, int nq_max, int nt_max);
+int match_tc_launch(sfmb200_ctx* ctx, const uint32_t* d_desc, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
+                    int4* d_partial, int* d_error_flag);

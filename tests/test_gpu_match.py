@@ -86,3 +86,16 @@ def test_config4_properties_full_size(ctx):
     x = np.unpackbits(b[q] ^ a[t], axis=1).sum(1)
     np.testing.assert_array_equal(x.astype(np.float32), d)                   # reported distance is the true Hamming distance
     assert 0.15 * 5000 < len(q) < 0.3 * 5000
+
+
+@pytest.mark.parametrize("nq,nt", [(255, 257), (5000, 5000), (130, 9000), (4999, 513)])
+def test_popc_and_tensor_core_paths_are_bit_identical(ctx, oracle, monkeypatch, nq, nt):
+    """32-byte descriptors default to the tcgen05 integer-GEMM kernel (match_tc.cu); SFMB200_MATCH=popc forces the
+    XOR/POPC kernel.  Both must reproduce the oracle exactly (indices, distances, tie-breaks)."""
+    t = synth.make_descriptors(nt % 91, nt); q = synth.make_descriptors(nq % 83 + 200, nq, prev=t)
+    t[5:9] = t[4]                                                            # duplicate train rows: tie-break inside one MMA tile
+    ref = oracle.match_hamming(q, t)
+    monkeypatch.setenv("SFMB200_MATCH", "popc")
+    _same(ctx.match_knn2_ratio(q, t), ref)
+    monkeypatch.setenv("SFMB200_MATCH", "tc")
+    _same(ctx.match_knn2_ratio(q, t), ref)
