@@ -212,11 +212,14 @@ struct sfmb200_descset {
     uint32_t* d_desc = nullptr;
     std::vector<int32_t> img_off;
     int n_img = 0, words = 0, max_rows = 0;
+    // tcgen05 path (32-byte descriptors): operands expanded once to signed bytes, 64 KB blocks of 256 rows
+    uint8_t* d_exp = nullptr;
+    std::vector<int32_t> img_blk;      // first block of each image
 };
 
 // core: pairs already on the host as PairDesc; descriptors on the device.  Leaves the dense compacted results in
 // d_out_* (device) and per-pair dense start positions in d_pair_start [n_pairs+1].
-static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, int words, const std::vector<PairDesc>& hp, int64_t rows, int nq_max, int nt_max,
+static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d_exp, int words, const std::vector<PairDesc>& hp, int64_t rows, int nq_max, int nt_max,
                       double ratio, int32_t* d_out_q, int32_t* d_out_t, float* d_out_d, int32_t* d_pair_start, int64_t* d_total, DevBuf& work,
                       int** d_tc_error = nullptr) {
     const int n_pairs = (int)hp.size();
@@ -224,7 +227,7 @@ static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, int words, const
     // 32-byte descriptors (ORB, the reference's case): exact integer GEMM on the tensor cores (match_tc.cu);
     // SFMB200_MATCH=popc forces the XOR/POPC kernel (other widths always use it)
     const char* mode = getenv("SFMB200_MATCH");
-    const bool use_tc = words == 8 && !(mode && strcmp(mode, "popc") == 0);
+    const bool use_tc = words == 8 && d_exp != nullptr && !(mode && strcmp(mode, "popc") == 0);
     const int splits = use_tc ? match_tc_splits(ctx->sm_count, n_pairs, nq_max, nt_max) : choose_splits(ctx->sm_count, (int64_t)qblocks * n_pairs, nt_max);
     const int nblk = (int)ceil_div64(rows, SCAN_THREADS);
     size_t bytes = Carver::pad(sizeof(PairDesc) * n_pairs) + Carver::pad(sizeof(int4) * rows * splits) + Carver::pad(4 * rows) * 3 +
@@ -239,7 +242,7 @@ static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, int words, const
     dim3 grid(qblocks * splits, n_pairs);
     if (use_tc) {
         SFM_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
-        int rc = match_tc_launch(ctx, d_desc, d_pairs, n_pairs, nq_max, splits, d_partial, d_err);
+        int rc = match_tc_launch(ctx, d_exp, d_pairs, n_pairs, nq_max, splits, d_partial, d_err);
         if (rc) return rc;
         if (d_tc_error) *d_tc_error = d_err;
     } else switch (words) {
@@ -266,7 +269,9 @@ static int build_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32
         const int l = pairs[2 * p], r = pairs[2 * p + 1];
         if (l < 0 || r < 0 || l >= set->n_img || r >= set->n_img) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "pair %d: image id out of range", p);
         PairDesc d; d.q_row = set->img_off[l]; d.nq = set->img_off[l + 1] - d.q_row; d.t_row = set->img_off[r]; d.nt = set->img_off[r + 1] - d.t_row;
-        d.out_row = rows; rows += d.nq; hp[p] = d;
+        d.out_row = rows; rows += d.nq;
+        d.q_blk = set->img_blk.empty() ? 0 : set->img_blk[l]; d.t_blk = set->img_blk.empty() ? 0 : set->img_blk[r];
+        hp[p] = d;
         nq_max = std::max(nq_max, d.nq); nt_max = std::max(nt_max, d.nt);
     }
     return SFMB200_OK;
@@ -294,6 +299,28 @@ int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc, const int32_t*
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { cudaFree(s->d_desc); delete s; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e)); }
     }
+    if (s->words == 8 && img_off[n_img] > 0) {      // expanded operand store for the tensor-core kernel
+        const int br = match_tc_block_rows();
+        std::vector<int2> blocks;
+        s->img_blk.resize(n_img + 1);
+        for (int i = 0; i < n_img; ++i) {
+            s->img_blk[i] = (int)blocks.size();
+            const int rows = img_off[i + 1] - img_off[i];
+            for (int b0 = 0; b0 < rows; b0 += br) blocks.push_back(make_int2(img_off[i] + b0, std::min(br, rows - b0)));
+        }
+        s->img_blk[n_img] = (int)blocks.size();
+        int2* d_blocks = nullptr;
+        e = cudaMalloc(&s->d_exp, blocks.size() * match_tc_block_bytes());
+        if (e == cudaSuccess) e = cudaMalloc(&d_blocks, blocks.size() * sizeof(int2));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
+        int rc = e == cudaSuccess ? match_tc_expand(ctx, s->d_desc, d_blocks, (int)blocks.size(), s->d_exp) : SFMB200_ERR_NOMEM;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (d_blocks) cudaFree(d_blocks);
+        if (e != cudaSuccess || rc) {
+            cudaFree(s->d_desc); if (s->d_exp) cudaFree(s->d_exp); delete s;
+            return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "expanded operand store: %s", cudaGetErrorString(e));
+        }
+    }
     *out = s;
     return SFMB200_OK;
 }
@@ -302,6 +329,7 @@ void sfmb200_descset_destroy(sfmb200_descset* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaFree(s->d_desc);
+    if (s->d_exp) cudaFree(s->d_exp);
     delete s;
 }
 
@@ -315,7 +343,7 @@ int sfmb200_match_pairs_device(sfmb200_ctx* ctx, const sfmb200_descset* set, con
     int rc = build_pairs(ctx, set, pairs, n_pairs, hp, rows, nq_max, nt_max);
     if (rc) return rc;
     if (rows == 0) return SFMB200_OK;
-    return match_core(ctx, set->d_desc, set->words, hp, rows, nq_max, nt_max, ratio, d_out_q, d_out_t, d_out_d, d_pair_start, d_total, ctx->scratch);
+    return match_core(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, d_out_q, d_out_t, d_out_d, d_pair_start, d_total, ctx->scratch);
 }
 
 int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, double ratio,
@@ -339,7 +367,7 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     int32_t* d_q = cv.take<int32_t>(rows); int32_t* d_t = cv.take<int32_t>(rows); float* d_d = cv.take<float>(rows);
     int32_t* d_start = cv.take<int32_t>(n_pairs + 1); int64_t* d_total = cv.take<int64_t>(1);
     int* d_tc_err = nullptr;
-    rc = match_core(ctx, set->d_desc, set->words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb, &d_tc_err);
+    rc = match_core(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb, &d_tc_err);
     if (rc) return rc;
     // read back: pair starts + total, then only the survivors
     SFM_CUDA(ctx, ctx->pinned.reserve(Carver::pad(sizeof(int32_t) * (n_pairs + 1)) + 512 + 12 * (size_t)rows));

@@ -7,6 +7,7 @@ struct PairDesc {          // one (left,right) image pair
     int q_row, nq;         // rows of the left image inside the descriptor array
     int t_row, nt;         // rows of the right image
     int64_t out_row;       // first row of this pair in the flattened [sum nq] arrays
+    int q_blk, t_blk;      // first 256-row block of the left / right image in the expanded operand store (tcgen05 path)
 };
 
 struct Top2 { int d0, i0, d1, i1; };
@@ -19,5 +20,8 @@ __device__ __forceinline__ void top2_insert(Top2& b, int d, int j) {
 
 // tcgen05 path (match_tc.cu), 32-byte descriptors only
 int match_tc_splits(int sm_count, int n_pairs, int nq_max, int nt_max);
-int match_tc_launch(sfmb200_ctx* ctx, const uint32_t* d_desc, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
+size_t match_tc_block_bytes();
+int match_tc_block_rows();
+int match_tc_expand(sfmb200_ctx* ctx, const uint32_t* d_desc, const int2* d_blocks, int n_blocks, uint8_t* d_E);
+int match_tc_launch(sfmb200_ctx* ctx, const uint8_t* d_E, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
                     int4* d_partial, int* d_error_flag);

@@ -3,16 +3,18 @@
 // For 256-bit descriptors  ham(q,t) = popc(q) + popc(t) - 2 * <q,t>  with q,t in {0,1}^256: the
 // inner products of a 128-query x 256-train tile are ONE accumulator tile of  tcgen05.mma.kind::i8  (u8 x u8 -> s32,
 // exact: every sum <= 256), M=128 N=256 K=32 per instruction, 8 instructions per tile, accumulators in TMEM.
-//   * operands: the packed 32-byte descriptors are read from HBM as they are (no expanded copy) and expanded to one
-//     byte per bit inside the kernel while they are written to shared memory in the UMMA K-major, no-swizzle
-//     ("interleaved") canonical layout: core matrix = 8 rows x 16 bytes, LBO = distance between the two 16-byte K chunks
-//     of one instruction, SBO = distance between 8-row groups (cute/arch/mma_sm100_desc.hpp, make_umma_desc<Major::K>).
-//   * one elected thread issues the 8 MMAs of a tile and commits them to an mbarrier; the 128 threads (one per query
-//     row = one per TMEM lane) then pull the accumulators with tcgen05.ld.32x32b.x32 and keep the running top-2 in
-//     registers with exactly the ordering of the XOR/POPC kernel (strict '<', ascending train index), so the result is
-//     bit-identical and feeds the same merge / ratio-test / compaction epilogue (match.cu).
-//   * two accumulator stages (2 x 256 of the 512 TMEM columns) and two B stages in shared memory: the MMAs of tile t+1
-//     run while tile t is being reduced.
+//   * operands: bits are mapped to SIGNED bytes +1/-1, so that  <a,b> = 256 - 2*hamming  and the epilogue needs one compare
+//     per element and no popcount terms.  The expansion happens ONCE per descriptor set (expand_blocks_kernel) into 64 KB
+//     blocks of 256 rows laid out in the UMMA K-major, no-swizzle ("interleaved") canonical form: core matrix = 8 rows x
+//     16 bytes, LBO = distance between the two 16-byte K chunks of one instruction, SBO = distance between 8-row groups
+//     (cute/arch/mma_sm100_desc.hpp, make_umma_desc<Major::K>).  A tile then travels HBM -> shared memory as plain
+//     cp.async.bulk copies completing on an mbarrier (no tensor map needed: a block is contiguous).
+//   * warp-specialised pipeline: a loader thread (3 shared-memory stages of the train operand), an MMA thread (8
+//     tcgen05.mma per tile, two 256-column accumulator stages = all 512 TMEM columns; tcgen05.commit releases the smem
+//     stage and publishes the accumulator), and 4 epilogue warps (one per TMEM lane quarter, thread = query row) that pull
+//     the accumulators with tcgen05.ld.32x32b.x32 and keep the running top-2 in registers with exactly the ordering of
+//     the XOR/POPC kernel (strict '<', ascending train index) -> bit-identical results, same merge / ratio-test /
+//     compaction epilogue (match.cu).
 // Only descriptor width 32 bytes (ORB, the reference's case); other widths use the XOR/POPC kernel.
 #include "common.cuh"
 #include "match_common.cuh"
@@ -20,15 +22,16 @@
 namespace {
 
 constexpr int TC_M = 128;            // query rows per CTA  (UMMA M, TMEM lanes)
-constexpr int TC_N = 256;            // train rows per tile (UMMA N, TMEM columns per stage)
-constexpr int TC_K = 256;            // descriptor bits = K elements (one byte each after expansion)
-constexpr int TC_THREADS = 128;
-constexpr int TC_A_BYTES = TC_M * TC_K;      // 32 KB
-constexpr int TC_B_BYTES = TC_N * TC_K;      // 64 KB per stage
-constexpr int TC_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 2 * TC_N * 4 + 64;
-// instruction descriptor (UMMA::InstrDescriptor): c_format S32 (2) @bit4, a/b format UINT8 (0), K-major both,
+constexpr int TC_N = 256;            // train rows per tile (UMMA N, TMEM columns per accumulator stage) = rows per expanded block
+constexpr int TC_K = 256;            // descriptor bits = K elements (one signed byte each after expansion)
+constexpr int TC_BLOCK_BYTES = TC_N * TC_K;              // 64 KB: one 256-row block of expanded operands
+constexpr int TC_A_BYTES = TC_M * TC_K;                  // 32 KB
+constexpr int TC_BSTAGES = 3;                            // shared-memory stages of the train operand
+constexpr int TC_THREADS = 192;                          // warps 0-3: epilogue (one TMEM lane quarter each), warp 4: loader, warp 5: MMA issuer
+constexpr int TC_SMEM = TC_A_BYTES + TC_BSTAGES * TC_BLOCK_BYTES + 256;
+// instruction descriptor (UMMA::InstrDescriptor): c_format S32 (2) @bit4, a/b format signed INT8 (1) @bits 7/10, K-major both,
 // n_dim = N>>3 @bit17, m_dim = M>>4 @bit24
-constexpr uint32_t TC_IDESC = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -38,43 +41,37 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
            (1ull << 46);
 }
 
-// byte offset of (row r, 16-byte K chunk kc) inside a tile of R rows in the canonical layout:
-//   chunk-major: [kc][r/8][r%8][16 B]  ->  LBO = R*16 bytes between K chunks, SBO = 128 bytes between 8-row groups
-__device__ __forceinline__ uint32_t tile_offset(int r, int kc, int R) { return (uint32_t)kc * (R * 16) + (uint32_t)(r >> 3) * 128 + (uint32_t)(r & 7) * 16; }
-
-// 16 descriptor bits -> 16 bytes of 0/1 (little endian bit order = element order k)
+// 16 descriptor bits -> 16 signed bytes: bit 1 -> +1, bit 0 -> -1   (sum over k of a_k b_k = 256 - 2 * hamming)
+__device__ __forceinline__ uint32_t pm1(uint32_t nib) {
+    const uint32_t x = (nib * 0x00204081u) & 0x01010101u;
+    return x | ((x ^ 0x01010101u) * 0xFFu);
+}
 __device__ __forceinline__ uint4 expand16(uint32_t bits16) {
-    uint4 o;
-    o.x = ((bits16 & 0xF) * 0x00204081u) & 0x01010101u;
-    o.y = (((bits16 >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
-    o.z = (((bits16 >> 8) & 0xF) * 0x00204081u) & 0x01010101u;
-    o.w = (((bits16 >> 12) & 0xF) * 0x00204081u) & 0x01010101u;
-    return o;
+    return make_uint4(pm1(bits16 & 0xF), pm1((bits16 >> 4) & 0xF), pm1((bits16 >> 8) & 0xF), pm1((bits16 >> 12) & 0xF));
 }
 
-// expand `rows` packed descriptors (8 words each, row-major in global memory) into a canonical tile of R rows;
-// rows beyond `rows` are zero-filled.  Also writes popcounts (may be null).  All TC_THREADS threads participate.
-__device__ __forceinline__ void stage_tile(const uint32_t* __restrict__ src, int rows, int R, uint8_t* tile, int* popc) {
-    // work item = (row, word): 8 words per row, each word = two 16-byte chunks
-    for (int it = threadIdx.x; it < R * 8; it += TC_THREADS) {
-        const int w = it / R, r = it - w * R;          // consecutive threads = consecutive rows: contiguous 16-byte stores
-        const uint32_t v = r < rows ? __ldg(src + (size_t)r * 8 + w) : 0u;
-        *reinterpret_cast<uint4*>(tile + tile_offset(r, 2 * w, R)) = expand16(v & 0xFFFFu);
-        *reinterpret_cast<uint4*>(tile + tile_offset(r, 2 * w + 1, R)) = expand16(v >> 16);
-    }
-    if (popc) {
-        for (int r = threadIdx.x; r < R; r += TC_THREADS) {
-            int c = 0;
-            if (r < rows) {
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * 8)), b = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * 8 + 4));
-                c = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-            }
-            popc[r] = c;
-        }
+// Expanded operand store (built once per descriptor set): per 256-row block 64 KB in the UMMA K-major no-swizzle canonical
+// layout  [16-byte K chunk kc 0..15][row group r/8][r%8][16 B]  ->  LBO = 4096 B between K chunks, SBO = 128 B between
+// 8-row groups.  A 128-row half of a block is the same layout at start offset +2048 B per chunk, so one store serves
+// both the query (M=128) and the train (N=256) operand.  Rows beyond the image are zero (contribute nothing).
+__global__ void __launch_bounds__(256) expand_blocks_kernel(const uint32_t* __restrict__ desc, const int2* __restrict__ blocks /* (first row, valid rows) */,
+                                                            uint8_t* __restrict__ E) {
+    const int2 b = blocks[blockIdx.x];
+    uint8_t* out = E + (size_t)blockIdx.x * TC_BLOCK_BYTES;
+    for (int it = threadIdx.x; it < TC_N * 8; it += 256) {
+        const int w = it / TC_N, r = it - w * TC_N;
+        const bool valid = r < b.y;
+        const uint32_t v = valid ? __ldg(desc + (size_t)(b.x + r) * 8 + w) : 0u;
+        const uint4 lo = valid ? expand16(v & 0xFFFFu) : make_uint4(0, 0, 0, 0), hi = valid ? expand16(v >> 16) : make_uint4(0, 0, 0, 0);
+        const uint32_t off = (uint32_t)(r >> 3) * 128 + (uint32_t)(r & 7) * 16;
+        *reinterpret_cast<uint4*>(out + (size_t)(2 * w) * (TC_N * 16) + off) = lo;
+        *reinterpret_cast<uint4*>(out + (size_t)(2 * w + 1) * (TC_N * 16) + off) = hi;
     }
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory"); }
 // bounded wait: returns false if the barrier never flips (a descriptor mistake must not hang the GPU)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -85,7 +82,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     }
     return false;
 }
-
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -103,81 +103,92 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  : "r"(taddr) : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint32_t* __restrict__ desc, const PairDesc* __restrict__ pairs, int qblocks,
+// Warp-specialised: loader thread (cp.async.bulk of pre-expanded 64 KB blocks, 3 stages) -> MMA thread (8 x tcgen05.mma per
+// tile into one of 2 TMEM accumulator stages, commits release the smem stage and publish the accumulator) -> 4 epilogue
+// warps (tcgen05.ld, running top-2 per query row in registers).
+__global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8_t* __restrict__ E, const PairDesc* __restrict__ pairs, int qblocks,
                                                                      int splits, int4* __restrict__ partial, int* __restrict__ error_flag) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
-    uint8_t* sB = smem + TC_A_BYTES;                                      // two stages
-    int* sPopc = reinterpret_cast<int*>(smem + TC_A_BYTES + 2 * TC_B_BYTES);     // [2][TC_N]
-    __shared__ __align__(8) uint64_t mma_done[2];
+    uint8_t* sB = smem + TC_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_BSTAGES * TC_BLOCK_BYTES);
+    uint64_t* a_full = bars;                 // [1]
+    uint64_t* full = bars + 1;               // [TC_BSTAGES] bytes of a B stage have landed
+    uint64_t* smem_free = full + TC_BSTAGES; // [TC_BSTAGES] the MMAs that read the stage have completed
+    uint64_t* acc_full = smem_free + TC_BSTAGES;   // [2] accumulator stage holds a finished tile
+    uint64_t* acc_empty = acc_full + 2;      // [2] the 4 epilogue warps have drained the stage
     __shared__ uint32_t tmem_base_s;
 
     const PairDesc pd = pairs[blockIdx.y];
     const int qb = blockIdx.x / splits, sp = blockIdx.x % splits;
     if (qb * TC_M >= pd.nq) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // train rows of this split, tile-aligned split boundaries keep the ascending-index order inside a split
     const int tiles_total = (pd.nt + TC_N - 1) / TC_N;
     const int tiles_per_split = (tiles_total + splits - 1) / splits;
-    const int tile0 = sp * tiles_per_split, tile1 = min(tiles_total, tile0 + tiles_per_split);
+    const int tile0 = sp * tiles_per_split, ntiles = max(0, min(tiles_total, tile0 + tiles_per_split) - tile0);
+    const int q_row0 = qb * TC_M;
 
-    if (threadIdx.x == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (warp == 0) {        // TMEM: all 512 columns = two accumulator stages of 128 lanes x 256 columns (s32)
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int i = 0; i < TC_BSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(smem_free + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {        // TMEM: two accumulator stages of 128 lanes x 256 columns (s32) = all 512 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // A tile: this CTA's queries (rows beyond nq are zero)
-    const int q_row0 = qb * TC_M, q_rows = min(TC_M, pd.nq - q_row0);
-    stage_tile(desc + (size_t)(pd.q_row + q_row0) * 8, q_rows, TC_M, sA, nullptr);
-    int pq = 0;
-    {
-        const int r = threadIdx.x;
-        if (r < q_rows) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(pd.q_row + q_row0 + r) * 8)), b = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(pd.q_row + q_row0 + r) * 8 + 4));
-            pq = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-
-    Top2 best = {INT_MAX, -1, INT_MAX, -1};
     bool ok = true;
-    uint32_t phase[2] = {0, 0};
-    const int ntiles = tile1 - tile0;
 
-    auto produce = [&](int t) {      // stage train tile t into B stage (t&1) and launch its MMAs into accumulator stage (t&1)
-        const int st = t & 1;
-        const int t_row0 = (tile0 + t) * TC_N, t_rows = min(TC_N, pd.nt - t_row0);
-        stage_tile(desc + (size_t)(pd.t_row + t_row0) * 8, t_rows, TC_N, sB + st * TC_B_BYTES, sPopc + st * TC_N);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + st * TC_B_BYTES), d = tmem_base + (uint32_t)st * TC_N;
-#pragma unroll
-            for (int kk = 0; kk < TC_K / 32; ++kk) {                     // K = 32 bytes per instruction = two 16-byte chunks
-                const uint64_t ad = make_smem_desc(a0 + 2 * kk * (TC_M * 16), TC_M * 16, 128);
-                const uint64_t bd = make_smem_desc(b0 + 2 * kk * (TC_N * 16), TC_N * 16, 128);
-                tc_mma_i8(d, ad, bd, kk > 0 ? 1u : 0u);
+    if (warp == 4) {
+        if (lane == 0) {
+            // ---- loader: query tile (a 128-row half of a block: 16 chunks of 2 KB), then the train blocks
+            const uint8_t* qsrc = E + (size_t)(pd.q_blk + q_row0 / TC_N) * TC_BLOCK_BYTES + (size_t)((q_row0 / TC_M) & 1) * (TC_M * 16);
+            mbar_expect_tx(a_full, TC_A_BYTES);
+            for (int kc = 0; kc < 16; ++kc) bulk_g2s(sA + kc * (TC_M * 16), qsrc + (size_t)kc * (TC_N * 16), TC_M * 16, a_full);
+            for (int t = 0; t < ntiles && ok; ++t) {
+                const int s = t % TC_BSTAGES, u = t / TC_BSTAGES;
+                if (u > 0 && !mbar_wait(smem_free + s, (u - 1) & 1)) { ok = false; break; }
+                const uint8_t* src = E + (size_t)(pd.t_blk + tile0 + t) * TC_BLOCK_BYTES;
+                mbar_expect_tx(full + s, TC_BLOCK_BYTES);
+                for (int c = 0; c < 4; ++c) bulk_g2s(sB + s * TC_BLOCK_BYTES + c * (TC_BLOCK_BYTES / 4), src + c * (TC_BLOCK_BYTES / 4), TC_BLOCK_BYTES / 4, full + s);
             }
-            tc_commit(&mma_done[st]);
         }
-    };
-
-    if (ntiles > 0) produce(0);
-    for (int t = 0; t < ntiles; ++t) {
-        const int st = t & 1;
-        if (t + 1 < ntiles) produce(t + 1);           // overlaps with the tensor core working on tile t
-        if (ok && !mbar_wait(&mma_done[st], phase[st])) ok = false;
-        phase[st] ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (ok) {
+    } else if (warp == 5) {
+        if (lane == 0) {
+            // ---- MMA issuer
+            if (!mbar_wait(a_full, 0)) ok = false;
+            const uint32_t a0 = smem_u32(sA);
+            for (int t = 0; t < ntiles && ok; ++t) {
+                const int s = t % TC_BSTAGES, u = t / TC_BSTAGES, a = t & 1, ua = t >> 1;
+                if (!mbar_wait(full + s, u & 1)) { ok = false; break; }
+                if (ua > 0 && !mbar_wait(acc_empty + a, (ua - 1) & 1)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b0 = smem_u32(sB + s * TC_BLOCK_BYTES), d = tmem_base + (uint32_t)a * TC_N;
+#pragma unroll
+                for (int kk = 0; kk < TC_K / 32; ++kk) {                 // K = 32 bytes per instruction = two 16-byte chunks
+                    const uint64_t ad = make_smem_desc(a0 + 2 * kk * (TC_M * 16), TC_M * 16, 128);
+                    const uint64_t bd = make_smem_desc(b0 + 2 * kk * (TC_N * 16), TC_N * 16, 128);
+                    tc_mma_i8(d, ad, bd, kk > 0 ? 1u : 0u);
+                }
+                tc_commit(smem_free + s);          // B stage reusable once these MMAs have read it
+                tc_commit(acc_full + a);           // accumulator stage complete
+            }
+        }
+    } else {
+        // ---- epilogue warps: TMEM lanes [32*warp, 32*warp+32) = query rows; v = 256 - 2*hamming
+        Top2 best = {INT_MAX, -1, INT_MAX, -1};
+        int thr = INT_MIN;                                             // insert iff v > thr  <=>  hamming < best.d1
+        for (int t = 0; t < ntiles && ok; ++t) {
+            const int a = t & 1, ua = t >> 1;
+            if (!mbar_wait(acc_full + a, ua & 1)) { ok = false; break; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int t_row0 = (tile0 + t) * TC_N, t_rows = min(TC_N, pd.nt - t_row0);
-            const int* pc = sPopc + st * TC_N;
-            // this warp owns TMEM lanes [32*warp, 32*warp+32): lane field in bits [16,32) of the address
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)st * TC_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * TC_N;
 #pragma unroll 1
             for (int c0 = 0; c0 < TC_N; c0 += 32) {
                 if (c0 >= t_rows) break;                                  // warp-uniform
@@ -186,21 +197,23 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint3
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int d = pq + pc[c0 + j] - 2 * (int)v[j];
-                    if (d < best.d1 && c0 + j < t_rows) top2_insert(best, d, t_row0 + c0 + j);
+                    if ((int)v[j] > thr && c0 + j < t_rows) {
+                        top2_insert(best, (TC_K - (int)v[j]) >> 1, t_row0 + c0 + j);
+                        thr = best.d1 == INT_MAX ? INT_MIN : TC_K - 2 * best.d1;
+                    }
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + a);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                 // accumulator stage `st` and its popcounts are free again
+        const int row = q_row0 + warp * 32 + lane;
+        if (ok && row < pd.nq) partial[(size_t)(pd.out_row + row) * splits + sp] = make_int4(best.d0, best.i0, best.d1, best.i1);
     }
-    if (!ok && threadIdx.x == 0) atomicExch(error_flag, 1);
-    {
-        const int row = q_row0 + threadIdx.x;
-        if (row < pd.nq) partial[(size_t)(pd.out_row + row) * splits + sp] = make_int4(best.d0, best.i0, best.d1, best.i1);
-    }
+    if (!ok) atomicExch(error_flag, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 }  // namespace
@@ -212,13 +225,23 @@ int match_tc_splits(int sm_count, int n_pairs, int nq_max, int nt_max) {
     return splits;
 }
 
-int match_tc_launch(sfmb200_ctx* ctx, const uint32_t* d_desc, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
+size_t match_tc_block_bytes() { return TC_BLOCK_BYTES; }
+int match_tc_block_rows() { return TC_N; }
+
+int match_tc_expand(sfmb200_ctx* ctx, const uint32_t* d_desc, const int2* d_blocks, int n_blocks, uint8_t* d_E) {
+    if (n_blocks == 0) return SFMB200_OK;
+    expand_blocks_kernel<<<n_blocks, 256, 0, ctx->stream>>>(d_desc, d_blocks, d_E);
+    SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
+
+int match_tc_launch(sfmb200_ctx* ctx, const uint8_t* d_E, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
                     int4* d_partial, int* d_error_flag) {
     static bool attr_set = false;
     if (!attr_set) { SFM_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr_set = true; }
     const int qblocks = ceil_div(nq_max, TC_M);
     dim3 grid(qblocks * splits, n_pairs);
-    knn2_hamming_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(d_desc, d_pairs, qblocks, splits, d_partial, d_error_flag);
+    knn2_hamming_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(d_E, d_pairs, qblocks, splits, d_partial, d_error_flag);
     SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
