@@ -27,7 +27,8 @@ constexpr int TC_K = 256;            // descriptor bits = K elements (one signed
 constexpr int TC_BLOCK_BYTES = TC_N * TC_K;              // 64 KB: one 256-row block of expanded operands
 constexpr int TC_A_BYTES = TC_M * TC_K;                  // 32 KB
 constexpr int TC_BSTAGES = 3;                            // shared-memory stages of the train operand
-constexpr int TC_THREADS = 192;                          // warps 0-3: epilogue (one TMEM lane quarter each), warp 4: loader, warp 5: MMA issuer
+constexpr int TC_EPI_WARPS = 8;                          // two per TMEM lane quarter: warps 0-3 take columns [0,128), warps 4-7 [128,256)
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;      // + warp 8: loader, warp 9: MMA issuer
 constexpr int TC_SMEM = TC_A_BYTES + TC_BSTAGES * TC_BLOCK_BYTES + 256;
 // instruction descriptor (UMMA::InstrDescriptor): c_format S32 (2) @bit4, a/b format signed INT8 (1) @bits 7/10, K-major both,
 // n_dim = N>>3 @bit17, m_dim = M>>4 @bit24
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     uint64_t* acc_full = smem_free + TC_BSTAGES;   // [2] accumulator stage holds a finished tile
     uint64_t* acc_empty = acc_full + 2;      // [2] the 4 epilogue warps have drained the stage
     __shared__ uint32_t tmem_base_s;
+    __shared__ int4 half_best[TC_M];          // top-2 of the upper column half, merged by the lower-half warp at the end
 
     const PairDesc pd = pairs[blockIdx.y];
     const int qb = blockIdx.x / splits, sp = blockIdx.x % splits;
@@ -131,10 +133,10 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         for (int i = 0; i < TC_BSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(smem_free + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {        // TMEM: two accumulator stages of 128 lanes x 256 columns (s32) = all 512 columns
+    if (warp == TC_EPI_WARPS) {        // TMEM: two accumulator stages of 128 lanes x 256 columns (s32) = all 512 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     const uint32_t tmem_base = tmem_base_s;
     bool ok = true;
 
-    if (warp == 4) {
+    Top2 best = {INT_MAX, -1, INT_MAX, -1};
+    if (warp == TC_EPI_WARPS) {
         if (lane == 0) {
             // ---- loader: query tile (a 128-row half of a block: 16 chunks of 2 KB), then the train blocks
             const uint8_t* qsrc = E + (size_t)(pd.q_blk + q_row0 / TC_N) * TC_BLOCK_BYTES + (size_t)((q_row0 / TC_M) & 1) * (TC_M * 16);
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
                 for (int c = 0; c < 4; ++c) bulk_g2s(sB + s * TC_BLOCK_BYTES + c * (TC_BLOCK_BYTES / 4), src + c * (TC_BLOCK_BYTES / 4), TC_BLOCK_BYTES / 4, full + s);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == TC_EPI_WARPS + 1) {
         if (lane == 0) {
             // ---- MMA issuer
             if (!mbar_wait(a_full, 0)) ok = false;
@@ -180,40 +183,64 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
             }
         }
     } else {
-        // ---- epilogue warps: TMEM lanes [32*warp, 32*warp+32) = query rows; v = 256 - 2*hamming
-        Top2 best = {INT_MAX, -1, INT_MAX, -1};
-        int thr = INT_MIN;                                             // insert iff v > thr  <=>  hamming < best.d1
+        // ---- epilogue warps.  Lane quarter q = warp & 3 (hardware rule: a warp reads TMEM lanes 32*(warp%4)..+31), column
+        // half h = warp >> 2.  v = 256 - 2*hamming, so "hamming < best.d1" is "v > thr".  Per 32-column chunk: one
+        // tcgen05.ld, a 32-wide max, and a WARP-UNIFORM branch into a predicated (branch-free) insert sequence; after the
+        // first few hundred candidates most chunks take the 20-instruction fast path.
+        const int q = warp & 3, h = warp >> 2;
+        int thr = INT_MIN;
         for (int t = 0; t < ntiles && ok; ++t) {
             const int a = t & 1, ua = t >> 1;
             if (!mbar_wait(acc_full + a, ua & 1)) { ok = false; break; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int t_row0 = (tile0 + t) * TC_N, t_rows = min(TC_N, pd.nt - t_row0);
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * TC_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * TC_N + (uint32_t)h * (TC_N / 2);
 #pragma unroll 1
-            for (int c0 = 0; c0 < TC_N; c0 += 32) {
+            for (int cc = 0; cc < TC_N / 2; cc += 32) {
+                const int c0 = h * (TC_N / 2) + cc;
                 if (c0 >= t_rows) break;                                  // warp-uniform
                 uint32_t v[32];
-                tc_ld32(taddr + c0, v);
+                tc_ld32(taddr + cc, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int m = (int)v[0];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if ((int)v[j] > thr && c0 + j < t_rows) {
-                        top2_insert(best, (TC_K - (int)v[j]) >> 1, t_row0 + c0 + j);
-                        thr = best.d1 == INT_MAX ? INT_MIN : TC_K - 2 * best.d1;
+                for (int j = 1; j < 32; ++j) m = max(m, (int)v[j]);
+                const bool partial = c0 + 32 > t_rows;                    // zero-padded rows would look like hamming 128
+                if (__any_sync(0xffffffffu, m > thr) || partial) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int d = (TC_K - (int)v[j]) >> 1, idx = t_row0 + c0 + j;
+                        const bool valid = !partial || (c0 + j < t_rows);
+                        const bool lt0 = valid && d < best.d0, lt1 = valid && d < best.d1;
+                        const int nd1 = lt0 ? best.d0 : (lt1 ? d : best.d1), ni1 = lt0 ? best.i0 : (lt1 ? idx : best.i1);
+                        best.d0 = lt0 ? d : best.d0; best.i0 = lt0 ? idx : best.i0; best.d1 = nd1; best.i1 = ni1;
                     }
+                    thr = best.d1 == INT_MAX ? INT_MIN : TC_K - 2 * best.d1;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + a);
         }
-        const int row = q_row0 + warp * 32 + lane;
-        if (ok && row < pd.nq) partial[(size_t)(pd.out_row + row) * splits + sp] = make_int4(best.d0, best.i0, best.d1, best.i1);
+        if (h == 1) half_best[q * 32 + lane] = make_int4(best.d0, best.i0, best.d1, best.i1);
     }
     if (!ok) atomicExch(error_flag, 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (warp < 4) {
+        // merge the two column halves: lexicographic (distance, index), the order candidates would have arrived in
+        const int4 o = half_best[warp * 32 + lane];
+        auto lex_lt = [](int d, int i, int d2, int i2) { return d < d2 || (d == d2 && i < i2); };
+        auto ins = [&](int d, int i) {
+            if (i < 0) return;
+            if (best.i0 < 0 || lex_lt(d, i, best.d0, best.i0)) { best.d1 = best.d0; best.i1 = best.i0; best.d0 = d; best.i0 = i; }
+            else if (best.i1 < 0 || lex_lt(d, i, best.d1, best.i1)) { best.d1 = d; best.i1 = i; }
+        };
+        ins(o.x, o.y); ins(o.z, o.w);
+        const int row = q_row0 + warp * 32 + lane;
+        if (row < pd.nq) partial[(size_t)(pd.out_row + row) * splits + sp] = make_int4(best.d0, best.i0, best.d1, best.i1);
+    }
+    if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 }  // namespace
