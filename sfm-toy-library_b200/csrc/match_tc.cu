@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     uint64_t* acc_full = smem_free + TC_BSTAGES;   // [2] accumulator stage holds a finished tile
     uint64_t* acc_empty = acc_full + 2;      // [2] the 4 epilogue warps have drained the stage
     __shared__ uint32_t tmem_base_s;
-    __shared__ int4 half_best[TC_M];          // top-2 of the upper column half, merged by the lower-half warp at the end
 
     const PairDesc pd = pairs[blockIdx.y];
     const int qb = blockIdx.x / splits, sp = blockIdx.x % splits;
@@ -147,6 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     bool ok = true;
 
     Top2 best = {INT_MAX, -1, INT_MAX, -1};
+    int4* half_best = reinterpret_cast<int4*>(sA);     // top-2 of the upper column half; reuses the query tile once every MMA has retired
     if (warp == TC_EPI_WARPS) {
         if (lane == 0) {
             // ---- loader: query tile (a 128-row half of a block: 16 chunks of 2 KB), then the train blocks
