@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     bool ok = true;
 
     Top2 best = {INT_MAX, -1, INT_MAX, -1};
-    int4* half_best = reinterpret_cast<int4*>(sA);     // top-2 of the upper column half; reuses the query tile once every MMA has retired
+    // top-2 of the upper column half, merged by the lower-half warp at the end.  Lives in B stage 0: every bulk copy into a B
+    // stage is consumed (waited on) before the last accumulator is published, whereas the query-tile copy into sA may still
+    // be in flight when a split owns no train tile at all.
+    int4* half_best = reinterpret_cast<int4*>(sB);
     if (warp == TC_EPI_WARPS) {
         if (lane == 0) {
             // ---- loader: query tile (a 128-row half of a block: 16 chunks of 2 KB), then the train blocks
