@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     } else {
         // ---- epilogue warps.  Lane quarter q = warp & 3 (hardware rule: a warp reads TMEM lanes 32*(warp%4)..+31), column
         // half h = warp >> 2.  v = 256 - 2*hamming, so "hamming < best.d1" is "v > thr".  Per 32-column chunk: one
-        // tcgen05.ld, a 32-wide max, and a WARP-UNIFORM branch into a predicated (branch-free) insert sequence; after the
-        // first few hundred candidates most chunks take the 20-instruction fast path.
+        // tcgen05.ld, then per 8-column group a max and a WARP-UNIFORM branch into a predicated (branch-free) insert
+        // sequence.  (Per-element branches made the first version epilogue-bound: 8.7 k warp instructions per tile.)
         const int q = warp & 3, h = warp >> 2;
         int thr = INT_MIN;
         for (int t = 0; t < ntiles && ok; ++t) {
@@ -205,20 +205,26 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
                 uint32_t v[32];
                 tc_ld32(taddr + cc, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                int m = (int)v[0];
-#pragma unroll
-                for (int j = 1; j < 32; ++j) m = max(m, (int)v[j]);
+                // two-level filter: 8-wide group maxima, one vote per group; only groups in which SOME lane has a candidate
+                // better than its current second-best run the predicated insert sequence (expected: a fraction of a group
+                // per chunk once a few hundred candidates have been seen)
                 const bool partial = c0 + 32 > t_rows;                    // zero-padded rows would look like hamming 128
-                if (__any_sync(0xffffffffu, m > thr) || partial) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int d = (TC_K - (int)v[j]) >> 1, idx = t_row0 + c0 + j;
-                        const bool valid = !partial || (c0 + j < t_rows);
-                        const bool lt0 = valid && d < best.d0, lt1 = valid && d < best.d1;
-                        const int nd1 = lt0 ? best.d0 : (lt1 ? d : best.d1), ni1 = lt0 ? best.i0 : (lt1 ? idx : best.i1);
-                        best.d0 = lt0 ? d : best.d0; best.i0 = lt0 ? idx : best.i0; best.d1 = nd1; best.i1 = ni1;
+                for (int g = 0; g < 4; ++g) {
+                    int m = (int)v[8 * g];
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) m = max(m, (int)v[8 * g + j]);
+                    if (__any_sync(0xffffffffu, m > thr) || partial) {
+#pragma unroll
+                        for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                            const int d = (TC_K - (int)v[j]) >> 1, idx = t_row0 + c0 + j;
+                            const bool valid = !partial || (c0 + j < t_rows);
+                            const bool lt0 = valid && d < best.d0, lt1 = valid && d < best.d1;
+                            const int nd1 = lt0 ? best.d0 : (lt1 ? d : best.d1), ni1 = lt0 ? best.i0 : (lt1 ? idx : best.i1);
+                            best.d0 = lt0 ? d : best.d0; best.i0 = lt0 ? idx : best.i0; best.d1 = nd1; best.i1 = ni1;
+                        }
+                        thr = best.d1 == INT_MAX ? INT_MIN : TC_K - 2 * best.d1;
                     }
-                    thr = best.d1 == INT_MAX ? INT_MIN : TC_K - 2 * best.d1;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
