@@ -241,7 +241,7 @@ class DescriptorSet:
         off = np.zeros(npairs + 1, np.int64); cnt = np.zeros(max(npairs, 1), np.int32)
         self.ctx._check(lib().sfmb200_match_pairs(self.ctx._h, self._h, _p(pairs, C.c_int32), npairs, C.c_double(ratio),
                                                   _p(oq, C.c_int32), _p(ot, C.c_int32), _p(od, C.c_float), _p(off, C.c_int64), _p(cnt, C.c_int32)))
-        return [(oq[off[p]:off[p] + cnt[p]].copy(), ot[off[p]:off[p] + cnt[p]].copy(), od[off[p]:off[p] + cnt[p]].copy()) for p in range(npairs)]
+        return [(oq[off[p]:off[p] + cnt[p]], ot[off[p]:off[p] + cnt[p]], od[off[p]:off[p] + cnt[p]]) for p in range(npairs)]   # views
 
     def match_pairs_device(self, pairs, d_q, d_t, d_d, d_pair_start, d_total, ratio=RATIO_REFERENCE):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)

@@ -370,7 +370,9 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     rc = match_core(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb, &d_tc_err);
     if (rc) return rc;
     // read back: pair starts + total, then only the survivors
-    SFM_CUDA(ctx, ctx->pinned.reserve(Carver::pad(sizeof(int32_t) * (n_pairs + 1)) + 512 + 12 * (size_t)rows));
+    // (pinned staging is sized for the SURVIVORS, known after the first small read-back -- not for all query rows)
+    const size_t head = Carver::pad(sizeof(int32_t) * (n_pairs + 1)) + 512;
+    SFM_CUDA(ctx, ctx->pinned.reserve(head));
     int32_t* h_start = (int32_t*)ctx->pinned.p;
     int64_t* h_total = (int64_t*)((char*)ctx->pinned.p + Carver::pad(sizeof(int32_t) * (n_pairs + 1)));
     SFM_CUDA(ctx, cudaMemcpyAsync(h_start, d_start, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
@@ -380,6 +382,9 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (h_tc_err) return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "tcgen05 matcher: an MMA completion barrier timed out");
     const int64_t total = *h_total;
+    std::vector<int32_t> starts_copy(h_start, h_start + n_pairs);          // the staging buffer may move when it grows
+    SFM_CUDA(ctx, ctx->pinned.reserve(head + 12 * (size_t)total));
+    h_start = starts_copy.data();
     char* stage = (char*)ctx->pinned.p + Carver::pad(sizeof(int32_t) * (n_pairs + 1)) + 256;
     int32_t* hq = (int32_t*)stage; int32_t* ht = hq + total; float* hd = (float*)(ht + total);
     if (total) {
