@@ -208,16 +208,20 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
-    dev_ms = e0.elapsed_time(e1)
+    dev_ms_raw = e0.elapsed_time(e1)
+    # the L2 flush writes sit between the iterations on the same stream; they are benchmark hygiene, not part of the step,
+    # so their own CUDA-event time (summary.flush_ms_total) is taken out of the bracket
+    flush_ms = float(s["flush_ms_total"])
+    dev_ms = dev_ms_raw - flush_ms
     launches = ctx.kernel_launches - launches0
     clocks = sampler.stop() if sampler else None
     iters = s["num_iterations"]
     assert iters == args.steps, s
-    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, wall * 1e3, dev_ms_raw], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(p["nobs"]), float(launches), float(p["np"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms, wall_ms = t.tolist(); nobs_total, launches_total, np_total = tot.tolist()
+    dev_ms, wall_ms, dev_ms_raw = t.tolist(); nobs_total, launches_total, np_total = tot.tolist()
     value = nobs_total * iters / (dev_ms * 1e-3)
 
     # ---- e2e: the same K iterations through the one-shot C-ABI call with pinned HOST buffers ------------------------
@@ -266,8 +270,10 @@ def run_ours(args):
                            "points_total": int(np_total), "observations_total": int(nobs_total),
                            "step": "one LM iteration: residual+Jacobian+Schur pass, rank sum, dense Cholesky, back-substitution, candidate evaluation",
                            "parallelism": f"points sharded over {world} GPU(s), cameras replicated, reduced camera system summed over ranks ({exchange})",
-                           "l2": f"flushed: a {L2_FLUSH_MB} MB scratch buffer is written before every timed LM iteration (inside the timed region; per-GPU working set ~90 MB < L2)"},
-                "wall_ms_per_step": wall_ms / iters,
+                           "l2": f"flushed: a {L2_FLUSH_MB} MB scratch buffer is written before every timed LM iteration (per-GPU working set ~90 MB < L2); "
+                                 "the flush writes run inside the event bracket and their own event time is subtracted (ms_per_step_incl_flush keeps the raw bracket)"},
+                "wall_ms_per_step": wall_ms / iters, "ms_per_step_incl_flush": dev_ms_raw / iters,
+                "dense_solve_ms": s["solve_ms_total"] / max(1, s["num_linear_solves"]),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "note": f"one sfmb200_ba_solve call (create+upload from pinned host, {args.steps} LM iterations, download) = one step; mean of {reps}"},
                 "gpu_launches": int(launches_total),

@@ -138,6 +138,8 @@ typedef struct {
     double pair_ms_total;                   /* profile=1: CUDA-event time of the camera-pair block kernel (K3c), summed */
     int pair_launches;
     double camera_ms_total;                 /* profile=1: CUDA-event time of the camera-major kernel (K3b), summed (one launch per schur launch) */
+    double solve_ms_total;                  /* profile=1: CUDA-event time of the dense solve (K4: assemble, Cholesky, back substitution), summed */
+    double flush_ms_total;                  /* profile=1 and l2_flush_mb > 0: CUDA-event time of the L2 flush writes, summed (not part of the algorithm) */
     int64_t kernel_launches;                /* kernels launched by this solve */
     char message[160];
 } sfmb200_ba_summary;

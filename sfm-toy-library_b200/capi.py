@@ -37,6 +37,7 @@ class BASummary(C.Structure):
                 ("num_unsuccessful_steps", C.c_int), ("num_jacobian_passes", C.c_int), ("num_linear_solves", C.c_int),
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("total_time_s", C.c_double),
                 ("schur_ms_total", C.c_double), ("schur_launches", C.c_int), ("pair_ms_total", C.c_double), ("pair_launches", C.c_int), ("camera_ms_total", C.c_double),
+                ("solve_ms_total", C.c_double), ("flush_ms_total", C.c_double),
                 ("kernel_launches", C.c_int64),
                 ("message", C.c_char * 160)]
 

@@ -21,6 +21,7 @@
 //   LM control runs on the host from ~20 doubles read back once per iteration.
 #include "common.cuh"
 #include "ba_math.cuh"
+#include "chol.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -30,7 +31,6 @@ namespace {
 
 constexpr int PT_THREADS = 128;
 constexpr int CAM_THREADS = 128;
-constexpr int NB = 32;                 // Cholesky tile
 
 struct BAView {
     int nc, np, nobs, maxk;
@@ -455,15 +455,27 @@ __global__ void __launch_bounds__(256) pair_fill_kernel(const int32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3b: camera-major pass.  grid (chunks, nc).  Per camera: diagonal block, camera-focal column, rhs, gradient and
-// J^T J diagonal, all in registers; one reduction per CTA.
+// K3b: camera-major pass over the camera-sorted observation list.  Every CTA takes an equal, contiguous slice of the list
+// (grid = number of co-resident CTAs, one balanced wave; a per-camera grid left a third of the run to a ragged last wave)
+// and walks the cameras its slice touches.  Per camera: diagonal block, camera-focal column, rhs, gradient and J^T J
+// diagonal, all in registers; one reduction per (CTA, camera).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v) {
-    const int c = blockIdx.y;
-    const int begin = v.cm_off[c], end = v.cm_off[c + 1];
-    if (begin + (int)blockIdx.x * CAM_THREADS >= end) return;
-    const CamDerived d = v.camd[c];
+__global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int per_cta) {
+    const int start = blockIdx.x * per_cta, stop = min(v.nobs, start + per_cta);
+    if (start >= stop) return;
+    int c = 0;
+    {   // last camera whose list begins at or before `start`
+        int lo = 0, hi = v.nc - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (v.cm_off[mid] <= start) lo = mid; else hi = mid - 1; }
+        c = lo;
+    }
     const double f = *v.focal, sf = v.scale_cf[6 * v.nc];
+    __shared__ double red[CAM_THREADS / 32][48];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (; c < v.nc && v.cm_off[c] < stop; ++c) {
+    const int begin = max(start, v.cm_off[c]), end = min(stop, v.cm_off[c + 1]);
+    if (begin >= end) continue;
+    const CamDerived d = v.camd[c];
     double sc[6];
 #pragma unroll
     for (int a = 0; a < 6; ++a) sc[a] = v.scale_cf[6 * c + a];
@@ -473,7 +485,7 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v) {
     for (int a = 0; a < 21; ++a) A[a] = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) { Cf[a] = 0; R[a] = 0; Gd[a] = 0; D[a] = 0; }
-    for (int i = begin + blockIdx.x * CAM_THREADS + threadIdx.x; i < end; i += gridDim.x * CAM_THREADS) {
+    for (int i = begin + threadIdx.x; i < end; i += CAM_THREADS) {
         const int p = v.cm_pt[i];
         const double X[3] = {v.pts[3 * p], v.pts[3 * p + 1], v.pts[3 * p + 2]};
         const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
@@ -504,8 +516,6 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v) {
                 A[q] += J.Jc[a] * J.Jc[b] + J.Jc[6 + a] * J.Jc[6 + b] - (Z[a][0] * Z[b][0] + Z[a][1] * Z[b][1] + Z[a][2] * Z[b][2]);
     }
     // CTA reduction: 47 values
-    __shared__ double red[CAM_THREADS / 32][48];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < 21; ++a) { const double s = warp_sum(A[a]); if (lane == 0) red[warp][a] = s; }
 #pragma unroll
@@ -532,6 +542,8 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v) {
         else if (t == 45) { red_add(v.Sff, s); red_add(v.dcf + fidx, s); }
         else { red_add(v.rhs + fidx, s); red_add(v.gcf + fidx, s); }
     }
+    __syncthreads();            // red[] is reused by the next camera of this slice
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -555,178 +567,6 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
     } else if (r == n) val = c < n ? rhs[c] : 0.0;          // augmented row (its own pivot is forced to 1)
     else val = (r == c) ? 1.0 : 0.0;
     A[(size_t)r * npad + c] = val;
-}
-
-// Panel step k.  CTA = 4 warps = 128 threads; every CTA factors the 32x32 diagonal tile itself (11 k FMA, cheaper than a
-// cross-CTA dependency) and solves up to four sub-diagonal tiles against it.  A single warp working through the tile is
-// issue-latency bound (measured: ~5 k dependent instructions at IPC 0.09 = 26 us), so the work is restructured:
-//   phase 1  factorisation, lane = row, the 32 columns dealt round-robin to the 4 warps (8 registers each).  Per pivot the
-//            owning warp produces the column (shuffle, rsqrt, scale) and publishes it in shared memory; after ONE barrier
-//            every warp applies it to its 8 columns (8 broadcast-LDS + FMA instead of 31 in one warp).  The register set is
-//            rotated every 4 pivots so that the loop stays rolled with static register indices.
-//   phase 2  each warp solves X L^T = B for its tile, row per lane in registers (rotated like phase 1), L[c][j] as
-//            broadcast LDS.  (An explicit 32x32 inverse + product was measured slower: 15 k + 7 k cycles vs ~5 k.)
-// CTA 0 writes the factor back together with the reciprocal pivots (dinv) the back-substitution uses.  Pivots with
-// global index >= n are forced to 1 with a zero column (augmented rhs row / padding rows).
-constexpr int PANEL_WARPS = 4;
-__global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk,
-                                                                      double* __restrict__ dinv, int* __restrict__ fail) {
-    __shared__ double Ls[NB][NB + 1];          // diagonal tile, then its factor (lower)
-    __shared__ double colbuf[2][NB];
-    __shared__ double invd[NB];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int i = k + 1 + blockIdx.x * PANEL_WARPS + w;
-    const bool has_tile = i < nbk;
-    double b[NB];                               // this warp's sub-diagonal tile, row `lane`
-    if (has_tile) {
-        const double* src = A + (size_t)(i * NB + lane) * npad + k * NB;
-#pragma unroll
-        for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); b[c] = v.x; b[c + 1] = v.y; }
-    }
-    {   // diagonal tile -> shared memory; all 8 loads of a thread are issued before the first store
-        double v[NB * NB / (PANEL_WARPS * 32)];
-#pragma unroll
-        for (int u = 0; u < NB * NB / (PANEL_WARPS * 32); ++u) { const int e = threadIdx.x + u * PANEL_WARPS * 32; v[u] = A[(size_t)(k * NB + (e >> 5)) * npad + k * NB + (e & 31)]; }
-#pragma unroll
-        for (int u = 0; u < NB * NB / (PANEL_WARPS * 32); ++u) { const int e = threadIdx.x + u * PANEL_WARPS * 32; Ls[e >> 5][e & 31] = v[u]; }
-    }
-    __syncthreads();
-    // ---- phase 1: col[q] = column 4*(q + rot) + w of row `lane`  (rot = number of rotations so far)
-    double col[NB / PANEL_WARPS];
-#pragma unroll
-    for (int q = 0; q < NB / PANEL_WARPS; ++q) col[q] = Ls[lane][PANEL_WARPS * q + w];
-    bool bad = false;
-#pragma unroll 1
-    for (int jb = 0; jb < NB; jb += PANEL_WARPS) {
-#pragma unroll
-        for (int ow = 0; ow < PANEL_WARPS; ++ow) {                    // pivot j = jb + ow is column col[0] of warp ow
-            const int j = jb + ow, gj = k * NB + j;
-            if (w == ow) {
-                const double d = __shfl_sync(0xffffffffu, col[0], j);
-                double ljj, inv;
-                if (gj >= n) { ljj = 1.0; inv = 0.0; }
-                else if (!(d > 0.0) || !isfinite(d)) { bad = true; ljj = 1.0; inv = 1.0; }
-                else { inv = rsqrt(d); ljj = d * inv; }
-                const double lrj = lane == j ? ljj : (lane > j ? col[0] * inv : 0.0);
-                col[0] = lrj;
-                colbuf[j & 1][lane] = lrj;
-                if (lane == j) invd[j] = inv;
-            }
-            __syncthreads();
-            const double lrj = colbuf[j & 1][lane];
-#pragma unroll
-            for (int q = 0; q < NB / PANEL_WARPS; ++q) {
-                const int c = jb + PANEL_WARPS * q + w;               // column held in col[q]; >= NB means wrapped (finished)
-                if (c > j && c < NB) col[q] = fma(-lrj, colbuf[j & 1][c], col[q]);
-            }
-        }
-        // the pivot columns of this group are final: store them, rotate the register set by one
-        if (lane >= jb + w) Ls[lane][jb + w] = col[0]; else Ls[lane][jb + w] = 0.0;
-        const double t = col[0];
-#pragma unroll
-        for (int q = 0; q < NB / PANEL_WARPS - 1; ++q) col[q] = col[q + 1];
-        col[NB / PANEL_WARPS - 1] = t;
-    }
-    if (bad && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(fail, 1);
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        for (int e = threadIdx.x; e < NB * NB; e += PANEL_WARPS * 32) { const int r = e >> 5, c = e & 31; if (c <= r) A[(size_t)(k * NB + r) * npad + k * NB + c] = Ls[r][c]; }
-        if (threadIdx.x < NB) dinv[k * NB + threadIdx.x] = invd[threadIdx.x];
-    }
-    if (!has_tile) return;
-    // ---- phase 2: X L^T = B for row `lane`, columns in registers.  The register row is rotated by PANEL_WARPS every
-    // PANEL_WARPS pivots so that the loop stays rolled with static indices; L[c][j] arrives as a broadcast LDS.
-#pragma unroll 1
-    for (int jb = 0; jb < NB; jb += PANEL_WARPS) {
-#pragma unroll
-        for (int u = 0; u < PANEL_WARPS; ++u) {
-            const int j = jb + u;
-            const double xj = b[u] * invd[j];
-            b[u] = xj;
-#pragma unroll
-            for (int p2 = u + 1; p2 < NB; ++p2)
-                if (jb + p2 < NB) b[p2] = fma(-xj, Ls[jb + p2][j], b[p2]);
-        }
-        double t[PANEL_WARPS];
-#pragma unroll
-        for (int u = 0; u < PANEL_WARPS; ++u) t[u] = b[u];
-#pragma unroll
-        for (int p2 = 0; p2 < NB - PANEL_WARPS; ++p2) b[p2] = b[p2 + PANEL_WARPS];
-#pragma unroll
-        for (int u = 0; u < PANEL_WARPS; ++u) b[NB - PANEL_WARPS + u] = t[u];
-    }
-    double* dst = A + (size_t)(i * NB + lane) * npad + k * NB;
-#pragma unroll
-    for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(b[c], b[c + 1]);
-}
-
-// Trailing update step k: tile (i, j), k < j <= i:  A[i][j] -= A[i][k] A[j][k]^T.  blockDim = (32, 32), grid = T(T+1)/2.
-__global__ void __launch_bounds__(1024) chol_update_kernel(double* __restrict__ A, int npad, int k, int nbk) {
-    __shared__ double P[NB][NB + 1], Q[NB][NB + 1];
-    // decode blockIdx.x -> (i, j) over the lower triangle of the trailing (T x T) tile matrix
-    int t = blockIdx.x, ii = 0;
-    while (t > ii) { t -= ii + 1; ++ii; }
-    const int i = k + 1 + ii, j = k + 1 + t;
-    (void)nbk;
-    const int r = threadIdx.y, c = threadIdx.x;
-    P[r][c] = A[(size_t)(i * NB + r) * npad + k * NB + c];
-    Q[r][c] = A[(size_t)(j * NB + r) * npad + k * NB + c];
-    __syncthreads();
-    double s = 0;
-#pragma unroll 8
-    for (int m = 0; m < NB; ++m) s += P[r][m] * Q[c][m];
-    if (i != j || c <= r) A[(size_t)(i * NB + r) * npad + j * NB + c] -= s;
-}
-
-// Back substitution L^T x = y with y = row n of the factored matrix.  Single CTA of 640 threads (warp 0 + 608 workers).
-// Per 32-block (descending): warp 0 holds the diagonal tile COLUMN-wise in registers (lane c = column c) and solves it with
-// one shuffle-broadcast per unknown, while all other threads already have the loads of their part of the block row in
-// flight; then  y[c] -= sum_m L[kb*32+m][c] x_m  for the columns to the left.
-__global__ void __launch_bounds__(640) chol_backsolve_kernel(const double* __restrict__ A, const double* __restrict__ dinv, int npad, int n, double* __restrict__ x) {
-    extern __shared__ double y[];                 // [npad]
-    const int tid = threadIdx.x, lane = tid & 31, nworkers = blockDim.x - 32;
-    for (int i = tid; i < npad; i += blockDim.x) y[i] = i < n ? A[(size_t)n * npad + i] : 0.0;
-    __syncthreads();
-    for (int kb = (n - 1) / NB; kb >= 0; --kb) {
-        const int ncols = kb * NB;                // columns to the left of the diagonal tile
-        const int c0 = tid - 32;
-        const bool solver = tid < 32, has = !solver && c0 < ncols;
-        // one register array, two roles: warp 0 holds the diagonal tile column-wise (reg[r] = L[r][lane]); worker c0 holds
-        // its column of the block row (reg[m] = L[kb*32+m][c0]) -- these loads are in flight while warp 0 solves.
-        double reg[NB];
-        const double* src = A + (size_t)(kb * NB) * npad + (solver ? kb * NB + lane : (has ? c0 : 0));
-#pragma unroll
-        for (int m = 0; m < NB; ++m) reg[m] = src[(size_t)m * npad];
-        if (solver) {
-            double yc = y[kb * NB + lane];
-            const double di = dinv[kb * NB + lane];          // reciprocal pivot (0 for padding rows)
-#pragma unroll
-            for (int jj = 0; jj < NB; ++jj) {
-                const int j = NB - 1 - jj;
-                double xj = (lane == j) ? yc * di : 0.0;
-                xj = __shfl_sync(0xffffffffu, xj, j);
-                if (lane == j) yc = xj; else if (lane < j) yc = fma(-reg[j], xj, yc);
-            }
-            y[kb * NB + lane] = yc;
-        }
-        __syncthreads();
-        if (has) {
-            double s = 0;
-#pragma unroll
-            for (int m = 0; m < NB; ++m) s = fma(reg[m], y[kb * NB + m], s);
-            y[c0] -= s;
-        }
-        if (!solver) {
-            for (int c = c0 + nworkers; c < ncols; c += nworkers) {       // n > 640 only
-                double s = 0;
-#pragma unroll 8
-                for (int m = 0; m < NB; ++m) s = fma(A[(size_t)(kb * NB + m) * npad + c], y[kb * NB + m], s);
-                y[c] -= s;
-            }
-        }
-        __syncthreads();
-    }
-    for (int i = tid; i < n; i += blockDim.x) x[i] = y[i];
 }
 
 // cameras + focal: candidate = x - y*scale ; derived table of the candidate ; norms.  Single CTA.
@@ -954,9 +794,14 @@ struct sfmb200_ba_problem {
     double* locals;                   // [8] identical on every rank
     unsigned long long* gmax_pt_bits; int* fail;   // fail[0] point blocks, fail[1] dense Cholesky
     double* A; double* y_cf; double* dinv;
+    int grid_point = 0, grid_backsub = 0, grid_camera = 0; bool one_wave = true;   // persistent grids = co-resident CTA count
+    double* Linv = nullptr;           // [npad/NB][NB][NB] inverses of the diagonal tiles (dataflow Cholesky -> back substitution)
+    bool backsolve_staged = false;
+    unsigned* chol_progress = nullptr; int chol_grid_stream = 0; bool chol_stream = true;
+    unsigned* chol_ready = nullptr; unsigned chol_epoch = 0; int chol_grid = 0; bool chol_fused = true, chol_lookahead = false;   // dataflow Cholesky (K4)
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
     bool have_scale = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, evf0 = nullptr, evf1 = nullptr;
     // gather mode (K3c): Z per observation + per-camera-pair entry lists
     bool gather = true;
     double* Zbuf = nullptr; int32_t* pair_off = nullptr; int32_t* pair_blk = nullptr; uint2* pair_ent = nullptr;
@@ -984,11 +829,23 @@ static size_t point_smem_bytes(int G, int maxk) {
     return (size_t)GB * maxk * 18 * 8 + (size_t)GB * maxk * 4 + (size_t)maxk * (maxk - 1) / 2 * 2 + 16;
 }
 
+// Grid for a grid-stride kernel: exactly the number of co-resident CTAs (one balanced wave), cached per problem.
+// SFMB200_BA_GRID=legacy keeps the fixed multiple of the SM count (A/B measurements).
+template <typename K> static int resident_grid(sfmb200_ba_problem* P, int* cache, K kernel, int threads, size_t smem, int work_blocks, int legacy_per_sm) {
+    if (!P->one_wave) return std::max(1, std::min(work_blocks, P->ctx->sm_count * legacy_per_sm));
+    if (*cache == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+        *cache = per_sm * P->ctx->sm_count;
+    }
+    return std::max(1, std::min(work_blocks, *cache));
+}
+
 template <int G> static int launch_point_pass(sfmb200_ba_problem* P, const BAView& v, double inv_radius) {
     sfmb200_ctx* ctx = P->ctx;
     const int GB = PT_THREADS / G;
     if (P->gather) {
-        const int blocks = std::max(1, std::min(ceil_div(P->np, GB), ctx->sm_count * 16));
+        const int blocks = resident_grid(P, &P->grid_point, ba_point_kernel<G, true>, PT_THREADS, 0, ceil_div(P->np, GB), 16);
         ba_point_kernel<G, true><<<blocks, PT_THREADS, 0, ctx->stream>>>(v, inv_radius);
         SFM_LAUNCH_CHECK(ctx);
         return SFMB200_OK;
@@ -1011,7 +868,7 @@ template <int G> static int launch_point_norm(sfmb200_ba_problem* P, const BAVie
 template <int G> static int launch_backsub(sfmb200_ba_problem* P, const BAView& v) {
     sfmb200_ctx* ctx = P->ctx;
     const int GB = PT_THREADS / G, nxt = P->cur ^ 1;
-    const int blocks = std::max(1, std::min(ceil_div(P->np, GB), ctx->sm_count * 16));
+    const int blocks = resident_grid(P, &P->grid_backsub, ba_backsub_eval_kernel<G>, PT_THREADS, 0, ceil_div(P->np, GB), 16);
     ba_backsub_eval_kernel<G><<<blocks, PT_THREADS, 0, ctx->stream>>>(v, P->y_cf, P->cf[nxt], P->camd[nxt], P->pts[nxt], P->post);
     SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
@@ -1087,7 +944,10 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
             if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev3, ctx->stream));
         }
         if (profile && !(P->gather && P->n_pairs_nonempty > 0)) SFM_CUDA(ctx, cudaEventRecord(P->ev3, ctx->stream));
-        ba_camera_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v); SFM_LAUNCH_CHECK(ctx);
+        {
+            const int blocks = resident_grid(P, &P->grid_camera, ba_camera_kernel, CAM_THREADS, 0, ceil_div(P->nobs, CAM_THREADS), 4);
+            ba_camera_kernel<<<blocks, CAM_THREADS, 0, ctx->stream>>>(v, ceil_div(P->nobs, blocks)); SFM_LAUNCH_CHECK(ctx);
+        }
         if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev4, ctx->stream));
     }
     return ba_allreduce(P, P->red, P->red_n, 0);
@@ -1099,12 +959,30 @@ static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, dou
     ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(P->Sblk, P->Scf, P->Sff, P->rhs, P->dcf, P->nc, npad, 1.0 / radius,
                                                                                  opt->min_lm_diagonal, opt->max_lm_diagonal, P->A);
     SFM_LAUNCH_CHECK(ctx);
-    for (int k = 0; k < nbk; ++k) {
-        chol_panel_kernel<<<std::max(1, ceil_div(nbk - k - 1, PANEL_WARPS)), PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, k, nbk, P->dinv, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
-        const int T = nbk - k - 1;
-        if (T > 0) { chol_update_kernel<<<T * (T + 1) / 2, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, k, nbk); SFM_LAUNCH_CHECK(ctx); }
+    if (P->chol_fused) {
+        const bool la = P->chol_lookahead || P->chol_stream;
+        const int ntasks = chol_fused_tasks(nbk, la);
+        const int grid = std::min(ntasks, P->chol_grid);
+        if (P->chol_stream) chol_stream_kernel<<<std::min(ntasks, P->chol_grid_stream), CS_THREADS, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, P->chol_progress,
+                                                                                                                   ++P->chol_epoch, P->Linv, nullptr);
+        else if (la) chol_fused_kernel<true><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, ++P->chol_epoch, P->Linv, nullptr);
+        else chol_fused_kernel<false><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, ++P->chol_epoch, P->Linv, nullptr);
+        SFM_LAUNCH_CHECK(ctx);
+    } else {
+        for (int k = 0; k < nbk; ++k) {
+            chol_panel_kernel<<<std::max(1, ceil_div(nbk - k - 1, PANEL_WARPS)), PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, k, nbk, P->dinv, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
+            const int T = nbk - k - 1;
+            if (T > 0) { chol_update_kernel<<<T * (T + 1) / 2, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, k, nbk); SFM_LAUNCH_CHECK(ctx); }
+        }
     }
-    chol_backsolve_kernel<<<1, 640, sizeof(double) * npad, ctx->stream>>>(P->A, P->dinv, npad, P->n, P->y_cf); SFM_LAUNCH_CHECK(ctx);
+    {
+        const size_t smem = chol_backsolve_smem(npad, P->backsolve_staged);
+        if (P->backsolve_staged && P->chol_fused) chol_backsolve_kernel<true, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf);
+        else if (P->backsolve_staged) chol_backsolve_kernel<true, false><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf);
+        else if (P->chol_fused) chol_backsolve_kernel<false, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf);
+        else chol_backsolve_kernel<false, false><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf);
+        SFM_LAUNCH_CHECK(ctx);
+    }
     return SFMB200_OK;
 }
 
@@ -1157,6 +1035,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     add(sizeof(CamDerived) * (size_t)nc); add(sizeof(CamDerived) * (size_t)nc);
     add(8 * n); add(24 * (size_t)np); add(96 * (size_t)np); add(8 * (P->red_n + 32));
     add(8 * (size_t)P->npad * P->npad); add(8 * n); add(8 * (size_t)P->npad); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
+    add(4 * (size_t)(P->npad / NB) * (P->npad / NB)); add(8 * (size_t)P->npad * NB); add(4 * (size_t)(P->npad / NB));
     cudaError_t e = P->mem.reserve(bytes);
     if (e != cudaSuccess) { delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
     Carver cv(P->mem.p);
@@ -1179,6 +1058,9 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->post = P->red + P->red_n; P->xflags = (unsigned long long*)(P->post + 24); P->locals = P->post + 8; P->gmax_pt_bits = (unsigned long long*)(P->locals + 8); P->fail = (int*)(P->locals + 10);
     P->A = cv.take<double>((size_t)P->npad * P->npad); P->y_cf = cv.take<double>(n); P->dinv = cv.take<double>(P->npad);
     int32_t* obs_pt = cv.take<int32_t>(nobs); int* cnt = cv.take<int>(2 * (size_t)(nc + 1)); int* cursor = cnt + nc + 1;
+    P->chol_ready = cv.take<unsigned>((size_t)(P->npad / NB) * (P->npad / NB));
+    P->Linv = cv.take<double>((size_t)P->npad * NB);
+    P->chol_progress = cv.take<unsigned>((size_t)(P->npad / NB));
 
     cudaStream_t st = ctx->stream;
 #define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { P->mem.release(); P->gmem.release(); cudaFree(P->xmem); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
@@ -1189,6 +1071,31 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     CRT(cudaStreamSynchronize(st));     // `focal` is a stack variable
     // camera-major copy (device counting sort)
     CRT(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * (nc + 1), st));
+    {   // dataflow Cholesky: ready flags start at epoch 0; the grid must stay within the co-resident CTA count
+        const int nbk = P->npad / NB;
+        CRT(cudaMemsetAsync(P->chol_ready, 0, 4 * (size_t)nbk * nbk, st));
+        CRT(cudaMemsetAsync(P->chol_progress, 0, 4 * (size_t)nbk, st));
+        int per_sm = 0;
+        CRT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_fused_kernel<false>, PANEL_WARPS * 32, 0));
+        P->chol_grid = std::max(1, per_sm * ctx->sm_count);
+        const char* gm = getenv("SFMB200_BA_GRID");
+        P->one_wave = !(gm && strcmp(gm, "legacy") == 0);
+        const char* cm = getenv("SFMB200_BA_CHOL");
+        P->chol_fused = !(cm && strcmp(cm, "steps") == 0) && per_sm > 0;
+        P->chol_lookahead = cm && strcmp(cm, "lookahead") == 0;
+        int per_sm_stream = 0;
+        CRT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_stream, chol_stream_kernel, CS_THREADS, 0));
+        P->chol_grid_stream = std::max(1, per_sm_stream * ctx->sm_count);
+        P->chol_stream = P->chol_fused && per_sm_stream > 0 && !(cm && (strcmp(cm, "fused") == 0 || strcmp(cm, "lookahead") == 0));
+        // back substitution with the next block row staged in shared memory (cp.async) when it fits
+        const char* bm = getenv("SFMB200_BA_BACKSOLVE");
+        const size_t bs = chol_backsolve_smem(P->npad, true);
+        P->backsolve_staged = !(bm && strcmp(bm, "direct") == 0) && bs <= 220 * 1024;
+        if (P->backsolve_staged) {
+            CRT(cudaFuncSetAttribute(chol_backsolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs));
+            CRT(cudaFuncSetAttribute(chol_backsolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs));
+        }
+    }
     if (nobs) {
         const int use_smem = (size_t)nc * 8 <= 40 * 1024;
         count_cams_kernel<<<ceil_div(nobs, SORT_THREADS), SORT_THREADS, use_smem ? nc * 4 : 0, st>>>(P->obs_cam, nobs, nc, use_smem, cnt);
@@ -1202,6 +1109,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     CRT(cudaGetLastError());
     CRT(cudaMallocHost((void**)&P->h_scal, sizeof(double) * 32));
     CRT(cudaEventCreate(&P->ev0)); CRT(cudaEventCreate(&P->ev1)); CRT(cudaEventCreate(&P->ev2)); CRT(cudaEventCreate(&P->ev3)); CRT(cudaEventCreate(&P->ev4));
+    CRT(cudaEventCreate(&P->ev5)); CRT(cudaEventCreate(&P->ev6)); CRT(cudaEventCreate(&P->evf0)); CRT(cudaEventCreate(&P->evf1));
     {   // off-diagonal Schur blocks: "gather" (default; per-camera-pair lists, no atomics in the hot loop) or "red"
         const char* mode = getenv("SFMB200_BA_SCHUR");
         P->gather = !(mode && strcmp(mode, "red") == 0);
@@ -1255,6 +1163,10 @@ void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     if (P->ev2) cudaEventDestroy(P->ev2);
     if (P->ev3) cudaEventDestroy(P->ev3);
     if (P->ev4) cudaEventDestroy(P->ev4);
+    if (P->ev5) cudaEventDestroy(P->ev5);
+    if (P->ev6) cudaEventDestroy(P->ev6);
+    if (P->evf0) cudaEventDestroy(P->evf0);
+    if (P->evf1) cudaEventDestroy(P->evf1);
     for (int r = 0; r < MAX_PEERS; ++r) if (P->peer_base[r]) cudaIpcCloseMemHandle(P->peer_base[r]);
     P->gmem.release();
     P->mem.release();
@@ -1376,12 +1288,16 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
         }
         if (opt.l2_flush_mb > 0) {      // benchmark hygiene: evict the working set from L2 between iterations
             SFM_CUDA(ctx, ctx->scratch2.reserve((size_t)opt.l2_flush_mb << 20));
+            if (opt.profile) SFM_CUDA(ctx, cudaEventRecord(P->evf0, ctx->stream));
             SFM_CUDA(ctx, cudaMemsetAsync(ctx->scratch2.p, 0, (size_t)opt.l2_flush_mb << 20, ctx->stream));
+            if (opt.profile) SFM_CUDA(ctx, cudaEventRecord(P->evf1, ctx->stream));
         }
         // ---- one LM iteration on the device: pass at x, dense solve, candidate, evaluation -------------------
         rc = schur_pass(P, &opt, radius, opt.profile != 0); if (rc) return rc;
         sum->num_jacobian_passes++;
+        if (opt.profile) SFM_CUDA(ctx, cudaEventRecord(P->ev5, ctx->stream));
         rc = dense_solve(P, &opt, radius); if (rc) return rc;
+        if (opt.profile) SFM_CUDA(ctx, cudaEventRecord(P->ev6, ctx->stream));
         sum->num_linear_solves++;
         const int nxt = P->cur ^ 1;
         ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(P->cf[P->cur], P->y_cf, P->scale_cf, P->gcf, P->nc, P->cf[nxt], P->camd[nxt], P->locals,
@@ -1393,6 +1309,11 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
         SFM_CUDA(ctx, cudaMemcpyAsync(h, P->sums, 64, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaMemcpyAsync(h + 8, P->post, 8 * 16, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (opt.profile) {
+            float ms = 0;
+            if (opt.l2_flush_mb > 0 && cudaEventElapsedTime(&ms, P->evf0, P->evf1) == cudaSuccess) sum->flush_ms_total += ms;
+            if (cudaEventElapsedTime(&ms, P->ev5, P->ev6) == cudaSuccess) sum->solve_ms_total += ms;
+        }
         if (opt.profile && P->np > 0 && P->nobs > 0) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, P->ev0, P->ev1) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; }

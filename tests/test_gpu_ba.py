@@ -177,6 +177,32 @@ def test_red_and_gather_schur_modes_agree(ctx, oracle, monkeypatch):
     np.testing.assert_allclose(out["gather"][2][1], out["red"][2][1], rtol=0, atol=1e-8)
 
 
+@pytest.mark.parametrize("n_cams,n_pts", [(5, 400), (40, 3000), (100, 6000), (180, 5000)])
+def test_dataflow_and_stepwise_cholesky_agree(ctx, monkeypatch, n_cams, n_pts):
+    """The single-kernel dataflow tile Cholesky (streaming = default, plain, lookahead) against the panel/update kernel
+    sequence: same LM trajectory.
+    1 / 8 / 19 / 34 tile rows; the last case has more tiles (595) than co-resident CTAs, so CTAs own several tiles."""
+    p = synth.make_ba_problem(n_cams=n_cams, n_pts=n_pts, obs_per_pt=min(6, n_cams), seed=21)
+    out = {}
+    for mode in ("stream", "fused", "lookahead", "steps"):
+        monkeypatch.setenv("SFMB200_BA_CHOL", mode)
+        monkeypatch.setenv("SFMB200_BA_BACKSOLVE", "direct" if mode == "lookahead" else "staged")
+        prob = ctx.ba_problem(*_args(p))
+        o = capi.ba_default_options(); o.max_num_iterations = 8
+        out[mode] = (prob.run(o), prob.download())
+        prob.close()
+    for m in ("stream", "fused", "lookahead"):
+        _same_trajectory(out[m], out["steps"])
+
+
+def _same_trajectory(a, b):
+    assert a[0]["termination_type"] == b[0]["termination_type"] and a[0]["num_iterations"] == b[0]["num_iterations"]
+    assert a[0]["final_cost"] < 0.1 * a[0]["initial_cost"]
+    assert abs(a[0]["final_cost"] - b[0]["final_cost"]) < 1e-9 * b[0]["final_cost"]
+    np.testing.assert_allclose(a[1][0], b[1][0], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(a[1][1], b[1][1], rtol=0, atol=1e-8)
+
+
 def test_many_observations_per_point_and_ragged_tracks(ctx, oracle):
     """Track lengths 2..40 in one problem (G = 32 groups, multi-chunk points, long pair lists)."""
     rs = np.random.RandomState(5)
