@@ -228,17 +228,21 @@ def run_ours(args):
     def pinned(x):
         return torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
     h = [pinned(p["cams"]), pinned(p["pts"]), p["focal"], pinned(p["obs_xy"]), pinned(p["obs_cam"]), pinned(p["pt_off"])]
+    cams0, pts0 = np.array(h[0]), np.array(h[1])                       # pristine start; h[0], h[1] are overwritten with the result
     h2d = sum(x.nbytes for x in h if isinstance(x, np.ndarray)) + 8
     d2h = h[0].nbytes + h[1].nbytes + 8
     reps = 3
-    ctx.ba_solve(*h, fixed_iteration_options(capi, 1))                 # allocator / first-touch warm-up
-    barrier()
-    t0 = time.perf_counter()
+    ctx.ba_solve(*h, fixed_iteration_options(capi, args.steps), inplace=True)   # untimed warm-up solve: allocator, first touch of every code path
     e2e_iters = 0
+    rep_ms = []
     for _ in range(reps):
-        e2e_iters += ctx.ba_solve(*h, fixed_iteration_options(capi, args.steps))[3]["num_iterations"]
+        h[0][...] = cams0; h[1][...] = pts0                            # untimed: restore the inputs in the pinned buffers
+        barrier()
+        t1 = time.perf_counter()
+        e2e_iters += ctx.ba_solve(*h, fixed_iteration_options(capi, args.steps), inplace=True)[3]["num_iterations"]
+        rep_ms.append(round((time.perf_counter() - t1) * 1e3, 3))
     barrier()
-    e2e_wall = time.perf_counter() - t0
+    e2e_wall = sum(rep_ms) * 1e-3
     te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -275,7 +279,7 @@ def run_ours(args):
                 "wall_ms_per_step": wall_ms / iters, "ms_per_step_incl_flush": dev_ms_raw / iters,
                 "dense_solve_ms": s["solve_ms_total"] / max(1, s["num_linear_solves"]),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "note": f"one sfmb200_ba_solve call (create+upload from pinned host, {args.steps} LM iterations, download) = one step; mean of {reps}"},
+                        "note": f"one sfmb200_ba_solve call (create+upload from pinned host, {args.steps} LM iterations, download) = one step; mean of {reps}", "rep_ms": rep_ms},
                 "gpu_launches": int(launches_total),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": "K3 = ba_point_kernel + ba_pair_kernel + ba_camera_kernel (one residual+Jacobian+Schur pass)",

@@ -160,9 +160,17 @@ class Context:
     def ba_problem(self, cams, pts, focal, obs_xy, obs_cam, pt_off):
         return BAProblem(self, cams, pts, focal, obs_xy, obs_cam, pt_off)
 
-    def ba_solve(self, cams, pts, focal, obs_xy, obs_cam, pt_off, options=None):
-        """One-shot sfmb200_ba_solve with host buffers.  Returns (cams, pts, focal, summary dict)."""
-        cams = np.array(cams, np.float64, order="C").reshape(-1, 6); pts = np.array(pts, np.float64, order="C").reshape(-1, 3)
+    def ba_solve(self, cams, pts, focal, obs_xy, obs_cam, pt_off, options=None, inplace=False):
+        """One-shot sfmb200_ba_solve with host buffers.  Returns (cams, pts, focal, summary dict).
+        inplace=True hands the caller's float64 C-contiguous cams / pts arrays (e.g. pinned memory) to the library, which
+        overwrites them with the result -- exactly what the C ABI does; the default works on copies."""
+        if inplace:
+            for x in (cams, pts):
+                if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous and x.flags.writeable):
+                    raise ValueError("inplace=True needs writeable float64 C-contiguous arrays")
+            cams = cams.reshape(-1, 6); pts = pts.reshape(-1, 3)
+        else:
+            cams = np.array(cams, np.float64, order="C").reshape(-1, 6); pts = np.array(pts, np.float64, order="C").reshape(-1, 3)
         obs_xy = np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2); obs_cam = np.ascontiguousarray(obs_cam, np.int32)
         pt_off = np.ascontiguousarray(pt_off, np.int32)
         f = C.c_double(float(focal)); s = BASummary(); o = options or ba_default_options()

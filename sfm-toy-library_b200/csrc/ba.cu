@@ -329,7 +329,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 constexpr int PAIR_UNROLL = 8;
-__global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 8) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
                                                                    const uint2* __restrict__ pair_ent, int n_nonempty, int nseg, int splits,
                                                                    const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk) {
     const int lane = threadIdx.x & 31;
@@ -343,29 +343,34 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) ba_pair_kernel(const double* 
     const int fr = lane >> 2, fc = lane & 3;
     const bool valid = fr < 6 && fc < 3;
     const int fidx = valid ? fr * 3 + fc : 0;
-    double c0[8], c1[8];               // 8 independent accumulator fragments
+    double c0[4], c1[4];               // 4 independent accumulator fragments
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { c0[u] = 0.0; c1[u] = 0.0; }
-    int e = b0;
-    for (; e + PAIR_UNROLL <= b1; e += PAIR_UNROLL) {
+    for (int u = 0; u < 4; ++u) { c0[u] = 0.0; c1[u] = 0.0; }
+    // Entries arrive in batches of PAIR_UNROLL: lanes 0..7 fetch the batch's index pairs with ONE coalesced 64-byte load (a
+    // broadcast load per entry cost a wavefront each) and hand them round with shuffles; the NEXT batch's indices are
+    // requested before this batch's operands are consumed, so that the index round trip and the operand round trip of
+    // consecutive batches overlap (the kernel is latency bound: 83% long-scoreboard stalls).
+    uint2 cur = make_uint2(0u, 0u);
+    if (lane < PAIR_UNROLL && b0 + lane < b1) cur = __ldg(pair_ent + b0 + lane);
+    for (int e = b0; e < b1; e += PAIR_UNROLL) {
+        uint2 nxt = make_uint2(0u, 0u);
+        const int en = e + PAIR_UNROLL;
+        if (lane < PAIR_UNROLL && en + lane < b1) nxt = __ldg(pair_ent + en + lane);
         double a[PAIR_UNROLL], b[PAIR_UNROLL];
 #pragma unroll
         for (int u = 0; u < PAIR_UNROLL; ++u) {
-            const uint2 ent = __ldg(pair_ent + e + u);                // same address in every lane: one broadcast transaction
-            const double va = __ldg(Zbuf + (size_t)ent.x * 18 + fidx), vb = __ldg(Zbuf + (size_t)ent.y * 18 + fidx);
-            a[u] = valid ? va : 0.0; b[u] = valid ? vb : 0.0;
+            const unsigned ox = __shfl_sync(0xffffffffu, cur.x, u), oy = __shfl_sync(0xffffffffu, cur.y, u);
+            const bool live = valid && e + u < b1;                     // past the end: indices are 0, operands forced to 0
+            const double va = __ldg(Zbuf + (size_t)ox * 18 + fidx), vb = __ldg(Zbuf + (size_t)oy * 18 + fidx);
+            a[u] = live ? va : 0.0; b[u] = live ? vb : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < PAIR_UNROLL; ++u) dmma_m8n8k4(c0[u & 7], c1[u & 7], a[u], b[u]);
-    }
-    for (; e < b1; ++e) {
-        const uint2 ent = __ldg(pair_ent + e);
-        const double va = __ldg(Zbuf + (size_t)ent.x * 18 + fidx), vb = __ldg(Zbuf + (size_t)ent.y * 18 + fidx);
-        dmma_m8n8k4(c0[0], c1[0], valid ? va : 0.0, valid ? vb : 0.0);
+        for (int u = 0; u < PAIR_UNROLL; ++u) dmma_m8n8k4(c0[u & 3], c1[u & 3], a[u], b[u]);
+        cur = nxt;
     }
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { s0 += c0[u]; s1 += c1[u]; }
+    for (int u = 0; u < 4; ++u) { s0 += c0[u]; s1 += c1[u]; }
     // accumulator fragment: row = lane>>2, columns 2*(lane&3) and 2*(lane&3)+1
     const int cc = 2 * fc;
     if (fr < 6 && cc < 6) {
@@ -782,6 +787,7 @@ struct sfmb200_ba_problem {
     sfmb200_ctx* ctx = nullptr;
     int nc = 0, np = 0, nobs = 0, maxk = 0, G = 8, n = 0, npad = 0;
     DevBuf mem;                       // one allocation, carved below
+    DevBuf xbuf; PinBuf hpin; bool borrowed = false;   // exchange memory / pinned read-back; workspace borrowed from ctx->ba_ws
     // observations
     float2* obs_xy; int32_t* obs_cam; int32_t* pt_off; int32_t* cm_off; float2* cm_xy; int32_t* cm_pt;
     // state: x = (cf, pts), candidate, initial
@@ -811,6 +817,16 @@ struct sfmb200_ba_problem {
     void* xmem = nullptr; size_t xmem_doubles = 0; double* xtmp = nullptr; unsigned long long* xflags = nullptr;
     bool peers = false; PeerTable ptab; void* peer_base[MAX_PEERS] = {nullptr}; unsigned long long epoch = 0;
 };
+
+// give the buffers back to the context's cache (or free them when this problem allocated its own)
+static void ba_release_buffers(sfmb200_ba_problem* P) {
+    sfmb200_ctx* ctx = P->ctx;
+    if (P->borrowed) {
+        ctx->ba_ws.mem = P->mem; ctx->ba_ws.gmem = P->gmem; ctx->ba_ws.xbuf = P->xbuf; ctx->ba_ws.hpin = P->hpin;
+        ctx->ba_ws.in_use = false;
+    } else { P->mem.release(); P->gmem.release(); P->xbuf.release(); P->hpin.release(); }
+    P->mem = DevBuf(); P->gmem = DevBuf(); P->xbuf = DevBuf(); P->hpin = PinBuf(); P->xmem = nullptr; P->h_scal = nullptr; P->borrowed = false;
+}
 
 static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* opt) {
     BAView v;
@@ -1036,8 +1052,13 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     add(8 * n); add(24 * (size_t)np); add(96 * (size_t)np); add(8 * (P->red_n + 32));
     add(8 * (size_t)P->npad * P->npad); add(8 * n); add(8 * (size_t)P->npad); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
     add(4 * (size_t)(P->npad / NB) * (P->npad / NB)); add(8 * (size_t)P->npad * NB); add(4 * (size_t)(P->npad / NB));
+    if (!ctx->ba_ws.in_use) {           // borrow the cached workspace (grown below when too small)
+        P->mem = ctx->ba_ws.mem; P->gmem = ctx->ba_ws.gmem; P->xbuf = ctx->ba_ws.xbuf; P->hpin = ctx->ba_ws.hpin;
+        ctx->ba_ws.mem = DevBuf(); ctx->ba_ws.gmem = DevBuf(); ctx->ba_ws.xbuf = DevBuf(); ctx->ba_ws.hpin = PinBuf();
+        ctx->ba_ws.in_use = true; P->borrowed = true;
+    }
     cudaError_t e = P->mem.reserve(bytes);
-    if (e != cudaSuccess) { delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { ba_release_buffers(P); delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
     Carver cv(P->mem.p);
     P->obs_xy = cv.take<float2>(nobs); P->obs_cam = cv.take<int32_t>(nobs); P->pt_off = cv.take<int32_t>(np + 1); P->cm_off = cv.take<int32_t>(nc + 1);
     P->cm_xy = cv.take<float2>(nobs); P->cm_pt = cv.take<int32_t>(nobs);
@@ -1048,8 +1069,9 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     // exchange memory: [red (red_n) | post 8 | locals 8 | gmax 1 | pad 1 | fail 1 | pad][flags 2*MAX_PEERS u64]
     P->xmem_doubles = P->red_n + 24 + 2 * MAX_PEERS;
     {
-        cudaError_t ex = cudaMalloc(&P->xmem, 8 * P->xmem_doubles + 256);
-        if (ex != cudaSuccess) { P->mem.release(); delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(exchange): %s", cudaGetErrorString(ex)); }
+        cudaError_t ex = P->xbuf.reserve(8 * P->xmem_doubles + 256);
+        if (ex != cudaSuccess) { ba_release_buffers(P); delete P; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(exchange): %s", cudaGetErrorString(ex)); }
+        P->xmem = P->xbuf.p;
         cudaMemsetAsync(P->xmem, 0, 8 * P->xmem_doubles + 256, ctx->stream);
     }
     P->red = (double*)P->xmem;
@@ -1063,7 +1085,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->chol_progress = cv.take<unsigned>((size_t)(P->npad / NB));
 
     cudaStream_t st = ctx->stream;
-#define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { P->mem.release(); P->gmem.release(); cudaFree(P->xmem); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
+#define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { ba_release_buffers(P); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
     if (nobs) { CRT(cudaMemcpyAsync(P->obs_xy, obs_xy, 8 * (size_t)nobs, cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->obs_cam, obs_cam, 4 * (size_t)nobs, cudaMemcpyHostToDevice, st)); }
     if (np) { CRT(cudaMemcpyAsync(P->pt_off, pt_off, 4 * (size_t)(np + 1), cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->pts0, pts3, 24 * (size_t)np, cudaMemcpyHostToDevice, st)); }
     if (nc) CRT(cudaMemcpyAsync(P->cf0, cams6, 48 * (size_t)nc, cudaMemcpyHostToDevice, st));
@@ -1107,7 +1129,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor); ctx->launches += 1;
     }
     CRT(cudaGetLastError());
-    CRT(cudaMallocHost((void**)&P->h_scal, sizeof(double) * 32));
+    CRT(P->hpin.reserve(sizeof(double) * 32)); P->h_scal = (double*)P->hpin.p;
     CRT(cudaEventCreate(&P->ev0)); CRT(cudaEventCreate(&P->ev1)); CRT(cudaEventCreate(&P->ev2)); CRT(cudaEventCreate(&P->ev3)); CRT(cudaEventCreate(&P->ev4));
     CRT(cudaEventCreate(&P->ev5)); CRT(cudaEventCreate(&P->ev6)); CRT(cudaEventCreate(&P->evf0)); CRT(cudaEventCreate(&P->evf1));
     {   // off-diagonal Schur blocks: "gather" (default; per-camera-pair lists, no atomics in the hot loop) or "red"
@@ -1155,9 +1177,9 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
 
 void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     if (!P) return;
+    std::lock_guard<std::mutex> lk(P->ctx->mu);
     cudaSetDevice(P->ctx->device);
     cudaStreamSynchronize(P->ctx->stream);
-    if (P->h_scal) cudaFreeHost(P->h_scal);
     if (P->ev0) cudaEventDestroy(P->ev0);
     if (P->ev1) cudaEventDestroy(P->ev1);
     if (P->ev2) cudaEventDestroy(P->ev2);
@@ -1168,9 +1190,7 @@ void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     if (P->evf0) cudaEventDestroy(P->evf0);
     if (P->evf1) cudaEventDestroy(P->evf1);
     for (int r = 0; r < MAX_PEERS; ++r) if (P->peer_base[r]) cudaIpcCloseMemHandle(P->peer_base[r]);
-    P->gmem.release();
-    P->mem.release();
-    if (P->xmem) cudaFree(P->xmem);
+    ba_release_buffers(P);
     delete P;
 }
 

@@ -77,6 +77,67 @@ __device__ __forceinline__ bool chol_tile_factor(double (&col)[NB / PANEL_WARPS]
     return *bad_flag != 0;
 }
 
+// Pair-pivot variant of phase 1 (used by the streaming dataflow kernel).  The chain of phase 1 is one barrier + shared-memory
+// round trip per pivot (owner warps alternate), ~350 cycles per pivot.  Here warp w owns the column PAIRS 8q+2w, 8q+2w+1
+// (col[q][h]), so two consecutive pivots are produced inside one warp from three shuffles issued together -- d0, a(j1,j0),
+// d1 -- and one barrier serves two pivots; the validity tests are selects and the reciprocal square root is the
+// MUFU seed + one cubic refinement without the library's range branches (a non-finite result marks the pivot bad).
+// Finished columns go to Ls at once; groups_done counts published 4-column groups.
+__device__ __forceinline__ double chol_rsqrt_fast(double d) {
+    double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = y * y, e = fma(-d, t, 1.0), p2 = fma(e, 0.375, 0.5), q = y * e;
+    return fma(p2, q, y);
+}
+__device__ __forceinline__ void chol_pivot(double d, double cval, int lane, int j, bool pad, double& l, double& inv, bool& bad) {
+    const double r = chol_rsqrt_fast(d);
+    const bool good = d > 0.0 && r > 0.0 && r < 1.7976931348623157e308;
+    inv = pad ? 0.0 : (good ? r : 1.0);
+    const double ljj = pad ? 1.0 : (good ? d * r : 1.0);
+    bad = bad || (!pad && !good);
+    l = lane == j ? ljj : (lane > j ? cval * inv : 0.0);
+}
+__device__ __forceinline__ bool chol_tile_factor2(double (&col)[NB / (2 * PANEL_WARPS)][2], double (*Ls)[NB + 1], double (*cb)[2][NB], double* invd,
+                                                  int lane, int w, int gbase, int n, volatile int* groups_done, int* bad_flag) {
+    bool bad = false;
+#pragma unroll 1
+    for (int jb = 0; jb < NB; jb += 2 * PANEL_WARPS) {
+#pragma unroll
+        for (int ow = 0; ow < PANEL_WARPS; ++ow) {                    // pivots j0, j0+1 are columns col[0][0..1] of warp ow
+            const int j0 = jb + 2 * ow, j1 = j0 + 1, pp = ow & 1;
+            if (w == ow) {
+                const double a0 = col[0][0], a1 = col[0][1];
+                const double d0 = __shfl_sync(0xffffffffu, a0, j0), r10 = __shfl_sync(0xffffffffu, a0, j1), d1raw = __shfl_sync(0xffffffffu, a1, j1);
+                double l0, inv0, l1, inv1;
+                chol_pivot(d0, a0, lane, j0, gbase + j0 >= n, l0, inv0, bad);
+                const double t = r10 * inv0;                          // L(j1, j0)
+                chol_pivot(fma(-t, t, d1raw), fma(-l0, t, a1), lane, j1, gbase + j1 >= n, l1, inv1, bad);
+                cb[pp][0][lane] = l0; cb[pp][1][lane] = l1;
+                Ls[lane][j0] = l0; Ls[lane][j1] = l1;
+                if (lane == j0) invd[j0] = inv0;
+                if (lane == j1) invd[j1] = inv1;
+            }
+            chol_factor_barrier<true>();
+            if ((ow & 1) && groups_done && threadIdx.x == 0) { __threadfence_block(); *groups_done = (j1 + 1) / PANEL_WARPS; }
+            const double m0 = cb[pp][0][lane], m1 = cb[pp][1][lane];
+#pragma unroll
+            for (int q = 0; q < NB / (2 * PANEL_WARPS); ++q) {
+                const int c0 = jb + 2 * PANEL_WARPS * q + 2 * w;      // columns held in col[q][0..1]; >= NB means wrapped (finished)
+                if (c0 > j1 && c0 < NB) {
+                    const double2 u0 = *reinterpret_cast<const double2*>(&cb[pp][0][c0]), u1 = *reinterpret_cast<const double2*>(&cb[pp][1][c0]);
+                    col[q][0] = fma(-m1, u1.x, fma(-m0, u0.x, col[q][0]));
+                    col[q][1] = fma(-m1, u1.y, fma(-m0, u0.y, col[q][1]));
+                }
+            }
+        }
+        // rotate the register set by one pair
+#pragma unroll
+        for (int q = 0; q < NB / (2 * PANEL_WARPS) - 1; ++q) { col[q][0] = col[q + 1][0]; col[q][1] = col[q + 1][1]; }
+    }
+    if (bad) *bad_flag = 1;                        // a pivot is seen by its owning warp only
+    chol_factor_barrier<true>();
+    return *bad_flag != 0;
+}
+
 // Phase 2, pivots jb .. jb+PANEL_WARPS-1, for one warp: X L^T = B for row `lane`, b[] rotated so that b[0] is column jb.
 // L in Ls (rows > pivot of columns jb..jb+3 are read), reciprocal pivots in invd.  Rotates b[] by PANEL_WARPS on return, so
 // that the loop over the groups stays rolled with static register indices; L[c][j] arrives as a broadcast LDS.
@@ -419,7 +480,7 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
                                                                  double* __restrict__ Linv, unsigned long long* __restrict__ trace) {
     __shared__ __align__(16) double Pt[NB][TS], Qt[NB][TS], Xs[NB][TS];
     __shared__ double Ls[NB][NB + 1];
-    __shared__ double colbuf[2][NB];
+    __shared__ __align__(16) double colbuf[2][2][NB];
     __shared__ double invd[NB];
     __shared__ int bad_flag, groups_done, ls_groups, abort_flag;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, fr = lane >> 2, fc = lane & 3;
@@ -542,10 +603,13 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
                     *reinterpret_cast<double2*>(&Xs[8 * w + fr][8 * cb + 2 * fc]) = make_double2(v0, v1);
                 }
                 chol_factor_barrier<true>();
-                double col[NB / PANEL_WARPS];
+                double col[NB / (2 * PANEL_WARPS)][2];
 #pragma unroll
-                for (int q = 0; q < NB / PANEL_WARPS; ++q) col[q] = Xs[lane][PANEL_WARPS * q + w];
-                const bool bad = chol_tile_factor<true>(col, Ls, colbuf, invd, lane, w, i * NB, n, &groups_done, &bad_flag);
+                for (int q = 0; q < NB / (2 * PANEL_WARPS); ++q) {
+                    const double2 v = *reinterpret_cast<const double2*>(&Xs[lane][2 * PANEL_WARPS * q + 2 * w]);
+                    col[q][0] = v.x; col[q][1] = v.y;
+                }
+                const bool bad = chol_tile_factor2(col, Ls, colbuf, invd, lane, w, i * NB, n, &groups_done, &bad_flag);
                 if (bad && threadIdx.x == 0) atomicAdd(fail, 1);
                 CHOL_TRACE(5);
             } else {

@@ -53,6 +53,16 @@ struct Carver {
 
 struct CommState;   // comm.cu
 
+// Device / pinned workspace of one bundle-adjustment problem, kept by the context between problems: adjustBundle is called
+// once per added view (SfM.cpp:350, :529) and the one-shot sfmb200_ba_solve would otherwise pay cudaMalloc / cudaFree /
+// cudaMallocHost of several hundred MB on every call.  One problem at a time borrows it; further live problems allocate.
+struct BAWorkspace {
+    DevBuf mem, gmem, xbuf;
+    PinBuf hpin;
+    bool in_use = false;
+    void release() { mem.release(); gmem.release(); xbuf.release(); hpin.release(); }
+};
+
 struct sfmb200_ctx {
     int device = 0;
     int sm_count = 0;
@@ -63,6 +73,7 @@ struct sfmb200_ctx {
     DevBuf scratch;             // per-call device scratch (kernel workspace)
     DevBuf scratch2;            // per-call device scratch (stage outputs)
     PinBuf pinned;              // per-call pinned staging (results read-back)
+    BAWorkspace ba_ws;          // cached bundle-adjustment workspace
     CommState* comm = nullptr;
     int rank = 0, nranks = 1;
 };
