@@ -807,6 +807,7 @@ struct sfmb200_ba_problem {
     unsigned* chol_ready = nullptr; unsigned chol_epoch = 0; int chol_grid = 0; bool chol_fused = true, chol_lookahead = false;   // dataflow Cholesky (K4)
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
     bool have_scale = false;
+    bool camd_valid[2] = {false, false};   // camd[i] matches cf[i] (written by cam_derive or, for the candidate, by ba_cam_update_kernel)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, evf0 = nullptr, evf1 = nullptr;
     // gather mode (K3c): Z per observation + per-camera-pair entry lists
     bool gather = true;
@@ -929,6 +930,7 @@ static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt)
     }
     BAView v = make_view(P, opt);
     cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
+    P->camd_valid[P->cur] = true;
     double* colnorm = P->gcf;    // scratch: reuse (zeroed here, re-zeroed before every pass)
     SFM_CUDA(ctx, cudaMemsetAsync(colnorm, 0, sizeof(double) * n, ctx->stream));
     if (P->np > 0 && P->nobs > 0) {
@@ -945,9 +947,11 @@ static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt)
 static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius, bool profile) {
     sfmb200_ctx* ctx = P->ctx;
     BAView v = make_view(P, opt);
-    SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * P->red_n, ctx->stream));
-    SFM_CUDA(ctx, cudaMemsetAsync(P->post, 0, sizeof(double) * 20, ctx->stream));   // post, locals, gmax, fail
-    cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
+    SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * (P->red_n + 20), ctx->stream));   // red | post, locals, gmax, fail (contiguous)
+    if (!P->camd_valid[P->cur]) {       // after an accepted step the candidate's table (ba_cam_update_kernel) is already there
+        cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
+        P->camd_valid[P->cur] = true;
+    }
     if (P->np > 0 && P->nobs > 0) {
         if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev0, ctx->stream));
         int rc = DISPATCH_G(P, launch_point_pass)(P, v, 1.0 / radius); if (rc) return rc;
@@ -1170,7 +1174,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     *out = P;
     SFM_CUDA(ctx, cudaMemcpyAsync(P->cf[0], P->cf0, 8 * n, cudaMemcpyDeviceToDevice, st));
     if (np) SFM_CUDA(ctx, cudaMemcpyAsync(P->pts[0], P->pts0, 24 * (size_t)np, cudaMemcpyDeviceToDevice, st));
-    P->cur = 0; P->have_scale = false;
+    P->cur = 0; P->have_scale = false; P->camd_valid[0] = P->camd_valid[1] = false;
     SFM_CUDA(ctx, cudaStreamSynchronize(st));
     return SFMB200_OK;
 }
@@ -1201,7 +1205,7 @@ int sfmb200_ba_problem_reset(sfmb200_ba_problem* P) {
     SFM_CUDA(ctx, cudaSetDevice(ctx->device));
     SFM_CUDA(ctx, cudaMemcpyAsync(P->cf[0], P->cf0, 8 * (size_t)P->n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (P->np) SFM_CUDA(ctx, cudaMemcpyAsync(P->pts[0], P->pts0, 24 * (size_t)P->np, cudaMemcpyDeviceToDevice, ctx->stream));
-    P->cur = 0; P->have_scale = false;
+    P->cur = 0; P->have_scale = false; P->camd_valid[0] = P->camd_valid[1] = false;
     return SFMB200_OK;
 }
 
@@ -1323,11 +1327,11 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
         ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(P->cf[P->cur], P->y_cf, P->scale_cf, P->gcf, P->nc, P->cf[nxt], P->camd[nxt], P->locals,
                                                          P->post, P->gmax_pt_bits, P->fail);
         SFM_LAUNCH_CHECK(ctx);
+        P->camd_valid[nxt] = true;
         if (P->np > 0 && P->nobs > 0) { BAView v = make_view(P, &opt); rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }
         rc = ba_allreduce(P, P->post, 7, 1); if (rc) return rc;   // sums: candidate cost, model, norms, failure counts; max: |g| of the points
         // read back: sums[8] | post[8] locals[8]
-        SFM_CUDA(ctx, cudaMemcpyAsync(h, P->sums, 64, cudaMemcpyDeviceToHost, ctx->stream));
-        SFM_CUDA(ctx, cudaMemcpyAsync(h + 8, P->post, 8 * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(h, P->sums, 8 * 24, cudaMemcpyDeviceToHost, ctx->stream));      // sums[8] | post[8] | locals[8] are contiguous
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (opt.profile) {
             float ms = 0;
