@@ -32,8 +32,27 @@ namespace {
 constexpr int PT_THREADS = 128;
 constexpr int CAM_THREADS = 128;
 
+// Levenberg-Marquardt control state, resident on the device: the kernels of an iteration read `cur` (which of the two
+// state buffers is x), `radius` and `status` from it, ba_lm_control_kernel updates it after every iteration, and the host
+// only reads it back once per chunk of iterations (no stream sync per iteration).
+struct LMState {
+    double radius, decrease_factor, x_cost, x_norm, gmax, initial_cost;
+    double msg_a, msg_b;              // numbers quoted in the termination message
+    double last_rho;
+    int cur, iter, invalid_steps, new_point;
+    int status;                       // 0 = running; otherwise LM_* reason, every later kernel of the chunk is a no-op
+    int termination_type;
+    int num_successful, num_unsuccessful;
+    int passes;                       // iterations whose kernels actually ran
+};
+enum { LM_RUNNING = 0, LM_EVAL_FAILED = 1, LM_GRADIENT_TOL = 2, LM_MAX_TIME = 3, LM_MAX_ITER = 4, LM_MIN_RADIUS = 5, LM_INVALID_STEPS = 6,
+       LM_PARAMETER_TOL = 7, LM_FUNCTION_TOL = 8 };
+
 struct BAView {
     int nc, np, nobs, maxk;
+    // device-resident LM loop (st != nullptr): both state buffers; the kernels pick x = buffer st->cur themselves
+    const LMState* st;
+    double* cf2[2]; double* pts2[2]; CamDerived* camd2[2];
     // point-major observations
     const float2* obs_xy; const int32_t* obs_cam; const int32_t* pt_off;
     // camera-major copy
@@ -50,6 +69,20 @@ struct BAView {
     int* fail;                                                        // count of non-SPD point blocks
     double min_diag, max_diag;
 };
+
+// The current x of a kernel: the view's own pointers, or -- inside an LM chunk -- buffer st->cur.  run = false when the solve
+// has already terminated (the kernel is a no-op).  (Kept out of BAView: writing to the by-value parameter struct makes the
+// compiler copy all of it to local memory.)
+struct LMX { const double* focal; const double* pts; const CamDerived* camd; bool run; };
+__device__ __forceinline__ LMX lm_x(const BAView& v) {
+    LMX x; x.focal = v.focal; x.pts = v.pts; x.camd = v.camd; x.run = true;
+    if (v.st) {
+        x.run = v.st->status == LM_RUNNING;
+        const int cur = v.st->cur;
+        x.focal = v.cf2[cur] + 6 * v.nc; x.pts = v.pts2[cur]; x.camd = v.camd2[cur];
+    }
+    return x;
+}
 
 __device__ __forceinline__ void red_add(double* p, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
@@ -165,7 +198,10 @@ __global__ void fill_kernel(double* __restrict__ p, size_t n, double v) {
 // Shared memory per group: Z [maxk][18] + camera ids [maxk]; pair table shared by the CTA.
 // ---------------------------------------------------------------------------------------------------------------
 template <int G, bool GATHER>
-__global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double inv_radius) {
+__global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, double inv_radius) {
+    const LMX x = lm_x(v);
+    if (!x.run) return;
+    if (v.st) inv_radius = 1.0 / v.st->radius;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GB = PT_THREADS / G, GW = 32 / G;
     const int maxk = v.maxk;
@@ -183,7 +219,7 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
     const int group_in_block = warp * GW + gi;
     double* Zg = GATHER ? nullptr : Zall + (size_t)group_in_block * maxk * 18;
     int* camg = GATHER ? nullptr : camall + group_in_block * maxk;
-    const double f = *v.focal, sf = v.scale_cf[6 * v.nc];
+    const double f = *x.focal, sf = v.scale_cf[6 * v.nc];
     const int nb = v.nc;
 
     double acc_cost = 0, acc_xn = 0, acc_sff = 0, acc_rf = 0, acc_gmax = 0;
@@ -195,7 +231,7 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
         double X[3] = {0, 0, 0}, sp[3] = {1, 1, 1};
         if (active) {
             o0 = v.pt_off[p]; k = v.pt_off[p + 1] - o0;
-            X[0] = v.pts[3 * p]; X[1] = v.pts[3 * p + 1]; X[2] = v.pts[3 * p + 2];
+            X[0] = x.pts[3 * p]; X[1] = x.pts[3 * p + 1]; X[2] = x.pts[3 * p + 2];
             sp[0] = v.scale_pt[3 * p]; sp[1] = v.scale_pt[3 * p + 1]; sp[2] = v.scale_pt[3 * p + 2];
         }
         double U[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, wf[3] = {0, 0, 0}, cost = 0;
@@ -203,7 +239,7 @@ __global__ void __launch_bounds__(PT_THREADS) ba_point_kernel(BAView v, double i
         for (int j = gl; j < k; j += G) {
             const int o = o0 + j, c = v.obs_cam[o];
             ObsJ J;
-            eval_scaled(v.camd[c], X, f, v.obs_xy[o], v.scale_cf + 6 * c, sp, sf, J);
+            eval_scaled(x.camd[c], X, f, v.obs_xy[o], v.scale_cf + 6 * c, sp, sf, J);
             const double* e = J.Jp;
             U[0] += e[0] * e[0] + e[3] * e[3]; U[1] += e[0] * e[1] + e[3] * e[4]; U[2] += e[0] * e[2] + e[3] * e[5];
             U[3] += e[1] * e[1] + e[4] * e[4]; U[4] += e[1] * e[2] + e[4] * e[5]; U[5] += e[2] * e[2] + e[5] * e[5];
@@ -331,7 +367,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 constexpr int PAIR_UNROLL = 8;
 __global__ void __launch_bounds__(PAIR_WARPS * 32, 8) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
                                                                    const uint2* __restrict__ pair_ent, int n_nonempty, int nseg, int splits,
-                                                                   const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk) {
+                                                                   const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk, const LMState* __restrict__ st) {
+    if (st && st->status != LM_RUNNING) return;
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);       // index into the list of non-empty pairs
     if (q >= n_nonempty) return;
@@ -466,6 +503,8 @@ __global__ void __launch_bounds__(256) pair_fill_kernel(const int32_t* __restric
 // diagonal, all in registers; one reduction per (CTA, camera).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int per_cta) {
+    const LMX x = lm_x(v);
+    if (!x.run) return;
     const int start = blockIdx.x * per_cta, stop = min(v.nobs, start + per_cta);
     if (start >= stop) return;
     int c = 0;
@@ -474,13 +513,13 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (v.cm_off[mid] <= start) lo = mid; else hi = mid - 1; }
         c = lo;
     }
-    const double f = *v.focal, sf = v.scale_cf[6 * v.nc];
+    const double f = *x.focal, sf = v.scale_cf[6 * v.nc];
     __shared__ double red[CAM_THREADS / 32][48];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (; c < v.nc && v.cm_off[c] < stop; ++c) {
     const int begin = max(start, v.cm_off[c]), end = min(stop, v.cm_off[c + 1]);
     if (begin >= end) continue;
-    const CamDerived d = v.camd[c];
+    const CamDerived d = x.camd[c];
     double sc[6];
 #pragma unroll
     for (int a = 0; a < 6; ++a) sc[a] = v.scale_cf[6 * c + a];
@@ -492,7 +531,7 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
     for (int a = 0; a < 6; ++a) { Cf[a] = 0; R[a] = 0; Gd[a] = 0; D[a] = 0; }
     for (int i = begin + threadIdx.x; i < end; i += CAM_THREADS) {
         const int p = v.cm_pt[i];
-        const double X[3] = {v.pts[3 * p], v.pts[3 * p + 1], v.pts[3 * p + 2]};
+        const double X[3] = {x.pts[3 * p], x.pts[3 * p + 1], x.pts[3 * p + 2]};
         const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
         const double* pb = v.ptblk + (size_t)p * 12;
         const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
@@ -557,7 +596,8 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double* __restrict__ Scf, const double* __restrict__ Sff,
                                    const double* __restrict__ rhs, const double* __restrict__ dcf, int nc, int npad,
-                                   double inv_radius, double min_diag, double max_diag, double* __restrict__ A) {
+                                   double inv_radius, double min_diag, double max_diag, double* __restrict__ A, const LMState* __restrict__ st) {
+    if (st) { if (st->status != LM_RUNNING) return; inv_radius = 1.0 / st->radius; }
     const int n = 6 * nc + 1;
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c >= npad || c > r) return;
@@ -576,11 +616,16 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
 
 // cameras + focal: candidate = x - y*scale ; derived table of the candidate ; norms.  Single CTA.
 // locals[0] = |delta_cf|^2, [1] = |x_cf|^2, [2] = |cand_cf|^2, [3] = max |g_cf| (unscaled); post[7] = max |g_pts| (max-reduced over ranks)
-__global__ void __launch_bounds__(256) ba_cam_update_kernel(const double* __restrict__ x_cf, const double* __restrict__ y_cf,
+__global__ void __launch_bounds__(256) ba_cam_update_kernel(BAView v, const double* x_cf, const double* __restrict__ y_cf,
                                                             const double* __restrict__ scale_cf, const double* __restrict__ gcf, int nc,
-                                                            double* __restrict__ cand_cf, CamDerived* __restrict__ camd_c, double* __restrict__ locals,
+                                                            double* cand_cf, CamDerived* camd_c, double* __restrict__ locals,
                                                             double* __restrict__ post, const unsigned long long* __restrict__ gmax_pt_bits,
                                                             const int* __restrict__ fail) {
+    if (v.st) {                                 // device-resident LM loop: x = buffer cur, candidate = the other one
+        if (v.st->status != LM_RUNNING) return;
+        const int cur = v.st->cur;
+        x_cf = v.cf2[cur]; cand_cf = v.cf2[cur ^ 1]; camd_c = v.camd2[cur ^ 1];
+    }
     const int n = 6 * nc + 1;
     double dn = 0, xn = 0, cn = 0, gm = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -607,23 +652,97 @@ __global__ void __launch_bounds__(256) ba_cam_update_kernel(const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// LM control, one thread, after every iteration's evaluation: Ceres' TrustRegionMinimizer decisions (SURVEY.md appendix
+// A.3; order of the tests: gradient, radius, [iteration], invalid step, parameter tolerance, function tolerance, step
+// quality) on the scalars the kernels left in sums[8] | post[8] | locals[8].  Same arithmetic as a host loop would do;
+// all ranks hold identical inputs (post and sums are rank-reduced), so every rank takes the same decision.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void ba_lm_control_kernel(LMState* __restrict__ st, const double* __restrict__ sums, const double* __restrict__ post,
+                                     const double* __restrict__ locals, sfmb200_ba_options opt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || st->status != LM_RUNNING) return;
+    LMState s = *st;
+    ++s.passes;
+    const double cost_x = 0.5 * sums[0], xn2_pts = sums[1];
+    const double cand_cost_raw = 0.5 * post[0], model_acc = post[1], dn2_pts = post[2], cn2_pts = post[3];
+    const double fail0 = post[4], fail1 = post[5], gmax_pt = post[7];
+    const double dn2_cf = locals[0], xn2_cf = locals[1], cn2_cf = locals[2], gmax_cf = locals[3];
+    auto stop = [&](int status, int type) { s.status = status; s.termination_type = type; *st = s; };
+    if (s.new_point) {
+        s.x_cost = cost_x; s.x_norm = sqrt(xn2_pts + xn2_cf); s.gmax = fmax(gmax_pt, gmax_cf);
+        s.new_point = 0;
+        if (s.iter == 0) {
+            s.initial_cost = s.x_cost;
+            if (!isfinite(s.x_cost)) return stop(LM_EVAL_FAILED, SFMB200_BA_FAILURE);
+            if (s.gmax <= opt.gradient_tolerance) return stop(LM_GRADIENT_TOL, SFMB200_BA_CONVERGENCE);
+            if (s.iter >= opt.max_num_iterations) return stop(LM_MAX_ITER, SFMB200_BA_NO_CONVERGENCE);
+        }
+    }
+    if (s.gmax <= opt.gradient_tolerance) return stop(LM_GRADIENT_TOL, SFMB200_BA_CONVERGENCE);
+    if (s.radius <= opt.min_trust_region_radius) return stop(LM_MIN_RADIUS, SFMB200_BA_CONVERGENCE);
+    ++s.iter;
+    const bool lin_ok = fail0 == 0.0 && fail1 == 0.0 && isfinite(model_acc) && isfinite(dn2_pts) && isfinite(dn2_cf);
+    const double model_cost_change = -model_acc;
+    bool decided = false;
+    if (!lin_ok || !(model_cost_change > 0.0)) {
+        s.num_unsuccessful++;
+        if (++s.invalid_steps >= opt.max_num_consecutive_invalid_steps) return stop(LM_INVALID_STEPS, SFMB200_BA_FAILURE);
+        s.radius /= s.decrease_factor; s.decrease_factor *= 2.0;
+        decided = true;
+    }
+    if (!decided) {
+        s.invalid_steps = 0;
+        const double step_norm = sqrt(dn2_pts + dn2_cf);
+        const double cand_cost = isfinite(cand_cost_raw) ? cand_cost_raw : 1.7976931348623157e308;
+        if (step_norm <= opt.parameter_tolerance * (s.x_norm + opt.parameter_tolerance)) {
+            s.msg_a = step_norm / (s.x_norm + opt.parameter_tolerance); s.msg_b = opt.parameter_tolerance;
+            return stop(LM_PARAMETER_TOL, SFMB200_BA_CONVERGENCE);
+        }
+        const double cost_change = s.x_cost - cand_cost;
+        if (fabs(cost_change) <= opt.function_tolerance * s.x_cost) {
+            s.msg_a = fabs(cost_change) / s.x_cost; s.msg_b = opt.function_tolerance;
+            return stop(LM_FUNCTION_TOL, SFMB200_BA_CONVERGENCE);
+        }
+        const double relative_decrease = cost_change / model_cost_change;
+        s.last_rho = relative_decrease;
+        if (relative_decrease > opt.min_relative_decrease) {
+            s.cur ^= 1;                              // x <- candidate
+            s.x_norm = sqrt(cn2_pts + cn2_cf); s.new_point = 1;
+            const double q = 2.0 * relative_decrease - 1.0;
+            s.radius = fmin(opt.max_trust_region_radius, s.radius / fmax(1.0 / 3.0, 1.0 - q * q * q));
+            s.decrease_factor = 2.0;
+            s.num_successful++;
+            s.x_cost = cand_cost;                   // refreshed from the pass at the new point next iteration
+        } else {
+            s.radius /= s.decrease_factor; s.decrease_factor *= 2.0;
+            s.num_unsuccessful++;
+        }
+    }
+    // FinalizeIterationAndCheckIfMinimizerCanContinue of the next iteration (the time limit is the host's, between chunks)
+    if (s.iter >= opt.max_num_iterations) return stop(LM_MAX_ITER, SFMB200_BA_NO_CONVERGENCE);
+    *st = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Back substitution for the points + step evaluation, fused (point-major, same grouping as K3a):
 //   y_p = M^T (zg - M sum_o Jp^T (Jc y_c + Jf y_f)) ;  candidate X' = X - y_p*scale
 //   model cost change accumulates  m.(r + m/2)  with m = J*step ;  candidate cost from the residual at the candidate.
 // post[0] = sum r'^2, post[1] = sum m.(r+m/2), post[2] = |delta_pts|^2, post[3] = |cand_pts|^2
 // ---------------------------------------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, const double* __restrict__ y_cf, const double* __restrict__ cand_cf,
-                                                                     const CamDerived* __restrict__ camd_c, double* __restrict__ pts_c,
+__global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, const double* __restrict__ y_cf, const double* cand_cf,
+                                                                     const CamDerived* camd_c, double* pts_c,
                                                                      double* __restrict__ post) {
+    const LMX x = lm_x(v);
+    if (!x.run) return;
+    if (v.st) { const int nxt = v.st->cur ^ 1; cand_cf = v.cf2[nxt]; camd_c = v.camd2[nxt]; pts_c = v.pts2[nxt]; }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
     constexpr int GB = PT_THREADS / G;
-    const double f = *v.focal, sf = v.scale_cf[6 * v.nc], yf = y_cf[6 * v.nc], fc = cand_cf[6 * v.nc];
+    const double f = *x.focal, sf = v.scale_cf[6 * v.nc], yf = y_cf[6 * v.nc], fc = cand_cf[6 * v.nc];
     double acc_cc = 0, acc_m = 0, acc_dn = 0, acc_cn = 0;
     for (int p = blockIdx.x * GB + threadIdx.x / G; p < v.np; p += gridDim.x * GB) {
         const int o0 = v.pt_off[p], k = v.pt_off[p + 1] - o0;
-        const double X[3] = {v.pts[3 * p], v.pts[3 * p + 1], v.pts[3 * p + 2]};
+        const double X[3] = {x.pts[3 * p], x.pts[3 * p + 1], x.pts[3 * p + 2]};
         const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
         const double* pb = v.ptblk + (size_t)p * 12;
         const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
@@ -635,7 +754,7 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, c
         for (int j = gl; j < k; j += G) {
             const int o = o0 + j, c = v.obs_cam[o];
             ObsJ J;
-            eval_scaled(v.camd[c], X, f, v.obs_xy[o], v.scale_cf + 6 * c, sp, sf, J);
+            eval_scaled(x.camd[c], X, f, v.obs_xy[o], v.scale_cf + 6 * c, sp, sf, J);
             double m0 = J.Jf[0] * yf, m1 = J.Jf[1] * yf;
 #pragma unroll
             for (int a = 0; a < 6; ++a) { const double yc = y_cf[6 * c + a]; m0 += J.Jc[a] * yc; m1 += J.Jc[6 + a] * yc; }
@@ -670,7 +789,7 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, c
                 for (int a = 0; a < 3; ++a) { m0 += k_Jp[a] * yp[a]; m1 += k_Jp[3 + a] * yp[a]; }
             } else {
                 ObsJ J;
-                eval_scaled(v.camd[c], X, f, xy, v.scale_cf + 6 * c, sp, sf, J);
+                eval_scaled(x.camd[c], X, f, xy, v.scale_cf + 6 * c, sp, sf, J);
                 m0 = J.Jf[0] * yf; m1 = J.Jf[1] * yf; r0 = J.r[0]; r1 = J.r[1];
 #pragma unroll
                 for (int a = 0; a < 6; ++a) { const double yc = y_cf[6 * c + a]; m0 += J.Jc[a] * yc; m1 += J.Jc[6 + a] * yc; }
@@ -783,6 +902,10 @@ __global__ void __launch_bounds__(256) peer_copyback_kernel(PeerTable t, size_t 
 }  // namespace
 
 // =================================================================================================================
+// events of one LM iteration: 0 point start, 1 point end, 2 pair end, 3 camera end, 4 solve start, 5 solve end, 6/7 flush
+constexpr int LM_CHUNK = 4;            // LM iterations enqueued per host read-back
+struct EvSet { cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
+
 struct sfmb200_ba_problem {
     sfmb200_ctx* ctx = nullptr;
     int nc = 0, np = 0, nobs = 0, maxk = 0, G = 8, n = 0, npad = 0;
@@ -808,7 +931,9 @@ struct sfmb200_ba_problem {
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
     bool have_scale = false;
     bool camd_valid[2] = {false, false};   // camd[i] matches cf[i] (written by cam_derive or, for the candidate, by ba_cam_update_kernel)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, evf0 = nullptr, evf1 = nullptr;
+    EvSet evs[LM_CHUNK];              // profile mode: one set of events per iteration of a chunk (created on first use)
+    bool have_events = false;
+    LMState* d_state = nullptr; LMState* h_state = nullptr;    // device-resident LM control state + pinned read-back
     // gather mode (K3c): Z per observation + per-camera-pair entry lists
     bool gather = true;
     double* Zbuf = nullptr; int32_t* pair_off = nullptr; int32_t* pair_blk = nullptr; uint2* pair_ent = nullptr;
@@ -829,8 +954,10 @@ static void ba_release_buffers(sfmb200_ba_problem* P) {
     P->mem = DevBuf(); P->gmem = DevBuf(); P->xbuf = DevBuf(); P->hpin = PinBuf(); P->xmem = nullptr; P->h_scal = nullptr; P->borrowed = false;
 }
 
-static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* opt) {
+static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* opt, bool lm = false) {
     BAView v;
+    v.st = lm ? P->d_state : nullptr;
+    for (int i = 0; i < 2; ++i) { v.cf2[i] = P->cf[i]; v.pts2[i] = P->pts[i]; v.camd2[i] = P->camd[i]; }
     v.nc = P->nc; v.np = P->np; v.nobs = P->nobs; v.maxk = P->maxk;
     v.obs_xy = P->obs_xy; v.obs_cam = P->obs_cam; v.pt_off = P->pt_off; v.cm_off = P->cm_off; v.cm_xy = P->cm_xy; v.cm_pt = P->cm_pt;
     v.cams = P->cf[P->cur]; v.focal = P->cf[P->cur] + 6 * P->nc; v.pts = P->pts[P->cur]; v.camd = P->camd[P->cur];
@@ -943,64 +1070,67 @@ static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt)
     return SFMB200_OK;
 }
 
-// One residual+Jacobian+Schur pass at the current x for a given radius; leaves the (rank-summed) reduced system in red.
-static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius, bool profile) {
+// One residual+Jacobian+Schur pass at the current x; leaves the (rank-summed) reduced system in red.
+// lm = true: inside the device-resident LM loop (x, radius and the early-out come from P->d_state, `radius` is ignored);
+// es: CUDA events of this iteration's slot (profile mode) or nullptr.
+static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius, const EvSet* es, bool lm) {
     sfmb200_ctx* ctx = P->ctx;
-    BAView v = make_view(P, opt);
+    BAView v = make_view(P, opt, lm);
+    const LMState* st = lm ? P->d_state : nullptr;
     SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * (P->red_n + 20), ctx->stream));   // red | post, locals, gmax, fail (contiguous)
-    if (!P->camd_valid[P->cur]) {       // after an accepted step the candidate's table (ba_cam_update_kernel) is already there
+    if (!lm && !P->camd_valid[P->cur]) {
         cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
         P->camd_valid[P->cur] = true;
     }
     if (P->np > 0 && P->nobs > 0) {
-        if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev0, ctx->stream));
+        if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[0], ctx->stream));
         int rc = DISPATCH_G(P, launch_point_pass)(P, v, 1.0 / radius); if (rc) return rc;
-        if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev1, ctx->stream));
+        if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[1], ctx->stream));
         if (P->gather && P->n_pairs_nonempty > 0) {
-            if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev2, ctx->stream));
             ba_pair_kernel<<<dim3(ceil_div(P->n_pairs_nonempty, PAIR_WARPS), P->pair_nseg * P->pair_splits), PAIR_WARPS * 32, 0, ctx->stream>>>(
-                P->Zbuf, P->pair_off, P->pair_ent, P->n_pairs_nonempty, P->pair_nseg, P->pair_splits, P->pair_blk, P->Sblk);
+                P->Zbuf, P->pair_off, P->pair_ent, P->n_pairs_nonempty, P->pair_nseg, P->pair_splits, P->pair_blk, P->Sblk, st);
             SFM_LAUNCH_CHECK(ctx);
-            if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev3, ctx->stream));
         }
-        if (profile && !(P->gather && P->n_pairs_nonempty > 0)) SFM_CUDA(ctx, cudaEventRecord(P->ev3, ctx->stream));
+        if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[2], ctx->stream));
         {
             const int blocks = resident_grid(P, &P->grid_camera, ba_camera_kernel, CAM_THREADS, 0, ceil_div(P->nobs, CAM_THREADS), 4);
             ba_camera_kernel<<<blocks, CAM_THREADS, 0, ctx->stream>>>(v, ceil_div(P->nobs, blocks)); SFM_LAUNCH_CHECK(ctx);
         }
-        if (profile) SFM_CUDA(ctx, cudaEventRecord(P->ev4, ctx->stream));
+        if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[3], ctx->stream));
     }
     return ba_allreduce(P, P->red, P->red_n, 0);
 }
 
-static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius) {
+static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius, bool lm) {
     sfmb200_ctx* ctx = P->ctx;
     const int npad = P->npad, nbk = npad / NB;
+    const LMState* st = lm ? P->d_state : nullptr;
+    const int* skip = lm ? &P->d_state->status : nullptr;
     ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(P->Sblk, P->Scf, P->Sff, P->rhs, P->dcf, P->nc, npad, 1.0 / radius,
-                                                                                 opt->min_lm_diagonal, opt->max_lm_diagonal, P->A);
+                                                                                 opt->min_lm_diagonal, opt->max_lm_diagonal, P->A, st);
     SFM_LAUNCH_CHECK(ctx);
     if (P->chol_fused) {
         const bool la = P->chol_lookahead || P->chol_stream;
         const int ntasks = chol_fused_tasks(nbk, la);
         const int grid = std::min(ntasks, P->chol_grid);
         if (P->chol_stream) chol_stream_kernel<<<std::min(ntasks, P->chol_grid_stream), CS_THREADS, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, P->chol_progress,
-                                                                                                                   ++P->chol_epoch, P->Linv, nullptr);
-        else if (la) chol_fused_kernel<true><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, ++P->chol_epoch, P->Linv, nullptr);
-        else chol_fused_kernel<false><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, ++P->chol_epoch, P->Linv, nullptr);
+                                                                                                                   ++P->chol_epoch, P->Linv, nullptr, skip);
+        else if (la) chol_fused_kernel<true><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, ++P->chol_epoch, P->Linv, nullptr, skip);
+        else chol_fused_kernel<false><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, ++P->chol_epoch, P->Linv, nullptr, skip);
         SFM_LAUNCH_CHECK(ctx);
     } else {
         for (int k = 0; k < nbk; ++k) {
-            chol_panel_kernel<<<std::max(1, ceil_div(nbk - k - 1, PANEL_WARPS)), PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, k, nbk, P->dinv, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
+            chol_panel_kernel<<<std::max(1, ceil_div(nbk - k - 1, PANEL_WARPS)), PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, k, nbk, P->dinv, P->fail + 1, skip); SFM_LAUNCH_CHECK(ctx);
             const int T = nbk - k - 1;
-            if (T > 0) { chol_update_kernel<<<T * (T + 1) / 2, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, k, nbk); SFM_LAUNCH_CHECK(ctx); }
+            if (T > 0) { chol_update_kernel<<<T * (T + 1) / 2, dim3(NB, NB), 0, ctx->stream>>>(P->A, npad, k, nbk, skip); SFM_LAUNCH_CHECK(ctx); }
         }
     }
     {
         const size_t smem = chol_backsolve_smem(npad, P->backsolve_staged);
-        if (P->backsolve_staged && P->chol_fused) chol_backsolve_kernel<true, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf);
-        else if (P->backsolve_staged) chol_backsolve_kernel<true, false><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf);
-        else if (P->chol_fused) chol_backsolve_kernel<false, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf);
-        else chol_backsolve_kernel<false, false><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf);
+        if (P->backsolve_staged && P->chol_fused) chol_backsolve_kernel<true, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
+        else if (P->backsolve_staged) chol_backsolve_kernel<true, false><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
+        else if (P->chol_fused) chol_backsolve_kernel<false, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
+        else chol_backsolve_kernel<false, false><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
         SFM_LAUNCH_CHECK(ctx);
     }
     return SFMB200_OK;
@@ -1055,7 +1185,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     add(sizeof(CamDerived) * (size_t)nc); add(sizeof(CamDerived) * (size_t)nc);
     add(8 * n); add(24 * (size_t)np); add(96 * (size_t)np); add(8 * (P->red_n + 32));
     add(8 * (size_t)P->npad * P->npad); add(8 * n); add(8 * (size_t)P->npad); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
-    add(4 * (size_t)(P->npad / NB) * (P->npad / NB)); add(8 * (size_t)P->npad * NB); add(4 * (size_t)(P->npad / NB));
+    add(4 * (size_t)(P->npad / NB) * (P->npad / NB)); add(8 * (size_t)P->npad * NB); add(4 * (size_t)(P->npad / NB)); add(sizeof(LMState));
     if (!ctx->ba_ws.in_use) {           // borrow the cached workspace (grown below when too small)
         P->mem = ctx->ba_ws.mem; P->gmem = ctx->ba_ws.gmem; P->xbuf = ctx->ba_ws.xbuf; P->hpin = ctx->ba_ws.hpin;
         ctx->ba_ws.mem = DevBuf(); ctx->ba_ws.gmem = DevBuf(); ctx->ba_ws.xbuf = DevBuf(); ctx->ba_ws.hpin = PinBuf();
@@ -1087,6 +1217,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->chol_ready = cv.take<unsigned>((size_t)(P->npad / NB) * (P->npad / NB));
     P->Linv = cv.take<double>((size_t)P->npad * NB);
     P->chol_progress = cv.take<unsigned>((size_t)(P->npad / NB));
+    P->d_state = cv.take<LMState>(1);
 
     cudaStream_t st = ctx->stream;
 #define CRT(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { ba_release_buffers(P); delete P; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); } } while (0)
@@ -1133,9 +1264,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor); ctx->launches += 1;
     }
     CRT(cudaGetLastError());
-    CRT(P->hpin.reserve(sizeof(double) * 32)); P->h_scal = (double*)P->hpin.p;
-    CRT(cudaEventCreate(&P->ev0)); CRT(cudaEventCreate(&P->ev1)); CRT(cudaEventCreate(&P->ev2)); CRT(cudaEventCreate(&P->ev3)); CRT(cudaEventCreate(&P->ev4));
-    CRT(cudaEventCreate(&P->ev5)); CRT(cudaEventCreate(&P->ev6)); CRT(cudaEventCreate(&P->evf0)); CRT(cudaEventCreate(&P->evf1));
+    CRT(P->hpin.reserve(sizeof(double) * 32 + sizeof(LMState))); P->h_scal = (double*)P->hpin.p; P->h_state = (LMState*)(P->h_scal + 32);
     {   // off-diagonal Schur blocks: "gather" (default; per-camera-pair lists, no atomics in the hot loop) or "red"
         const char* mode = getenv("SFMB200_BA_SCHUR");
         P->gather = !(mode && strcmp(mode, "red") == 0);
@@ -1184,15 +1313,7 @@ void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     std::lock_guard<std::mutex> lk(P->ctx->mu);
     cudaSetDevice(P->ctx->device);
     cudaStreamSynchronize(P->ctx->stream);
-    if (P->ev0) cudaEventDestroy(P->ev0);
-    if (P->ev1) cudaEventDestroy(P->ev1);
-    if (P->ev2) cudaEventDestroy(P->ev2);
-    if (P->ev3) cudaEventDestroy(P->ev3);
-    if (P->ev4) cudaEventDestroy(P->ev4);
-    if (P->ev5) cudaEventDestroy(P->ev5);
-    if (P->ev6) cudaEventDestroy(P->ev6);
-    if (P->evf0) cudaEventDestroy(P->evf0);
-    if (P->evf1) cudaEventDestroy(P->evf1);
+    for (int k = 0; k < LM_CHUNK; ++k) for (int e = 0; e < 8; ++e) if (P->evs[k].ev[e]) cudaEventDestroy(P->evs[k].ev[e]);
     for (int r = 0; r < MAX_PEERS; ++r) if (P->peer_base[r]) cudaIpcCloseMemHandle(P->peer_base[r]);
     ba_release_buffers(P);
     delete P;
@@ -1265,10 +1386,10 @@ int sfmb200_ba_problem_reduced_system(sfmb200_ba_problem* P, const sfmb200_ba_op
     SFM_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
     if (!P->have_scale) { rc = compute_scaling(P, &opt); if (rc) return rc; }
-    rc = schur_pass(P, &opt, radius, false); if (rc) return rc;
+    rc = schur_pass(P, &opt, radius, nullptr, false); if (rc) return rc;
     const int n = P->n, npad = P->npad;
     ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(P->Sblk, P->Scf, P->Sff, P->rhs, P->dcf, P->nc, npad, 1.0 / radius,
-                                                                                 opt.min_lm_diagonal, opt.max_lm_diagonal, P->A);
+                                                                                 opt.min_lm_diagonal, opt.max_lm_diagonal, P->A, nullptr);
     SFM_LAUNCH_CHECK(ctx);
     std::vector<double> hA((size_t)npad * npad), hg(n), hs(n), hsum(8);
     SFM_CUDA(ctx, cudaMemcpyAsync(hA.data(), P->A, 8 * hA.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1283,6 +1404,11 @@ int sfmb200_ba_problem_reduced_system(sfmb200_ba_problem* P, const sfmb200_ba_op
     return SFMB200_OK;
 }
 
+// The LM loop.  Control state lives on the device (LMState, ba_lm_control_kernel); the host enqueues LM_CHUNK complete
+// iterations at a time -- pass, rank sum, dense solve, candidate, evaluation, rank sum, control -- and reads the state back
+// once per chunk: no stream synchronisation, read-back or host decision inside a chunk, and the next chunk's launches are
+// issued while the GPU is still working when the solve continues.  An iteration enqueued after the solve has terminated is a
+// no-op (every kernel checks LMState::status first).  Only the wall-clock limit is tested on the host, between chunks.
 int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_in, sfmb200_ba_summary* sum) {
     if (!P || !sum) return SFMB200_ERR_INVALID;
     sfmb200_ctx* ctx = P->ctx;
@@ -1294,119 +1420,90 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
     auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     const int64_t launches0 = ctx->launches;
     int rc = compute_scaling(P, &opt); if (rc) return rc;
-
-    double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
-    int iter = 0, invalid_steps = 0;
-    bool new_point = true;          // gradient / cost of the current x not yet examined
-    double x_cost = 0, x_norm = 0, gmax = 0;
-    sum->termination_type = SFMB200_BA_NO_CONVERGENCE;
-    double* h = P->h_scal;
+    if (opt.profile && !P->have_events) {
+        for (int k = 0; k < LM_CHUNK; ++k) for (int e = 0; e < 8; ++e) SFM_CUDA(ctx, cudaEventCreate(&P->evs[k].ev[e]));
+        P->have_events = true;
+    }
+    if (!P->camd_valid[P->cur]) {       // inside the loop the table of an accepted candidate comes from ba_cam_update_kernel
+        cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(P->cf[P->cur], P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
+        P->camd_valid[P->cur] = true;
+    }
+    LMState* hs = P->h_state;
+    memset(hs, 0, sizeof *hs);
+    hs->radius = opt.initial_trust_region_radius; hs->decrease_factor = 2.0; hs->cur = P->cur; hs->new_point = 1;
+    hs->status = LM_RUNNING; hs->termination_type = SFMB200_BA_NO_CONVERGENCE;
+    SFM_CUDA(ctx, cudaMemcpyAsync(P->d_state, hs, sizeof *hs, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                 // hs is reused for the read-back
+    int chunk = opt.verbose ? 1 : LM_CHUNK;
+    if (const char* ce = getenv("SFMB200_BA_CHUNK")) chunk = std::max(1, std::min(LM_CHUNK, atoi(ce)));
+    bool timed_out = false;
+    int executed = 0;
 
     for (;;) {
-        // FinalizeIterationAndCheckIfMinimizerCanContinue of the previous iteration, Ceres' order: time, iterations,
-        // gradient, radius.  The first two need no device data, so they are tested before any kernel is launched:
-        // max_num_iterations = K performs exactly K passes / solves / candidate evaluations.
-        if (iter > 0) {
-            if (opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { snprintf(sum->message, sizeof sum->message, "Maximum solver time reached."); break; }
-            if (iter >= opt.max_num_iterations) { snprintf(sum->message, sizeof sum->message, "Maximum number of iterations reached."); break; }
+        if (executed > 0 && opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { timed_out = true; break; }
+        const int n_it = std::max(1, std::min(chunk, opt.max_num_iterations - hs->iter));
+        for (int k = 0; k < n_it; ++k) {
+            const EvSet* es = opt.profile ? &P->evs[k] : nullptr;
+            if (opt.l2_flush_mb > 0) {      // benchmark hygiene: evict the working set from L2 between iterations
+                SFM_CUDA(ctx, ctx->scratch2.reserve((size_t)opt.l2_flush_mb << 20));
+                if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[6], ctx->stream));
+                SFM_CUDA(ctx, cudaMemsetAsync(ctx->scratch2.p, 0, (size_t)opt.l2_flush_mb << 20, ctx->stream));
+                if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[7], ctx->stream));
+            }
+            // ---- one LM iteration on the device: pass at x, dense solve, candidate, evaluation, decision ----------
+            rc = schur_pass(P, &opt, 0.0, es, true); if (rc) return rc;
+            if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[4], ctx->stream));
+            rc = dense_solve(P, &opt, 0.0, true); if (rc) return rc;
+            if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[5], ctx->stream));
+            BAView v = make_view(P, &opt, true);
+            ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(v, nullptr, P->y_cf, P->scale_cf, P->gcf, P->nc, nullptr, nullptr, P->locals,
+                                                             P->post, P->gmax_pt_bits, P->fail);
+            SFM_LAUNCH_CHECK(ctx);
+            if (P->np > 0 && P->nobs > 0) { rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }
+            rc = ba_allreduce(P, P->post, 7, 1); if (rc) return rc;   // sums: candidate cost, model, norms, failure counts; max: |g| of the points
+            ba_lm_control_kernel<<<1, 32, 0, ctx->stream>>>(P->d_state, P->sums, P->post, P->locals, opt); SFM_LAUNCH_CHECK(ctx);
         }
-        if (opt.l2_flush_mb > 0) {      // benchmark hygiene: evict the working set from L2 between iterations
-            SFM_CUDA(ctx, ctx->scratch2.reserve((size_t)opt.l2_flush_mb << 20));
-            if (opt.profile) SFM_CUDA(ctx, cudaEventRecord(P->evf0, ctx->stream));
-            SFM_CUDA(ctx, cudaMemsetAsync(ctx->scratch2.p, 0, (size_t)opt.l2_flush_mb << 20, ctx->stream));
-            if (opt.profile) SFM_CUDA(ctx, cudaEventRecord(P->evf1, ctx->stream));
-        }
-        // ---- one LM iteration on the device: pass at x, dense solve, candidate, evaluation -------------------
-        rc = schur_pass(P, &opt, radius, opt.profile != 0); if (rc) return rc;
-        sum->num_jacobian_passes++;
-        if (opt.profile) SFM_CUDA(ctx, cudaEventRecord(P->ev5, ctx->stream));
-        rc = dense_solve(P, &opt, radius); if (rc) return rc;
-        if (opt.profile) SFM_CUDA(ctx, cudaEventRecord(P->ev6, ctx->stream));
-        sum->num_linear_solves++;
-        const int nxt = P->cur ^ 1;
-        ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(P->cf[P->cur], P->y_cf, P->scale_cf, P->gcf, P->nc, P->cf[nxt], P->camd[nxt], P->locals,
-                                                         P->post, P->gmax_pt_bits, P->fail);
-        SFM_LAUNCH_CHECK(ctx);
-        P->camd_valid[nxt] = true;
-        if (P->np > 0 && P->nobs > 0) { BAView v = make_view(P, &opt); rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }
-        rc = ba_allreduce(P, P->post, 7, 1); if (rc) return rc;   // sums: candidate cost, model, norms, failure counts; max: |g| of the points
-        // read back: sums[8] | post[8] locals[8]
-        SFM_CUDA(ctx, cudaMemcpyAsync(h, P->sums, 8 * 24, cudaMemcpyDeviceToHost, ctx->stream));      // sums[8] | post[8] | locals[8] are contiguous
+        SFM_CUDA(ctx, cudaMemcpyAsync(hs, P->d_state, sizeof *hs, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        // iterations of this chunk that actually ran: all of them unless the solve terminated inside the chunk
+        const int ran = hs->status == LM_RUNNING ? n_it : std::max(1, std::min(n_it, hs->passes - executed));
+        executed += ran;
         if (opt.profile) {
-            float ms = 0;
-            if (opt.l2_flush_mb > 0 && cudaEventElapsedTime(&ms, P->evf0, P->evf1) == cudaSuccess) sum->flush_ms_total += ms;
-            if (cudaEventElapsedTime(&ms, P->ev5, P->ev6) == cudaSuccess) sum->solve_ms_total += ms;
-        }
-        if (opt.profile && P->np > 0 && P->nobs > 0) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, P->ev0, P->ev1) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; }
-            if (P->gather && P->n_pairs_nonempty > 0 && cudaEventElapsedTime(&ms, P->ev2, P->ev3) == cudaSuccess) { sum->pair_ms_total += ms; sum->pair_launches++; }
-            if (cudaEventElapsedTime(&ms, P->ev3, P->ev4) == cudaSuccess) sum->camera_ms_total += ms;
-        }
-        const double cost_x = 0.5 * h[0], xn2_pts = h[1];
-        const double cand_cost_raw = 0.5 * h[8], model_acc = h[9], dn2_pts = h[10], cn2_pts = h[11];
-        const double fails[2] = {h[12], h[13]};                        // summed over ranks
-        const double dn2_cf = h[16], xn2_cf = h[17], cn2_cf = h[18], gmax_cf = h[19], gmax_pt = h[15];     // gmax_pt: max over ranks
-        if (new_point) {
-            x_cost = cost_x; x_norm = std::sqrt(xn2_pts + xn2_cf); gmax = std::max(gmax_pt, gmax_cf);
-            new_point = false;
-            if (iter == 0) {
-                sum->initial_cost = x_cost;
-                if (!std::isfinite(x_cost)) { sum->termination_type = SFMB200_BA_FAILURE; snprintf(sum->message, sizeof sum->message, "Residual and Jacobian evaluation failed."); break; }
-                if (opt.verbose) printf("iter %3d cost %.9e |g|max %.3e radius %.3e\n", 0, x_cost, gmax, radius);
-                if (gmax <= opt.gradient_tolerance) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break; }
-                if (opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { snprintf(sum->message, sizeof sum->message, "Maximum solver time reached."); break; }
-                if (iter >= opt.max_num_iterations) { snprintf(sum->message, sizeof sum->message, "Maximum number of iterations reached."); break; }
+            for (int k = 0; k < ran; ++k) {
+                const EvSet& es = P->evs[k];
+                float ms = 0;
+                if (opt.l2_flush_mb > 0 && cudaEventElapsedTime(&ms, es.ev[6], es.ev[7]) == cudaSuccess) sum->flush_ms_total += ms;
+                if (cudaEventElapsedTime(&ms, es.ev[4], es.ev[5]) == cudaSuccess) sum->solve_ms_total += ms;
+                if (P->np > 0 && P->nobs > 0) {
+                    if (cudaEventElapsedTime(&ms, es.ev[0], es.ev[1]) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; }
+                    if (P->gather && P->n_pairs_nonempty > 0 && cudaEventElapsedTime(&ms, es.ev[1], es.ev[2]) == cudaSuccess) { sum->pair_ms_total += ms; sum->pair_launches++; }
+                    if (cudaEventElapsedTime(&ms, es.ev[2], es.ev[3]) == cudaSuccess) sum->camera_ms_total += ms;
+                }
             }
         }
-        if (gmax <= opt.gradient_tolerance) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break; }
-        if (radius <= opt.min_trust_region_radius) { sum->termination_type = SFMB200_BA_CONVERGENCE; snprintf(sum->message, sizeof sum->message, "Minimum trust region radius reached."); break; }
-        ++iter;
-
-        const bool lin_ok = fails[0] == 0.0 && fails[1] == 0.0 && std::isfinite(model_acc) && std::isfinite(dn2_pts) && std::isfinite(dn2_cf);
-        const double model_cost_change = -model_acc;
-        if (!lin_ok || !(model_cost_change > 0.0)) {
-            sum->num_unsuccessful_steps++;
-            if (++invalid_steps >= opt.max_num_consecutive_invalid_steps) {
-                sum->termination_type = SFMB200_BA_FAILURE;
-                snprintf(sum->message, sizeof sum->message, "Number of consecutive invalid steps more than max_num_consecutive_invalid_steps: %d", opt.max_num_consecutive_invalid_steps);
-                break;
-            }
-            radius /= decrease_factor; decrease_factor *= 2.0;
-            if (opt.verbose) printf("iter %3d INVALID step radius %.3e\n", iter, radius);
-            continue;
-        }
-        invalid_steps = 0;
-        const double step_norm = std::sqrt(dn2_pts + dn2_cf);
-        const double cand_cost = std::isfinite(cand_cost_raw) ? cand_cost_raw : DBL_MAX;
-        if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
-            sum->termination_type = SFMB200_BA_CONVERGENCE;
-            snprintf(sum->message, sizeof sum->message, "Parameter tolerance reached. Relative step_norm: %e <= %e.", step_norm / (x_norm + opt.parameter_tolerance), opt.parameter_tolerance);
-            break;
-        }
-        const double cost_change = x_cost - cand_cost;
-        if (std::fabs(cost_change) <= opt.function_tolerance * x_cost) {
-            sum->termination_type = SFMB200_BA_CONVERGENCE;
-            snprintf(sum->message, sizeof sum->message, "Function tolerance reached. |cost_change|/cost: %e <= %e", std::fabs(cost_change) / x_cost, opt.function_tolerance);
-            break;
-        }
-        const double relative_decrease = cost_change / model_cost_change;
-        if (relative_decrease > opt.min_relative_decrease) {
-            P->cur = nxt;                       // x <- candidate
-            x_norm = std::sqrt(cn2_pts + cn2_cf); new_point = true;
-            const double q = 2.0 * relative_decrease - 1.0;
-            radius = std::min(opt.max_trust_region_radius, radius / std::max(1.0 / 3.0, 1.0 - q * q * q));
-            decrease_factor = 2.0;
-            sum->num_successful_steps++;
-            x_cost = cand_cost;                 // refreshed from the pass at the new point next iteration
-        } else {
-            radius /= decrease_factor; decrease_factor *= 2.0;
-            sum->num_unsuccessful_steps++;
-        }
-        if (opt.verbose) printf("iter %3d cost %.9e |g|max %.3e radius %.3e rho %.3e %s\n", iter, x_cost, gmax, radius, relative_decrease, new_point ? "ok" : "rejected");
+        if (opt.verbose) printf("iter %3d cost %.9e |g|max %.3e radius %.3e rho %.3e %s\n", hs->iter, hs->x_cost, hs->gmax, hs->radius, hs->last_rho,
+                                hs->status != LM_RUNNING ? "stop" : (hs->new_point ? "ok" : "rejected"));
+        if (hs->status != LM_RUNNING) break;
     }
-    sum->num_iterations = iter; sum->final_cost = x_cost; sum->total_time_s = elapsed();
+    P->cur = hs->cur;
+    P->camd_valid[P->cur] = true; P->camd_valid[P->cur ^ 1] = false;
+    sum->termination_type = hs->termination_type;
+    sum->num_iterations = hs->iter; sum->num_successful_steps = hs->num_successful; sum->num_unsuccessful_steps = hs->num_unsuccessful;
+    sum->num_jacobian_passes = executed; sum->num_linear_solves = executed;
+    sum->initial_cost = hs->initial_cost; sum->final_cost = hs->x_cost;
+    const int why = timed_out ? LM_MAX_TIME : hs->status;
+    switch (why) {
+        case LM_EVAL_FAILED: snprintf(sum->message, sizeof sum->message, "Residual and Jacobian evaluation failed."); break;
+        case LM_GRADIENT_TOL: snprintf(sum->message, sizeof sum->message, "Gradient tolerance reached."); break;
+        case LM_MAX_TIME: snprintf(sum->message, sizeof sum->message, "Maximum solver time reached."); break;
+        case LM_MAX_ITER: snprintf(sum->message, sizeof sum->message, "Maximum number of iterations reached."); break;
+        case LM_MIN_RADIUS: snprintf(sum->message, sizeof sum->message, "Minimum trust region radius reached."); break;
+        case LM_INVALID_STEPS: snprintf(sum->message, sizeof sum->message, "Number of consecutive invalid steps more than max_num_consecutive_invalid_steps: %d", opt.max_num_consecutive_invalid_steps); break;
+        case LM_PARAMETER_TOL: snprintf(sum->message, sizeof sum->message, "Parameter tolerance reached. Relative step_norm: %e <= %e.", hs->msg_a, hs->msg_b); break;
+        case LM_FUNCTION_TOL: snprintf(sum->message, sizeof sum->message, "Function tolerance reached. |cost_change|/cost: %e <= %e", hs->msg_a, hs->msg_b); break;
+        default: break;
+    }
+    sum->total_time_s = elapsed();
     sum->kernel_launches = ctx->launches - launches0;
     return SFMB200_OK;
 }

@@ -165,8 +165,11 @@ __device__ __forceinline__ void chol_tile_trsm(double (&b)[NB], const double (*L
     for (int jb = 0; jb < NB; jb += PANEL_WARPS) chol_tile_trsm_group(b, Ls, invd, jb);
 }
 
+// `skip` (all kernels of this file, optional): when it points at a non-zero word the launch is a no-op -- the device-resident
+// LM loop enqueues whole chunks of iterations and the solve may terminate inside one.
 __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __restrict__ A, int npad, int n, int k, int nbk,
-                                                                      double* __restrict__ dinv, int* __restrict__ fail) {
+                                                                      double* __restrict__ dinv, int* __restrict__ fail, const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     __shared__ double Ls[NB][NB + 1];          // diagonal tile, then its factor (lower)
     __shared__ double colbuf[2][NB];
     __shared__ double invd[NB];
@@ -206,7 +209,8 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_panel_kernel(double* __
 }
 
 // Trailing update step k: tile (i, j), k < j <= i:  A[i][j] -= A[i][k] A[j][k]^T.  blockDim = (32, 32), grid = T(T+1)/2.
-__global__ void __launch_bounds__(1024) chol_update_kernel(double* __restrict__ A, int npad, int k, int nbk) {
+__global__ void __launch_bounds__(1024) chol_update_kernel(double* __restrict__ A, int npad, int k, int nbk, const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     __shared__ double P[NB][NB + 1], Q[NB][NB + 1];
     // decode blockIdx.x -> (i, j) over the lower triangle of the trailing (T x T) tile matrix
     int t = blockIdx.x, ii = 0;
@@ -317,7 +321,9 @@ template <bool LOOKAHEAD>
 __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_fused_kernel(double* __restrict__ A, int npad, int n, int nbk, int ntasks,
                                                                       double* __restrict__ dinv, int* __restrict__ fail,
                                                                       unsigned* __restrict__ ready, unsigned epoch,
-                                                                      double* __restrict__ Linv, unsigned long long* __restrict__ trace) {
+                                                                      double* __restrict__ Linv, unsigned long long* __restrict__ trace,
+                                                                      const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     __shared__ double Ps[NB][NB + 1], Qs[NB][NB + 1];
     __shared__ double colbuf[2][NB];
     __shared__ double invd[NB];
@@ -477,7 +483,9 @@ __device__ __forceinline__ bool progress_wait(const unsigned* p, unsigned want) 
 __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restrict__ A, int npad, int n, int nbk, int ntasks,
                                                                  double* __restrict__ dinv, int* __restrict__ fail,
                                                                  unsigned* __restrict__ ready, unsigned* __restrict__ progress, unsigned epoch,
-                                                                 double* __restrict__ Linv, unsigned long long* __restrict__ trace) {
+                                                                 double* __restrict__ Linv, unsigned long long* __restrict__ trace,
+                                                                 const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     __shared__ __align__(16) double Pt[NB][TS], Qt[NB][TS], Xs[NB][TS];
     __shared__ double Ls[NB][NB + 1];
     __shared__ __align__(16) double colbuf[2][2][NB];
@@ -662,7 +670,8 @@ __host__ __device__ inline size_t chol_backsolve_smem(int npad, bool staged) {
 
 template <bool STAGED, bool USE_INV>
 __global__ void __launch_bounds__(640) chol_backsolve_kernel(const double* __restrict__ A, const double* __restrict__ dinv, const double* __restrict__ Linv,
-                                                             int npad, int n, double* __restrict__ x) {
+                                                             int npad, int n, double* __restrict__ x, const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;
     extern __shared__ double sm[];
     double* y = sm;                               // [npad]
     double* dstage = sm + npad;                   // [NB][NB]    warp 0's next tile
