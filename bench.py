@@ -275,6 +275,9 @@ def run_ours(args):
     dev_ms, wall_ms, dev_ms_raw = t.tolist(); nobs_total, launches_total, np_total = tot.tolist()
     value = nobs_total * iters / (dev_ms * 1e-3)
 
+    # the resident problem gives its workspace back to the context's cache: the one-shot solves below borrow it instead of
+    # paying cudaMalloc / cudaFree of ~600 MB per call (which cost 1 ms on a quiet host and 100+ ms on a busy one)
+    prob.close()
     # ---- e2e: the same K iterations through the one-shot C-ABI call with pinned HOST buffers ------------------------
     def pinned(x):
         return torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
@@ -367,7 +370,7 @@ def run_ours(args):
                                 "sample": f"{args.workload} full problem, {it} LM iterations of the oracle (Ceres-equivalent LM+DENSE_SCHUR, dual-number Jacobians, 1 thread as the reference leaves Ceres), {dt:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    prob.close(); ctx.close()
+    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,6 +30,7 @@
 namespace {
 
 constexpr int PT_THREADS = 128;
+constexpr int PTB = 18;                // doubles per point in ptblk
 constexpr int CAM_THREADS = 128;
 
 // Levenberg-Marquardt control state, resident on the device: the kernels of an iteration read `cur` (which of the two
@@ -61,7 +62,7 @@ struct BAView {
     const double* cams; const double* pts; const double* focal;      // current x (focal = cams + 6*nc)
     const CamDerived* camd;                                           // derived per camera at x
     const double* scale_cf; const double* scale_pt;                   // Jacobi scaling
-    double* ptblk;                                                    // [np*12] M(6) zg(3) zf(3)
+    double* ptblk;                                                    // [np*PTB] M(6) zg(3) zf(3) g(3) diag(U)(3)
     double* Zbuf;                                                     // [nobs*18] Z_o = Jc^T Jp M^T (gather mode), point-major
     // reduced system (block layout) + sums
     double* Sblk; double* Scf; double* Sff; double* rhs; double* gcf; double* dcf; double* sums;
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, doubl
     if (!x.run) return;
     if (v.st) inv_radius = 1.0 / v.st->radius;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(16) double zstage[GATHER ? PT_THREADS / 32 : 1][GATHER ? 32 * 18 : 2];      // one warp-iteration of Z records
     constexpr int GB = PT_THREADS / G, GW = 32 / G;
     const int maxk = v.maxk;
     double* Zall = reinterpret_cast<double*>(smem_raw);                           // [GB][maxk][18]   (RED mode only)
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, doubl
         for (int a = 0; a < 3; ++a) { g[a] = group_sum<G>(g[a], gmask); wf[a] = group_sum<G>(wf[a], gmask); }
         cost = group_sum<G>(cost, gmask);
 
+        const double udiag[3] = {U[0], U[3], U[5]};                  // diag(J_p^T J_p), kept for the model cost (back-substitution kernel)
         // LM diagonal of the point block: clamp(diag(J^T J)) / radius
         U[0] += clampd(U[0], v.min_diag, v.max_diag) * inv_radius;
         U[3] += clampd(U[3], v.min_diag, v.max_diag) * inv_radius;
@@ -278,9 +281,9 @@ __global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, doubl
         const double zg[3] = {M[0] * g[0], M[1] * g[0] + M[2] * g[1], M[3] * g[0] + M[4] * g[1] + M[5] * g[2]};
         const double zf[3] = {M[0] * wf[0], M[1] * wf[0] + M[2] * wf[1], M[3] * wf[0] + M[4] * wf[1] + M[5] * wf[2]};
         if (active) {
-            const double blk[12] = {M[0], M[1], M[2], M[3], M[4], M[5], zg[0], zg[1], zg[2], zf[0], zf[1], zf[2]};
+            const double blk[PTB] = {M[0], M[1], M[2], M[3], M[4], M[5], zg[0], zg[1], zg[2], zf[0], zf[1], zf[2], g[0], g[1], g[2], udiag[0], udiag[1], udiag[2]};
 #pragma unroll
-            for (int q = 0; q < 12; ++q) if ((q % G) == gl) v.ptblk[(size_t)p * 12 + q] = blk[q];
+            for (int q = 0; q < PTB; ++q) if ((q % G) == gl) v.ptblk[(size_t)p * PTB + q] = blk[q];
             if (gl == 0) {
                 if (!ok && k > 0) atomicAdd(v.fail, 1);
                 acc_cost += cost;
@@ -290,9 +293,19 @@ __global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, doubl
                 acc_gmax = fmax(acc_gmax, fmax(fabs(g[0] / sp[0]), fmax(fabs(g[1] / sp[1]), fabs(g[2] / sp[2]))));
             }
         }
-        // Z = W M^T  (own rows; same thread wrote W)
+        // Z = W M^T  (own rows; same thread wrote W).  A lane-per-record store touches 36 cache lines per instruction (records
+        // are 144 bytes apart): with at most G observations per point the warp's records are one contiguous range of Zbuf, so
+        // they are assembled in shared memory (16-byte stores at a 36-word lane stride are conflict free) and written out with
+        // fully coalesced 16-byte stores.
+        const bool stage = GATHER && v.maxk <= G;
+        int o_first = 0, o_end = 0;
+        if (stage) {
+            const int p_first = base + warp * GW;
+            o_first = p_first < v.np ? v.pt_off[p_first] : 0; o_end = p_first < v.np ? v.pt_off[min(p_first + GW, v.np)] : 0;
+        }
         if (GATHER && gl < k) {
-            double2* dst = reinterpret_cast<double2*>(v.Zbuf + (size_t)(o0 + gl) * 18);
+            double2* dst = stage ? reinterpret_cast<double2*>(zstage[warp] + (size_t)(o0 + gl - o_first) * 18)
+                                 : reinterpret_cast<double2*>(v.Zbuf + (size_t)(o0 + gl) * 18);
 #pragma unroll
             for (int a = 0; a < 6; a += 2) {      // two rows = six doubles = three 16-byte stores
                 double z[6];
@@ -303,6 +316,13 @@ __global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, doubl
                 }
                 dst[a / 2 * 3] = make_double2(z[0], z[1]); dst[a / 2 * 3 + 1] = make_double2(z[2], z[3]); dst[a / 2 * 3 + 2] = make_double2(z[4], z[5]);
             }
+        }
+        if (stage) {
+            __syncwarp();
+            const double2* src = reinterpret_cast<const double2*>(zstage[warp]);
+            double2* out = reinterpret_cast<double2*>(v.Zbuf + (size_t)o_first * 18);
+            for (int i = lane; i < (o_end - o_first) * 9; i += 32) out[i] = src[i];
+            __syncwarp();
         }
         for (int j = gl + (GATHER ? G : 0); j < k; j += G) {
             double* W = GATHER ? v.Zbuf + (size_t)(o0 + j) * 18 : Zg + j * 18;
@@ -533,7 +553,7 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
         const int p = v.cm_pt[i];
         const double X[3] = {x.pts[3 * p], x.pts[3 * p + 1], x.pts[3 * p + 2]};
         const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
-        const double* pb = v.ptblk + (size_t)p * 12;
+        const double* pb = v.ptblk + (size_t)p * PTB;
         const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
         const double zg[3] = {pb[6], pb[7], pb[8]}, zf[3] = {pb[9], pb[10], pb[11]};
         ObsJ J;
@@ -615,8 +635,8 @@ __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double
 }
 
 // cameras + focal: candidate = x - y*scale ; derived table of the candidate ; norms.  Single CTA.
-// locals[0] = |delta_cf|^2, [1] = |x_cf|^2, [2] = |cand_cf|^2, [3] = max |g_cf| (unscaled); post[7] = max |g_pts| (max-reduced over ranks)
-__global__ void __launch_bounds__(256) ba_cam_update_kernel(BAView v, const double* x_cf, const double* __restrict__ y_cf,
+// locals[0] = |delta_cf|^2, [1] = |x_cf|^2, [2] = |cand_cf|^2, [3] = max |g_cf| (unscaled), [4] = camera part of -model cost change; post[7] = max |g_pts| (max-reduced over ranks)
+__global__ void __launch_bounds__(256) ba_cam_update_kernel(BAView v, double inv_radius, int model_from_step, const double* x_cf, const double* __restrict__ y_cf,
                                                             const double* __restrict__ scale_cf, const double* __restrict__ gcf, int nc,
                                                             double* cand_cf, CamDerived* camd_c, double* __restrict__ locals,
                                                             double* __restrict__ post, const unsigned long long* __restrict__ gmax_pt_bits,
@@ -625,24 +645,27 @@ __global__ void __launch_bounds__(256) ba_cam_update_kernel(BAView v, const doub
         if (v.st->status != LM_RUNNING) return;
         const int cur = v.st->cur;
         x_cf = v.cf2[cur]; cand_cf = v.cf2[cur ^ 1]; camd_c = v.camd2[cur ^ 1];
+        inv_radius = 1.0 / v.st->radius;
     }
     const int n = 6 * nc + 1;
-    double dn = 0, xn = 0, cn = 0, gm = 0;
+    double dn = 0, xn = 0, cn = 0, gm = 0, mc = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double d = -y_cf[i] * scale_cf[i], xv = x_cf[i], cv = xv + d;
+        const double yi = y_cf[i], d = -yi * scale_cf[i], xv = x_cf[i], cv = xv + d;
         cand_cf[i] = cv;
         const double dd = xv - cv;
         dn += dd * dd; xn += xv * xv; cn += cv * cv;
         gm = fmax(gm, fabs(gcf[i] / scale_cf[i]));
+        // camera/focal part of the model cost change  1/2 y.(g + D^2 y)  (see ba_backsub_z_kernel), negated like post[1]
+        mc -= 0.5 * yi * (gcf[i] + clampd(v.dcf[i], v.min_diag, v.max_diag) * inv_radius * yi);
     }
-    __shared__ double red[8][4];
-    const double a = warp_sum(dn), b = warp_sum(xn), c = warp_sum(cn), g = warp_max(gm);
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = a; red[threadIdx.x >> 5][1] = b; red[threadIdx.x >> 5][2] = c; red[threadIdx.x >> 5][3] = g; }
+    __shared__ double red[8][5];
+    const double a = warp_sum(dn), b = warp_sum(xn), c = warp_sum(cn), g = warp_max(gm), m = warp_sum(mc);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = a; red[threadIdx.x >> 5][1] = b; red[threadIdx.x >> 5][2] = c; red[threadIdx.x >> 5][3] = g; red[threadIdx.x >> 5][4] = m; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        for (int w = 0; w < 8; ++w) { s0 += red[w][0]; s1 += red[w][1]; s2 += red[w][2]; s3 = fmax(s3, red[w][3]); }
-        locals[0] = s0; locals[1] = s1; locals[2] = s2; locals[3] = s3;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+        for (int w = 0; w < 8; ++w) { s0 += red[w][0]; s1 += red[w][1]; s2 += red[w][2]; s3 = fmax(s3, red[w][3]); s4 += red[w][4]; }
+        locals[0] = s0; locals[1] = s1; locals[2] = s2; locals[3] = s3; locals[4] = model_from_step ? s4 : 0.0;
         // rank-local flags -> buffers that are reduced over ranks (sum / max) so that every rank takes the same decision
         post[7] = __longlong_as_double((long long)*gmax_pt_bits);      // max-reduced over ranks
         post[4] = (double)fail[0]; post[5] = (double)fail[1];
@@ -663,7 +686,7 @@ __global__ void ba_lm_control_kernel(LMState* __restrict__ st, const double* __r
     LMState s = *st;
     ++s.passes;
     const double cost_x = 0.5 * sums[0], xn2_pts = sums[1];
-    const double cand_cost_raw = 0.5 * post[0], model_acc = post[1], dn2_pts = post[2], cn2_pts = post[3];
+    const double cand_cost_raw = 0.5 * post[0], model_acc = post[1] + locals[4], dn2_pts = post[2], cn2_pts = post[3];
     const double fail0 = post[4], fail1 = post[5], gmax_pt = post[7];
     const double dn2_cf = locals[0], xn2_cf = locals[1], cn2_cf = locals[2], gmax_cf = locals[3];
     auto stop = [&](int status, int type) { s.status = status; s.termination_type = type; *st = s; };
@@ -723,6 +746,115 @@ __global__ void ba_lm_control_kernel(LMState* __restrict__ st, const double* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Back substitution for the points + step evaluation from STORED blocks (gather mode, default): no Jacobian is evaluated.
+// With Z_o = Jc^T Jp M^T (Zbuf, written by K3a) and M, zg = M g, zf = M wf, g, diag(U) per point (ptblk):
+//     y_p = M^T (zg - sum_o Z_o^T y_c(o) - zf y_f)                  [ M sum_o Jp^T (Jc y_c + Jf y_f) = sum_o Z_o^T y_c + zf y_f ]
+// and, because y solves (J^T J + D^2) y = g exactly (direct solve), Ceres' model cost change  -m.(r + m/2), m = -J y,  equals
+//     1/2 y.(g + D^2 y)        summed over all parameters, D^2 = clamp(diag(J^T J)) / radius
+// -- the point part is accumulated here, the camera/focal part by ba_cam_update_kernel (locals[4]).  What remains per
+// observation is one 144-byte record, 18 FMAs and the residual at the candidate: 93 -> ~50 us at cfg 3 (HBM: Zbuf 230 MB).
+// post[0] = sum r'^2, post[1] = -(point part of the model cost change), post[2] = |delta_pts|^2, post[3] = |cand_pts|^2
+// ---------------------------------------------------------------------------------------------------------------
+// Per-camera operands (candidate rotation + translation, y_c: 18 doubles) are staged in shared memory once per CTA when they
+// fit (CAMTAB): gathered per observation from global memory they were 12 of the 24 L1 sectors per observation of a kernel that
+// is L1-throughput bound (ncu: l1tex 77 %).
+template <int G, bool CAMTAB>
+__global__ void __launch_bounds__(PT_THREADS) ba_backsub_z_kernel(BAView v, double inv_radius, const double* __restrict__ y_cf, const double* cand_cf,
+                                                                  const CamDerived* camd_c, double* pts_c, double* __restrict__ post) {
+    extern __shared__ __align__(16) double camtab[];                  // [nc][18]: R(9) t(3) y_c(6)   (CAMTAB)
+    const LMX x = lm_x(v);
+    if (!x.run) return;
+    if (v.st) { const int nxt = v.st->cur ^ 1; cand_cf = v.cf2[nxt]; camd_c = v.camd2[nxt]; pts_c = v.pts2[nxt]; inv_radius = 1.0 / v.st->radius; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    constexpr int GB = PT_THREADS / G;
+    const double yf = y_cf[6 * v.nc], fc = cand_cf[6 * v.nc];
+    if (CAMTAB) {
+        for (int i = threadIdx.x; i < v.nc * 18; i += PT_THREADS) {
+            const int c = i / 18, q = i - 18 * c;
+            camtab[i] = q < 12 ? reinterpret_cast<const double*>(camd_c + c)[q] : y_cf[6 * c + q - 12];
+        }
+        __syncthreads();
+    }
+    double acc_cc = 0, acc_m = 0, acc_dn = 0, acc_cn = 0;
+    constexpr int GW = 32 / G;
+    __shared__ __align__(16) double zstage[PT_THREADS / 32][32 * 18];
+    const int np_round = (v.np + GB - 1) / GB * GB;
+    for (int p0 = blockIdx.x * GB; p0 < np_round; p0 += gridDim.x * GB) {
+        const int p = p0 + threadIdx.x / G;
+        const bool active = p < v.np;
+        const int o0 = active ? v.pt_off[p] : 0, k = active ? v.pt_off[p + 1] - o0 : 0;
+        // the warp's Z records are one contiguous range (at most G observations per point): coalesced load into shared memory,
+        // then every lane reads its own record (conflict free) -- a lane-per-record global load touches 36 lines per instruction
+        const bool stage = v.maxk <= G;
+        int o_first = 0;
+        if (stage) {
+            const int p_first = (p0 + warp * GW);
+            o_first = p_first < v.np ? v.pt_off[p_first] : 0;
+            const int o_end = p_first < v.np ? v.pt_off[min(p_first + GW, v.np)] : 0;
+            __syncwarp();
+            const double2* in = reinterpret_cast<const double2*>(v.Zbuf + (size_t)o_first * 18);
+            double2* dstz = reinterpret_cast<double2*>(zstage[warp]);
+            for (int i = lane; i < (o_end - o_first) * 9; i += 32) dstz[i] = in[i];
+            __syncwarp();
+        }
+        double t[3] = {0, 0, 0};
+        for (int j = gl; j < k; j += G) {
+            const int o = o0 + j, c = v.obs_cam[o];
+            const double2* z = stage ? reinterpret_cast<const double2*>(zstage[warp] + (size_t)(o - o_first) * 18)
+                                     : reinterpret_cast<const double2*>(v.Zbuf + (size_t)o * 18);
+#pragma unroll
+            for (int a = 0; a < 6; a += 2) {          // rows a, a+1 = six doubles = three 16-byte loads
+                const double2 z0 = z[a / 2 * 3], z1 = z[a / 2 * 3 + 1], z2 = z[a / 2 * 3 + 2];
+                const double ya = CAMTAB ? camtab[18 * c + 12 + a] : y_cf[6 * c + a], yb = CAMTAB ? camtab[18 * c + 13 + a] : y_cf[6 * c + a + 1];
+                t[0] += z0.x * ya + z1.y * yb; t[1] += z0.y * ya + z2.x * yb; t[2] += z1.x * ya + z2.y * yb;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t[a] = group_sum<G>(t[a], gmask);
+        if (!active) continue;
+        const double X[3] = {x.pts[3 * p], x.pts[3 * p + 1], x.pts[3 * p + 2]};
+        const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
+        const double* pb = v.ptblk + (size_t)p * PTB;
+        const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
+        const double u0 = pb[6] - t[0] - pb[9] * yf, u1 = pb[7] - t[1] - pb[10] * yf, u2 = pb[8] - t[2] - pb[11] * yf;
+        const double yp[3] = {M[0] * u0 + M[1] * u1 + M[3] * u2, M[2] * u1 + M[4] * u2, M[5] * u2};
+        const double Xc[3] = {X[0] - yp[0] * sp[0], X[1] - yp[1] * sp[1], X[2] - yp[2] * sp[2]};
+        if (gl == 0) {
+            pts_c[3 * p] = Xc[0]; pts_c[3 * p + 1] = Xc[1]; pts_c[3 * p + 2] = Xc[2];
+            const double d0 = X[0] - Xc[0], d1 = X[1] - Xc[1], d2 = X[2] - Xc[2];
+            acc_dn += d0 * d0 + d1 * d1 + d2 * d2;
+            acc_cn += Xc[0] * Xc[0] + Xc[1] * Xc[1] + Xc[2] * Xc[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) acc_m -= 0.5 * yp[a] * (pb[12 + a] + clampd(pb[15 + a], v.min_diag, v.max_diag) * inv_radius * yp[a]);
+        }
+        for (int j = gl; j < k; j += G) {
+            const int o = o0 + j, c = v.obs_cam[o];
+            const float2 xy = v.obs_xy[o];
+            double rc[2];
+            if (CAMTAB) {
+                const double* ct = camtab + 18 * c;                    // same arithmetic as obs_residual
+                const double p0 = ct[0] * Xc[0] + ct[1] * Xc[1] + ct[2] * Xc[2] + ct[9];
+                const double p1 = ct[3] * Xc[0] + ct[4] * Xc[1] + ct[5] * Xc[2] + ct[10];
+                const double p2 = ct[6] * Xc[0] + ct[7] * Xc[1] + ct[8] * Xc[2] + ct[11];
+                const double iz = 1.0 / p2;
+                rc[0] = fc * (p0 * iz) - (double)xy.x; rc[1] = fc * (p1 * iz) - (double)xy.y;
+            } else obs_residual(camd_c[c], Xc, fc, (double)xy.x, (double)xy.y, rc);
+            acc_cc += rc[0] * rc[0] + rc[1] * rc[1];
+        }
+    }
+    __shared__ double sred[PT_THREADS / 32][4];
+    const double c0 = warp_sum(acc_cc), c1 = warp_sum(acc_m), c2 = warp_sum(acc_dn), c3 = warp_sum(acc_cn);
+    if (lane == 0) { sred[warp][0] = c0; sred[warp][1] = c1; sred[warp][2] = c2; sred[warp][3] = c3; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w][threadIdx.x];
+        red_add(post + threadIdx.x, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Back substitution for the points + step evaluation, fused (point-major, same grouping as K3a):
 //   y_p = M^T (zg - M sum_o Jp^T (Jc y_c + Jf y_f)) ;  candidate X' = X - y_p*scale
 //   model cost change accumulates  m.(r + m/2)  with m = J*step ;  candidate cost from the residual at the candidate.
@@ -744,7 +876,7 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, c
         const int o0 = v.pt_off[p], k = v.pt_off[p + 1] - o0;
         const double X[3] = {x.pts[3 * p], x.pts[3 * p + 1], x.pts[3 * p + 2]};
         const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
-        const double* pb = v.ptblk + (size_t)p * 12;
+        const double* pb = v.ptblk + (size_t)p * PTB;
         const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
         const double zg[3] = {pb[6], pb[7], pb[8]};
         // pass 1: t = sum_o Jp^T (Jc y_c + Jf y_f).  For the lane's first observation the pieces pass 2 needs
@@ -930,6 +1062,7 @@ struct sfmb200_ba_problem {
     unsigned* chol_ready = nullptr; unsigned chol_epoch = 0; int chol_grid = 0; bool chol_fused = true, chol_lookahead = false;   // dataflow Cholesky (K4)
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
     bool have_scale = false;
+    bool backsub_from_z = false;      // back-substitution + model cost from the stored Z blocks (gather mode) instead of re-evaluated Jacobians
     bool camd_valid[2] = {false, false};   // camd[i] matches cf[i] (written by cam_derive or, for the candidate, by ba_cam_update_kernel)
     EvSet evs[LM_CHUNK];              // profile mode: one set of events per iteration of a chunk (created on first use)
     bool have_events = false;
@@ -1012,8 +1145,19 @@ template <int G> static int launch_point_norm(sfmb200_ba_problem* P, const BAVie
 template <int G> static int launch_backsub(sfmb200_ba_problem* P, const BAView& v) {
     sfmb200_ctx* ctx = P->ctx;
     const int GB = PT_THREADS / G, nxt = P->cur ^ 1;
-    const int blocks = resident_grid(P, &P->grid_backsub, ba_backsub_eval_kernel<G>, PT_THREADS, 0, ceil_div(P->np, GB), 16);
-    ba_backsub_eval_kernel<G><<<blocks, PT_THREADS, 0, ctx->stream>>>(v, P->y_cf, P->cf[nxt], P->camd[nxt], P->pts[nxt], P->post);
+    if (P->backsub_from_z) {            // gather mode: Z_o is in Zbuf, no Jacobian needed (inside the LM loop the radius comes from LMState)
+        const size_t tab = sizeof(double) * 18 * (size_t)P->nc;
+        if (tab <= 40 * 1024) {
+            const int blocks = resident_grid(P, &P->grid_backsub, ba_backsub_z_kernel<G, true>, PT_THREADS, tab, ceil_div(P->np, GB), 16);
+            ba_backsub_z_kernel<G, true><<<blocks, PT_THREADS, tab, ctx->stream>>>(v, 0.0, P->y_cf, P->cf[nxt], P->camd[nxt], P->pts[nxt], P->post);
+        } else {
+            const int blocks = resident_grid(P, &P->grid_backsub, ba_backsub_z_kernel<G, false>, PT_THREADS, 0, ceil_div(P->np, GB), 16);
+            ba_backsub_z_kernel<G, false><<<blocks, PT_THREADS, 0, ctx->stream>>>(v, 0.0, P->y_cf, P->cf[nxt], P->camd[nxt], P->pts[nxt], P->post);
+        }
+    } else {
+        const int blocks = resident_grid(P, &P->grid_backsub, ba_backsub_eval_kernel<G>, PT_THREADS, 0, ceil_div(P->np, GB), 16);
+        ba_backsub_eval_kernel<G><<<blocks, PT_THREADS, 0, ctx->stream>>>(v, P->y_cf, P->cf[nxt], P->camd[nxt], P->pts[nxt], P->post);
+    }
     SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
@@ -1183,7 +1327,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     add(8 * (size_t)nobs); add(4 * (size_t)nobs); add(4 * (size_t)(np + 1)); add(4 * (size_t)(nc + 1)); add(8 * (size_t)nobs); add(4 * (size_t)nobs);
     for (int i = 0; i < 3; ++i) { add(8 * n); add(24 * (size_t)np); }
     add(sizeof(CamDerived) * (size_t)nc); add(sizeof(CamDerived) * (size_t)nc);
-    add(8 * n); add(24 * (size_t)np); add(96 * (size_t)np); add(8 * (P->red_n + 32));
+    add(8 * n); add(24 * (size_t)np); add(8 * PTB * (size_t)np); add(8 * (P->red_n + 32));
     add(8 * (size_t)P->npad * P->npad); add(8 * n); add(8 * (size_t)P->npad); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
     add(4 * (size_t)(P->npad / NB) * (P->npad / NB)); add(8 * (size_t)P->npad * NB); add(4 * (size_t)(P->npad / NB)); add(sizeof(LMState));
     if (!ctx->ba_ws.in_use) {           // borrow the cached workspace (grown below when too small)
@@ -1199,7 +1343,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->cf[0] = cv.take<double>(n); P->pts[0] = cv.take<double>(3 * (size_t)np); P->cf[1] = cv.take<double>(n); P->pts[1] = cv.take<double>(3 * (size_t)np);
     P->cf0 = cv.take<double>(n); P->pts0 = cv.take<double>(3 * (size_t)np);
     P->camd[0] = cv.take<CamDerived>(nc); P->camd[1] = cv.take<CamDerived>(nc);
-    P->scale_cf = cv.take<double>(n); P->scale_pt = cv.take<double>(3 * (size_t)np); P->ptblk = cv.take<double>(12 * (size_t)np);
+    P->scale_cf = cv.take<double>(n); P->scale_pt = cv.take<double>(3 * (size_t)np); P->ptblk = cv.take<double>(PTB * (size_t)np);
     // exchange memory: [red (red_n) | post 8 | locals 8 | gmax 1 | pad 1 | fail 1 | pad][flags 2*MAX_PEERS u64]
     P->xmem_doubles = P->red_n + 24 + 2 * MAX_PEERS;
     {
@@ -1298,6 +1442,8 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
             CRT(P->gmem.reserve(Carver::pad(8 * 18 * (size_t)std::max(nobs, 1)) + 256));
             P->Zbuf = (double*)P->gmem.p;
         }
+        const char* bm = getenv("SFMB200_BA_BACKSUB");
+        P->backsub_from_z = P->gather && P->Zbuf && !(bm && strcmp(bm, "jacobian") == 0);
     }
 #undef CRT
     *out = P;
@@ -1456,7 +1602,7 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
             rc = dense_solve(P, &opt, 0.0, true); if (rc) return rc;
             if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[5], ctx->stream));
             BAView v = make_view(P, &opt, true);
-            ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(v, nullptr, P->y_cf, P->scale_cf, P->gcf, P->nc, nullptr, nullptr, P->locals,
+            ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(v, 0.0, P->backsub_from_z ? 1 : 0, nullptr, P->y_cf, P->scale_cf, P->gcf, P->nc, nullptr, nullptr, P->locals,
                                                              P->post, P->gmax_pt_bits, P->fail);
             SFM_LAUNCH_CHECK(ctx);
             if (P->np > 0 && P->nobs > 0) { rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }

@@ -203,6 +203,22 @@ def _same_trajectory(a, b):
     np.testing.assert_allclose(a[1][1], b[1][1], rtol=0, atol=1e-8)
 
 
+def test_backsubstitution_from_stored_blocks_matches_jacobian_path(ctx, monkeypatch):
+    """Default back-substitution (stored Z blocks, model cost change as 1/2 y.(g + D^2 y)) against the kernel that
+    re-evaluates the Jacobians and forms Ceres' -m.(r + m/2): same LM trajectory, accepted and rejected steps alike."""
+    p = synth.make_ba_problem(n_cams=30, n_pts=4000, obs_per_pt=7, seed=33)
+    out = {}
+    for mode in ("stored", "jacobian"):
+        monkeypatch.setenv("SFMB200_BA_BACKSUB", mode)
+        prob = ctx.ba_problem(*_args(p))
+        o = capi.ba_default_options(); o.max_num_iterations = 12; o.initial_trust_region_radius = 1e2    # small radius: some steps get rejected
+        out[mode] = (prob.run(o), prob.download())
+        prob.close()
+    a, b = out["stored"], out["jacobian"]
+    assert a[0]["num_successful_steps"] == b[0]["num_successful_steps"] and a[0]["num_unsuccessful_steps"] == b[0]["num_unsuccessful_steps"]
+    _same_trajectory(a, b)
+
+
 def test_many_observations_per_point_and_ragged_tracks(ctx, oracle):
     """Track lengths 2..40 in one problem (G = 32 groups, multi-chunk points, long pair lists)."""
     rs = np.random.RandomState(5)
