@@ -231,6 +231,14 @@ __global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, doubl
         const bool active = p < v.np;
         int o0 = 0, k = 0;
         double X[3] = {0, 0, 0}, sp[3] = {1, 1, 1};
+        {   // pull the next iteration's point and observation lines into L2 while this one computes (no registers held)
+            const int pn = p + gridDim.x * GB;
+            if (pn < v.np && gl == 0) {
+                const int on = v.pt_off[pn];
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(v.obs_cam + on)); asm volatile("prefetch.global.L2 [%0];" :: "l"(v.obs_xy + on));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(x.pts + 3 * (size_t)pn)); asm volatile("prefetch.global.L2 [%0];" :: "l"(v.scale_pt + 3 * (size_t)pn));
+            }
+        }
         if (active) {
             o0 = v.pt_off[p]; k = v.pt_off[p + 1] - o0;
             X[0] = x.pts[3 * p]; X[1] = x.pts[3 * p + 1]; X[2] = x.pts[3 * p + 2];
@@ -780,18 +788,40 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_z_kernel(BAView v, doub
     constexpr int GW = 32 / G;
     __shared__ __align__(16) double zstage[PT_THREADS / 32][32 * 18];
     const int np_round = (v.np + GB - 1) / GB * GB;
+    // The iteration is a chain of dependent loads (offsets -> records / indices -> per-camera data); with 24 warps per SM that
+    // latency is exposed, so the NEXT iteration's lines are pulled into L2 while this one computes (prefetch.global.L2: no
+    // registers), and its CSR offsets are loaded one iteration ahead.
+    int o0_next = 0, k_next = 0;
+    { const int pn = blockIdx.x * GB + threadIdx.x / G; if (pn < v.np) { o0_next = v.pt_off[pn]; k_next = v.pt_off[pn + 1] - o0_next; } }
     for (int p0 = blockIdx.x * GB; p0 < np_round; p0 += gridDim.x * GB) {
         const int p = p0 + threadIdx.x / G;
         const bool active = p < v.np;
-        const int o0 = active ? v.pt_off[p] : 0, k = active ? v.pt_off[p + 1] - o0 : 0;
+        const int o0 = o0_next, k = k_next;
+        {
+            const int pn = p + gridDim.x * GB;
+            o0_next = 0; k_next = 0;
+            if (pn < v.np) {
+                o0_next = v.pt_off[pn]; k_next = v.pt_off[pn + 1] - o0_next;
+                if (gl < k_next) {
+                    const char* zr = reinterpret_cast<const char*>(v.Zbuf + (size_t)(o0_next + gl) * 18);
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(zr)); asm volatile("prefetch.global.L2 [%0];" :: "l"(zr + 128));
+                }
+                if (gl == 0) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(v.obs_cam + o0_next)); asm volatile("prefetch.global.L2 [%0];" :: "l"(v.obs_xy + o0_next));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(x.pts + 3 * (size_t)pn)); asm volatile("prefetch.global.L2 [%0];" :: "l"(v.scale_pt + 3 * (size_t)pn));
+                    const char* pbn = reinterpret_cast<const char*>(v.ptblk + (size_t)pn * PTB);
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(pbn)); asm volatile("prefetch.global.L2 [%0];" :: "l"(pbn + 128));
+                }
+            }
+        }
         // the warp's Z records are one contiguous range (at most G observations per point): coalesced load into shared memory,
         // then every lane reads its own record (conflict free) -- a lane-per-record global load touches 36 lines per instruction
         const bool stage = v.maxk <= G;
         int o_first = 0;
         if (stage) {
-            const int p_first = (p0 + warp * GW);
-            o_first = p_first < v.np ? v.pt_off[p_first] : 0;
-            const int o_end = p_first < v.np ? v.pt_off[min(p_first + GW, v.np)] : 0;
+            // the warp's range of records: from its first group's offset to the end of its last active group (no extra loads)
+            o_first = __shfl_sync(0xffffffffu, o0, 0);
+            const int o_end = (int)__reduce_max_sync(0xffffffffu, (unsigned)(o0 + k));
             __syncwarp();
             const double2* in = reinterpret_cast<const double2*>(v.Zbuf + (size_t)o_first * 18);
             double2* dstz = reinterpret_cast<double2*>(zstage[warp]);
