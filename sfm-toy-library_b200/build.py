@@ -80,6 +80,23 @@ def build_host(force=False):
     return out
 
 
+def build_glue(force=False):
+    """Host glue of SURVEY.md 8(f-1) (host/sfm_glue.cpp: indexed find2D3DMatches / mergeNewPointCloud) + its test binary, which
+    checks it against the naive restatement in oracle/host_glue_naive.hpp.  Pure C++, no GPU, no CUDA library."""
+    hdir = os.path.join(HERE, "host"); out = os.path.join(hdir, "build", "test_glue")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    deps = [os.path.join(hdir, f) for f in ("sfm_glue.cpp", "sfm_glue.h", "test_glue.cpp", "sfmtoylib_b200.h", "cv_min.h")]
+    deps.append(os.path.join(os.path.dirname(HERE), "oracle", "host_glue_naive.hpp"))
+    if force or _stale(out, deps):
+        r = subprocess.run([HOST_CXX, "-std=c++17", "-O2", "-Wall", os.path.join(hdir, "sfm_glue.cpp"), os.path.join(hdir, "test_glue.cpp"),
+                            "-I", hdir, "-o", out], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("host glue build failed")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host(force="--force" in sys.argv))
+    print(build_glue(force="--force" in sys.argv))
