@@ -1034,8 +1034,11 @@ __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* 
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__global__ void peer_signal_kernel(PeerTable t, int slot, int my_rank, int nranks, unsigned long long epoch) {
-    if ((int)threadIdx.x < nranks) {
+// Every kernel of the exchange first tells the peers that THIS rank has reached the point the kernel stands for (stream order
+// guarantees it: `slot` 0 = "my partial buffer is final", 1 = "I have finished reading yours"), then waits until every rank
+// has said the same.  Folding the signal into the consumer kernel halves the launches of an all-reduce (4 -> 2).
+__device__ __forceinline__ void peer_signal(const PeerTable& t, int slot, int my_rank, int nranks, unsigned long long epoch) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < nranks) {
         __threadfence_system();
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.flags[threadIdx.x] + slot * MAX_PEERS + my_rank), "l"(epoch) : "memory");
     }
@@ -1047,6 +1050,7 @@ __device__ __forceinline__ void peer_wait(const unsigned long long* my_flags, in
 }
 __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerTable t, size_t offset, int my_rank, int nranks, unsigned long long epoch,
                                                           size_t n_sum, size_t n_max, double* __restrict__ tmp) {
+    peer_signal(t, 0, my_rank, nranks, epoch);
     peer_wait(t.flags[my_rank], 0, nranks, epoch);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sum + n_max; i += (size_t)gridDim.x * blockDim.x) {
         double acc = __ldcv(t.buf[0] + offset + i);
@@ -1056,6 +1060,7 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerTable t, size_t of
 }
 __global__ void __launch_bounds__(256) peer_copyback_kernel(PeerTable t, size_t offset, int my_rank, int nranks, unsigned long long epoch,
                                                             size_t n, const double* __restrict__ tmp) {
+    peer_signal(t, 1, my_rank, nranks, epoch);
     peer_wait(t.flags[my_rank], 1, nranks, epoch);
     double* dst = t.buf[my_rank] + offset;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = tmp[i];
@@ -1212,9 +1217,7 @@ static int ba_allreduce(sfmb200_ba_problem* P, double* buf, size_t n_sum, size_t
     const size_t offset = buf - (double*)P->xmem, n = n_sum + n_max;
     const unsigned long long e = ++P->epoch;
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 4));
-    peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(P->ptab, 0, ctx->rank, ctx->nranks, e); SFM_LAUNCH_CHECK(ctx);
     peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n_sum, n_max, P->xtmp); SFM_LAUNCH_CHECK(ctx);
-    peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(P->ptab, 1, ctx->rank, ctx->nranks, e); SFM_LAUNCH_CHECK(ctx);
     peer_copyback_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n, P->xtmp); SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
