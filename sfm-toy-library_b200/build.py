@@ -96,7 +96,22 @@ def build_glue(force=False):
     return out
 
 
+def build_ply(force=False):
+    """ASCII PLY writers of SURVEY.md 8(f-4) (host/sfm_ply.cpp) + the small driver the CPU test feeds scenes to."""
+    hdir = os.path.join(HERE, "host"); out = os.path.join(hdir, "build", "test_ply")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    deps = [os.path.join(hdir, f) for f in ("sfm_ply.cpp", "sfm_ply.h", "test_ply.cpp", "sfmtoylib_b200.h", "cv_min.h")]
+    if force or _stale(out, deps):
+        r = subprocess.run([HOST_CXX, "-std=c++17", "-O2", "-Wall", os.path.join(hdir, "sfm_ply.cpp"), os.path.join(hdir, "test_ply.cpp"),
+                            "-I", hdir, "-o", out], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("PLY writer build failed")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host(force="--force" in sys.argv))
     print(build_glue(force="--force" in sys.argv))
+    print(build_ply(force="--force" in sys.argv))

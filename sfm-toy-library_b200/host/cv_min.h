@@ -10,7 +10,8 @@
 
 namespace cv {
 
-enum { CV_8U = 0, CV_32F = 5 };
+enum { CV_8U = 0, CV_32F = 5, CV_8UC3 = 16 };
+struct Vec3b { unsigned char val[3]; unsigned char operator()(int i) const { return val[i]; } };
 
 template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T a, T b) : x(a), y(b) {} };
 typedef Point_<float> Point2f;
@@ -52,7 +53,7 @@ public:
     template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data) + (size_t)r * cols; }
     template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data) + (size_t)r * cols; }
 private:
-    static size_t elem(int t) { return t == CV_32F ? 4 : 1; }
+    static size_t elem(int t) { return t == CV_32F ? 4 : (t == CV_8UC3 ? 3 : 1); }
     int type_ = CV_8U;
     std::shared_ptr<std::vector<uint8_t>> buf_;
 };
