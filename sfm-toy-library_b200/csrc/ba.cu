@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(256) ba_cam_update_kernel(BAView v, double inv
         // rank-local flags -> buffers that are reduced over ranks (sum / max) so that every rank takes the same decision
         post[7] = __longlong_as_double((long long)*gmax_pt_bits);      // max-reduced over ranks
         post[4] = (double)fail[0]; post[5] = (double)fail[1];
+        post[0] = post[1] = post[2] = post[3] = post[6] = 0.0;        // accumulated by the back-substitution kernel that follows (not part of the pass memset: peers may still read it there)
     }
     __syncthreads();            // cand_cf complete
     for (int c2 = threadIdx.x; c2 < nc; c2 += blockDim.x) { CamDerived d; cam_derive(cand_cf + 6 * c2, d); camd_c[c2] = d; }
@@ -1034,9 +1035,12 @@ __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* 
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// Every kernel of the exchange first tells the peers that THIS rank has reached the point the kernel stands for (stream order
-// guarantees it: `slot` 0 = "my partial buffer is final", 1 = "I have finished reading yours"), then waits until every rank
-// has said the same.  Folding the signal into the consumer kernel halves the launches of an all-reduce (4 -> 2).
+// The reduction kernel first tells the peers that THIS rank's partial buffer is final (stream order guarantees it), then waits
+// until every rank has said the same, then sums the peers' buffers in rank order into a rank-LOCAL copy (P->xtmp, same
+// offsets as the exchange buffer) that the consumers read -- nothing is written back into the exchanged buffer, so no second
+// "done reading" handshake is needed: a rank overwrites a region of its exchange buffer only after a LATER hand-shake in
+// which every peer took part after finishing its reads (red: cleared after the post reduction of the same iteration; post:
+// cleared by ba_cam_update_kernel after the red reduction of the next one).  One launch and one hand-shake per all-reduce.
 __device__ __forceinline__ void peer_signal(const PeerTable& t, int slot, int my_rank, int nranks, unsigned long long epoch) {
     if (blockIdx.x == 0 && (int)threadIdx.x < nranks) {
         __threadfence_system();
@@ -1049,21 +1053,14 @@ __device__ __forceinline__ void peer_wait(const unsigned long long* my_flags, in
     __threadfence_system();
 }
 __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerTable t, size_t offset, int my_rank, int nranks, unsigned long long epoch,
-                                                          size_t n_sum, size_t n_max, double* __restrict__ tmp) {
+                                                          size_t n_sum, size_t n_max, double* __restrict__ out) {
     peer_signal(t, 0, my_rank, nranks, epoch);
     peer_wait(t.flags[my_rank], 0, nranks, epoch);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sum + n_max; i += (size_t)gridDim.x * blockDim.x) {
         double acc = __ldcv(t.buf[0] + offset + i);
         for (int r = 1; r < nranks; ++r) { const double v = __ldcv(t.buf[r] + offset + i); acc = i < n_sum ? acc + v : fmax(acc, v); }
-        tmp[i] = acc;
+        out[i] = acc;
     }
-}
-__global__ void __launch_bounds__(256) peer_copyback_kernel(PeerTable t, size_t offset, int my_rank, int nranks, unsigned long long epoch,
-                                                            size_t n, const double* __restrict__ tmp) {
-    peer_signal(t, 1, my_rank, nranks, epoch);
-    peer_wait(t.flags[my_rank], 1, nranks, epoch);
-    double* dst = t.buf[my_rank] + offset;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = tmp[i];
 }
 
 }  // namespace
@@ -1217,9 +1214,24 @@ static int ba_allreduce(sfmb200_ba_problem* P, double* buf, size_t n_sum, size_t
     const size_t offset = buf - (double*)P->xmem, n = n_sum + n_max;
     const unsigned long long e = ++P->epoch;
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 4));
-    peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n_sum, n_max, P->xtmp); SFM_LAUNCH_CHECK(ctx);
-    peer_copyback_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n, P->xtmp); SFM_LAUNCH_CHECK(ctx);
+    peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n_sum, n_max, P->xtmp + offset); SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
+}
+
+// Hand-shake only (peer exchange): after it every rank has finished the reads of all earlier reductions.  Needed where a region
+// of the exchange buffer is overwritten without a later reduction in between (after the scaling pass; at the end of the
+// reduced-system API call).
+static int ba_peer_barrier(sfmb200_ba_problem* P) {
+    sfmb200_ctx* ctx = P->ctx;
+    if (ctx->nranks <= 1 || !P->peers) return SFMB200_OK;
+    peer_reduce_kernel<<<1, 256, 0, ctx->stream>>>(P->ptab, 0, ctx->rank, ctx->nranks, ++P->epoch, 0, 0, P->xtmp); SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
+
+// Where the rank-summed value of a location of the exchange buffer lives: in place (single GPU, NCCL) or in the local copy the
+// peer reduction writes (same offset).
+template <typename T> static T* summed(const sfmb200_ba_problem* P, T* p) {
+    return P->peers ? reinterpret_cast<T*>(P->xtmp + (reinterpret_cast<double*>(p) - P->red)) : p;
 }
 
 // Jacobi scaling at the current x (iteration 0).  Multi-GPU: camera/focal column norms are summed over ranks.
@@ -1242,9 +1254,9 @@ static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt)
         ba_camera_norm_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v, colnorm); SFM_LAUNCH_CHECK(ctx);
     }
     int rc = ba_allreduce(P, colnorm, n, 0); if (rc) return rc;
-    scale_from_norm_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(colnorm, n, P->scale_cf); SFM_LAUNCH_CHECK(ctx);
+    scale_from_norm_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(summed(P, colnorm), n, P->scale_cf); SFM_LAUNCH_CHECK(ctx);
     P->have_scale = true;
-    return SFMB200_OK;
+    return ba_peer_barrier(P);          // the column norms sit in the region the first pass clears
 }
 
 // One residual+Jacobian+Schur pass at the current x; leaves the (rank-summed) reduced system in red.
@@ -1254,7 +1266,7 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
     sfmb200_ctx* ctx = P->ctx;
     BAView v = make_view(P, opt, lm);
     const LMState* st = lm ? P->d_state : nullptr;
-    SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * (P->red_n + 20), ctx->stream));   // red | post, locals, gmax, fail (contiguous)
+    SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * (P->red_n + 12), ctx->stream));   // red | locals, gmax, fail (contiguous); post is cleared by ba_cam_update_kernel
     if (!lm && !P->camd_valid[P->cur]) {
         cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
         P->camd_valid[P->cur] = true;
@@ -1283,7 +1295,7 @@ static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, dou
     const int npad = P->npad, nbk = npad / NB;
     const LMState* st = lm ? P->d_state : nullptr;
     const int* skip = lm ? &P->d_state->status : nullptr;
-    ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(P->Sblk, P->Scf, P->Sff, P->rhs, P->dcf, P->nc, npad, 1.0 / radius,
+    ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(summed(P, P->Sblk), summed(P, P->Scf), summed(P, P->Sff), summed(P, P->rhs), summed(P, P->dcf), P->nc, npad, 1.0 / radius,
                                                                                  opt->min_lm_diagonal, opt->max_lm_diagonal, P->A, st);
     SFM_LAUNCH_CHECK(ctx);
     if (P->chol_fused) {
@@ -1377,7 +1389,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->cf0 = cv.take<double>(n); P->pts0 = cv.take<double>(3 * (size_t)np);
     P->camd[0] = cv.take<CamDerived>(nc); P->camd[1] = cv.take<CamDerived>(nc);
     P->scale_cf = cv.take<double>(n); P->scale_pt = cv.take<double>(3 * (size_t)np); P->ptblk = cv.take<double>(PTB * (size_t)np);
-    // exchange memory: [red (red_n) | post 8 | locals 8 | gmax 1 | pad 1 | fail 1 | pad][flags 2*MAX_PEERS u64]
+    // exchange memory: [red (red_n) | locals 8 | gmax 1 | pad 1 | fail 1 | pad 1 | post 8 | pad 4][flags 2*MAX_PEERS u64]
     P->xmem_doubles = P->red_n + 24 + 2 * MAX_PEERS;
     {
         cudaError_t ex = P->xbuf.reserve(8 * P->xmem_doubles + 256);
@@ -1388,7 +1400,9 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->red = (double*)P->xmem;
     P->xtmp = cv.take<double>(P->red_n + 32);
     P->Sblk = P->red; P->Scf = P->Sblk + 36 * nblk; P->Sff = P->Scf + 6 * (size_t)nc; P->rhs = P->Sff + 1; P->gcf = P->rhs + n; P->dcf = P->gcf + n; P->sums = P->dcf + n;
-    P->post = P->red + P->red_n; P->xflags = (unsigned long long*)(P->post + 24); P->locals = P->post + 8; P->gmax_pt_bits = (unsigned long long*)(P->locals + 8); P->fail = (int*)(P->locals + 10);
+    // after red: locals 8 | gmax 1 | pad 1 | fail 1 | pad 1 | post 8 | pad 4 | flags
+    P->locals = P->red + P->red_n; P->gmax_pt_bits = (unsigned long long*)(P->locals + 8); P->fail = (int*)(P->locals + 10); P->post = P->locals + 12;
+    P->xflags = (unsigned long long*)(P->red + P->red_n + 24);
     P->A = cv.take<double>((size_t)P->npad * P->npad); P->y_cf = cv.take<double>(n); P->dinv = cv.take<double>(P->npad);
     int32_t* obs_pt = cv.take<int32_t>(nobs); int* cnt = cv.take<int>(2 * (size_t)(nc + 1)); int* cursor = cnt + nc + 1;
     P->chol_ready = cv.take<unsigned>((size_t)(P->npad / NB) * (P->npad / NB));
@@ -1567,14 +1581,15 @@ int sfmb200_ba_problem_reduced_system(sfmb200_ba_problem* P, const sfmb200_ba_op
     if (!P->have_scale) { rc = compute_scaling(P, &opt); if (rc) return rc; }
     rc = schur_pass(P, &opt, radius, nullptr, false); if (rc) return rc;
     const int n = P->n, npad = P->npad;
-    ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(P->Sblk, P->Scf, P->Sff, P->rhs, P->dcf, P->nc, npad, 1.0 / radius,
+    ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(summed(P, P->Sblk), summed(P, P->Scf), summed(P, P->Sff), summed(P, P->rhs), summed(P, P->dcf), P->nc, npad, 1.0 / radius,
                                                                                  opt.min_lm_diagonal, opt.max_lm_diagonal, P->A, nullptr);
     SFM_LAUNCH_CHECK(ctx);
     std::vector<double> hA((size_t)npad * npad), hg(n), hs(n), hsum(8);
     SFM_CUDA(ctx, cudaMemcpyAsync(hA.data(), P->A, 8 * hA.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    SFM_CUDA(ctx, cudaMemcpyAsync(hg.data(), P->gcf, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(hg.data(), summed(P, P->gcf), 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(ctx, cudaMemcpyAsync(hs.data(), P->scale_cf, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    SFM_CUDA(ctx, cudaMemcpyAsync(hsum.data(), P->sums, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(hsum.data(), summed(P, P->sums), 64, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = ba_peer_barrier(P); if (rc) return rc;
     SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (S) for (int r = 0; r < n; ++r) for (int c = 0; c <= r; ++c) { const double v = hA[(size_t)r * npad + c]; S[(size_t)r * n + c] = v; S[(size_t)c * n + r] = v; }
     if (rhs) for (int c = 0; c < n; ++c) rhs[c] = hA[(size_t)n * npad + c];
@@ -1635,12 +1650,15 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
             rc = dense_solve(P, &opt, 0.0, true); if (rc) return rc;
             if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[5], ctx->stream));
             BAView v = make_view(P, &opt, true);
-            ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(v, 0.0, P->backsub_from_z ? 1 : 0, nullptr, P->y_cf, P->scale_cf, P->gcf, P->nc, nullptr, nullptr, P->locals,
-                                                             P->post, P->gmax_pt_bits, P->fail);
+            {
+                BAView vc = v; vc.dcf = summed(P, P->dcf);              // the rank-summed J^T J diagonal and gradient
+                ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(vc, 0.0, P->backsub_from_z ? 1 : 0, nullptr, P->y_cf, P->scale_cf, summed(P, P->gcf), P->nc, nullptr, nullptr, P->locals,
+                                                                 P->post, P->gmax_pt_bits, P->fail);
+            }
             SFM_LAUNCH_CHECK(ctx);
             if (P->np > 0 && P->nobs > 0) { rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }
             rc = ba_allreduce(P, P->post, 7, 1); if (rc) return rc;   // sums: candidate cost, model, norms, failure counts; max: |g| of the points
-            ba_lm_control_kernel<<<1, 32, 0, ctx->stream>>>(P->d_state, P->sums, P->post, P->locals, opt); SFM_LAUNCH_CHECK(ctx);
+            ba_lm_control_kernel<<<1, 32, 0, ctx->stream>>>(P->d_state, summed(P, P->sums), summed(P, P->post), P->locals, opt); SFM_LAUNCH_CHECK(ctx);
         }
         SFM_CUDA(ctx, cudaMemcpyAsync(hs, P->d_state, sizeof *hs, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
