@@ -68,6 +68,7 @@ def main():
     l0 = ctx.kernel_launches
     ms = timed(lambda: ds.match_pairs_device(pairs, dq.data_ptr(), dt_.data_ptr(), dd.data_ptr(), dst.data_ptr(), dtot.data_ptr()), args.reps)
     launches = (ctx.kernel_launches - l0) // (args.reps + 1)
+    ds.match_pairs(pairs)                                   # untimed: first call allocates the pinned result staging
     t0 = time.perf_counter(); res = ds.match_pairs(pairs); e2e_s = time.perf_counter() - t0
     n_matches = int(sum(len(r[0]) for r in res))
     dist_evals = float(args.features) ** 2 * len(pairs)
@@ -99,6 +100,7 @@ def main():
     dl = torch.from_numpy(p["ptsL"]).cuda(); dr = torch.from_numpy(p["ptsR"]).cuda()
     dX = torch.empty(m * 3, dtype=torch.float32, device="cuda"); dk = torch.empty(m, dtype=torch.uint8, device="cuda"); dn = torch.empty(1, dtype=torch.int32, device="cuda")
     ms = timed(lambda: ctx.triangulate_device(p["K"], p["Pl"], p["Pr"], dl.data_ptr(), dr.data_ptr(), None, None, m, dX.data_ptr(), dk.data_ptr(), dn.data_ptr()), args.reps)
+    ctx.triangulate(p["K"], p["Pl"], p["Pr"], p["ptsL"], p["ptsR"])      # untimed: first call grows the device scratch
     t0 = time.perf_counter(); X, keep, nk = ctx.triangulate(p["K"], p["Pl"], p["Pr"], p["ptsL"], p["ptsR"]); e2e_s = time.perf_counter() - t0
     from oracle import cv2_reference as ref
     cv2.setNumThreads(os.cpu_count() or 1)
