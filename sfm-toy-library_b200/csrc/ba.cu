@@ -1047,15 +1047,23 @@ __device__ __forceinline__ void peer_signal(const PeerTable& t, int slot, int my
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.flags[threadIdx.x] + slot * MAX_PEERS + my_rank), "l"(epoch) : "memory");
     }
 }
-__device__ __forceinline__ void peer_wait(const unsigned long long* my_flags, int slot, int nranks, unsigned long long epoch) {
-    if ((int)threadIdx.x < nranks) { while (ld_flag(my_flags + slot * MAX_PEERS + threadIdx.x) < epoch) __nanosleep(64); }
+// Bounded: a peer that never arrives (a rank died) must not hang the GPU -- after ~20 s the wait gives up and raises the
+// dense-solve failure counter, which makes the LM loop reject the step and terminate with FAILURE.
+__device__ __forceinline__ void peer_wait(const unsigned long long* my_flags, int slot, int nranks, unsigned long long epoch, int* fail) {
+    if ((int)threadIdx.x < nranks) {
+        const long long t0 = clock64();
+        while (ld_flag(my_flags + slot * MAX_PEERS + threadIdx.x) < epoch) {
+            __nanosleep(64);
+            if (clock64() - t0 > 40000000000LL) { if (fail && blockIdx.x == 0) atomicAdd(fail, 1000); break; }
+        }
+    }
     __syncthreads();
     __threadfence_system();
 }
 __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerTable t, size_t offset, int my_rank, int nranks, unsigned long long epoch,
-                                                          size_t n_sum, size_t n_max, double* __restrict__ out) {
+                                                          size_t n_sum, size_t n_max, double* __restrict__ out, int* __restrict__ fail) {
     peer_signal(t, 0, my_rank, nranks, epoch);
-    peer_wait(t.flags[my_rank], 0, nranks, epoch);
+    peer_wait(t.flags[my_rank], 0, nranks, epoch, fail);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sum + n_max; i += (size_t)gridDim.x * blockDim.x) {
         double acc = __ldcv(t.buf[0] + offset + i);
         for (int r = 1; r < nranks; ++r) { const double v = __ldcv(t.buf[r] + offset + i); acc = i < n_sum ? acc + v : fmax(acc, v); }
@@ -1214,7 +1222,7 @@ static int ba_allreduce(sfmb200_ba_problem* P, double* buf, size_t n_sum, size_t
     const size_t offset = buf - (double*)P->xmem, n = n_sum + n_max;
     const unsigned long long e = ++P->epoch;
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 4));
-    peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n_sum, n_max, P->xtmp + offset); SFM_LAUNCH_CHECK(ctx);
+    peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(P->ptab, offset, ctx->rank, ctx->nranks, e, n_sum, n_max, P->xtmp + offset, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
 
@@ -1224,7 +1232,7 @@ static int ba_allreduce(sfmb200_ba_problem* P, double* buf, size_t n_sum, size_t
 static int ba_peer_barrier(sfmb200_ba_problem* P) {
     sfmb200_ctx* ctx = P->ctx;
     if (ctx->nranks <= 1 || !P->peers) return SFMB200_OK;
-    peer_reduce_kernel<<<1, 256, 0, ctx->stream>>>(P->ptab, 0, ctx->rank, ctx->nranks, ++P->epoch, 0, 0, P->xtmp); SFM_LAUNCH_CHECK(ctx);
+    peer_reduce_kernel<<<1, 256, 0, ctx->stream>>>(P->ptab, 0, ctx->rank, ctx->nranks, ++P->epoch, 0, 0, P->xtmp, P->fail + 1); SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
 
