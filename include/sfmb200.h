@@ -146,6 +146,12 @@ typedef struct {
 
 void sfmb200_ba_default_options(sfmb200_ba_options* opt);
 
+/* Host-only check of a flattened problem: CSR offsets monotone from 0 to nobs, cameras in [0, nc) and strictly ascending
+ * inside a point (the std::map order of reference :146), at most 255 views per point.  sfmb200_ba_problem_create /
+ * sfmb200_ba_solve run the same check; exported so that a host can validate without a device.  0 = valid; otherwise
+ * SFMB200_ERR_INVALID / _UNSUPPORTED with the reason in `message`. */
+int sfmb200_ba_validate(int nc, int np, int nobs, const int32_t* obs_cam, const int32_t* pt_off, char* message, int message_len);
+
 /*
  * Flattened adjustBundle problem (the layout the reference builds at :111-166):
  *   cams6 [nc*6]  angle-axis(3) + translation(3) per camera, world->camera (:123-134)

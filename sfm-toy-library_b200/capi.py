@@ -205,6 +205,16 @@ def ba_default_options(**kw):
     return o
 
 
+def ba_validate(nc, obs_cam, pt_off):
+    """sfmb200_ba_validate: host-only check of a flattened problem.  Returns (status, message); status 0 = valid."""
+    obs_cam = np.ascontiguousarray(obs_cam, np.int32); pt_off = np.ascontiguousarray(pt_off, np.int32)
+    msg = C.create_string_buffer(200)
+    f = lib().sfmb200_ba_validate
+    f.restype = C.c_int
+    rc = f(C.c_int(int(nc)), C.c_int(max(0, pt_off.shape[0] - 1)), C.c_int(obs_cam.shape[0]), _p(obs_cam, C.c_int32), _p(pt_off, C.c_int32), msg, C.c_int(200))
+    return int(rc), msg.value.decode()
+
+
 def rotmat_to_angle_axis_f32(R):
     R = np.ascontiguousarray(R, np.float32).reshape(9); aa = np.empty(3, np.float32)
     lib().sfmb200_rotmat_to_angle_axis_f32(_p(R, C.c_float), _p(aa, C.c_float))

@@ -68,3 +68,62 @@ def test_flatten_bundle_follows_reference_assembly_order(L):
     np.testing.assert_array_equal(obs_xy[0], feats[0].points[2] - np.float32([512, 384]))
     np.testing.assert_array_equal(obs_xy[1], feats[3].points[1] - np.float32([512, 384]))
     assert cams.shape == (3, 6) and np.all(cams == 0)
+
+
+def _naive_validate(nc, obs_cam, pt_off):
+    """The obvious nested loop (what the library's slow path and the previous implementation do)."""
+    np_, nobs = len(pt_off) - 1, len(obs_cam)
+    if np_ == 0:
+        return nobs == 0
+    if pt_off[0] != 0 or pt_off[np_] != nobs:
+        return False
+    for p in range(np_):
+        if pt_off[p + 1] < pt_off[p] or pt_off[p + 1] > nobs:
+            return False
+        for o in range(pt_off[p], pt_off[p + 1]):
+            if obs_cam[o] < 0 or obs_cam[o] >= nc:
+                return False
+            if o > pt_off[p] and obs_cam[o] <= obs_cam[o - 1]:
+                return False
+    return True
+
+
+def test_ba_validate_accepts_and_rejects_like_the_nested_loop(L):
+    """sfmb200_ba_validate (two flat sweeps + descent counting) against the nested loop on valid problems and on every kind of
+    corruption: camera out of range / negative, equal or descending cameras inside a point, legal descents at point boundaries,
+    empty points, offsets not starting at 0 / not ending at nobs / decreasing / beyond nobs."""
+    rs = np.random.RandomState(4)
+    p = synth.make_ba_problem(n_cams=9, n_pts=300, obs_per_pt=4, seed=2)
+    cam, off = p["obs_cam"].copy(), p["pt_off"].copy()
+    assert capi.ba_validate(9, cam, off)[0] == 0
+    # ragged with empty points
+    ks = rs.randint(0, 5, 200); off2 = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+    cam2 = np.concatenate([np.sort(rs.choice(9, k, replace=False)) for k in ks] + [np.empty(0, int)]).astype(np.int32)
+    assert _naive_validate(9, cam2, off2) and capi.ba_validate(9, cam2, off2)[0] == 0
+    n_bad = 0
+    for trial in range(300):
+        c, o = cam2.copy(), off2.copy()
+        kind = trial % 6
+        if kind == 0:
+            c[rs.randint(len(c))] = rs.choice([-1, 9, 1000, -2 ** 31])
+        elif kind == 1:                                     # duplicate or swap two neighbours somewhere
+            i = rs.randint(1, len(c)); c[i] = c[i - 1]
+        elif kind == 2:
+            i = rs.randint(1, len(c)); c[i - 1], c[i] = c[i], c[i - 1]
+        elif kind == 3:
+            o[rs.randint(1, len(o) - 1)] += rs.choice([-3, 3])
+        elif kind == 4:
+            o[-1] += rs.choice([-1, 1])
+        else:
+            o[0] = 1
+        want = _naive_validate(9, c, o)
+        rc, msg = capi.ba_validate(9, c, o)
+        assert (rc == 0) == want, (kind, msg)
+        n_bad += not want
+        if not want:
+            assert msg
+    assert n_bad > 150
+    assert capi.ba_validate(5, np.empty(0, np.int32), np.zeros(1, np.int32))[0] == 0           # no points, no observations
+    assert capi.ba_validate(5, np.zeros(3, np.int32), np.zeros(1, np.int32))[0] != 0           # observations without points
+    rc, msg = capi.ba_validate(300, np.arange(256, dtype=np.int32), np.array([0, 256], np.int32))
+    assert rc != 0 and "255" in msg                                                              # more views per point than supported
