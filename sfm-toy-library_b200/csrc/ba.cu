@@ -1086,7 +1086,7 @@ struct sfmb200_ba_problem {
     // observations
     float2* obs_xy; int32_t* obs_cam; int32_t* pt_off; int32_t* cm_off; float2* cm_xy; int32_t* cm_pt;
     // state: x = (cf, pts), candidate, initial
-    double* cf[2]; double* pts[2]; double* cf0; double* pts0; int cur = 0;
+    double* cf[2]; double* pts[2]; double* cf0; double* pts0; int cur = 0; double focal0 = 0;
     CamDerived* camd[2];
     double* scale_cf; double* scale_pt; double* ptblk;
     // reduced system buffer (one all-reduce): Sblk | Scf | Sff | rhs | gcf | dcf | sums[8]
@@ -1357,9 +1357,8 @@ static int ba_validate_csr(int nc, int np, int nobs, const int32_t* obs_cam, con
         if (k > 0 && a > 0 && a < nobs) boundary_descents += obs_cam[a] <= obs_cam[a - 1];
     }
     if (!neg) {
-        unsigned out_of_range = 0; long long descents = 0;
-        for (int o = 0; o < nobs; ++o) out_of_range |= (unsigned)obs_cam[o] >= (unsigned)nc;
-        for (int o = 1; o < nobs; ++o) descents += obs_cam[o] <= obs_cam[o - 1];
+        unsigned out_of_range = nobs ? (unsigned)obs_cam[0] >= (unsigned)nc : 0u; long long descents = 0;
+        for (int o = 1; o < nobs; ++o) { out_of_range |= (unsigned)obs_cam[o] >= (unsigned)nc; descents += obs_cam[o] <= obs_cam[o - 1]; }
         if (!out_of_range && descents == boundary_descents) {
             if (maxk_out) *maxk_out = maxk;
             if (pairs_out) *pairs_out = pairs;
@@ -1400,20 +1399,13 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     if (!ctx || !out || nc < 0 || np < 0 || nobs < 0) return SFMB200_ERR_INVALID;
     *out = nullptr;
     if ((nc && !cams6) || (np && (!pts3 || !pt_off)) || (nobs && (!obs_xy || !obs_cam))) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "null buffer");
-    // validate the CSR: offsets monotone, cameras in range and strictly ascending within a point (std::map order, :146)
+    // (the CSR is validated below, on the host, while the uploads are in flight)
     int maxk = 0; long long pair_entries = 0;
-    {
-        char msg[160];
-        if (ba_validate_csr(nc, np, nobs, obs_cam, pt_off, &maxk, &pair_entries, msg, sizeof msg) != SFMB200_OK) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "%s", msg);
-    }
-    if (maxk > 255) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "a point is observed by %d views; at most 255 supported", maxk);
 
     std::lock_guard<std::mutex> lk(ctx->mu);
     SFM_CUDA(ctx, cudaSetDevice(ctx->device));
     sfmb200_ba_problem* P = new sfmb200_ba_problem();
-    P->ctx = ctx; P->nc = nc; P->np = np; P->nobs = nobs; P->maxk = std::max(maxk, 1);
-    P->G = maxk <= 4 ? 4 : maxk <= 8 ? 8 : maxk <= 16 ? 16 : 32;
-    if (point_smem_bytes(P->G, P->maxk) > 200 * 1024) { delete P; return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "observations per point (%d) exceed the shared-memory budget", maxk); }
+    P->ctx = ctx; P->nc = nc; P->np = np; P->nobs = nobs;
     P->n = 6 * nc + 1; P->npad = ((P->n + 1) + NB - 1) / NB * NB;
     const size_t nblk = (size_t)nc * (nc + 1) / 2, n = P->n;
     P->red_n = 36 * nblk + 6 * (size_t)nc + 1 + 3 * n + 8;
@@ -1466,8 +1458,20 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     if (nobs) { CRT(cudaMemcpyAsync(P->obs_xy, obs_xy, 8 * (size_t)nobs, cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->obs_cam, obs_cam, 4 * (size_t)nobs, cudaMemcpyHostToDevice, st)); }
     if (np) { CRT(cudaMemcpyAsync(P->pt_off, pt_off, 4 * (size_t)(np + 1), cudaMemcpyHostToDevice, st)); CRT(cudaMemcpyAsync(P->pts0, pts3, 24 * (size_t)np, cudaMemcpyHostToDevice, st)); }
     if (nc) CRT(cudaMemcpyAsync(P->cf0, cams6, 48 * (size_t)nc, cudaMemcpyHostToDevice, st));
-    CRT(cudaMemcpyAsync(P->cf0 + 6 * nc, &focal, 8, cudaMemcpyHostToDevice, st));
-    CRT(cudaStreamSynchronize(st));     // `focal` is a stack variable
+    P->focal0 = focal;                  // the copy source must outlive this stack frame's uses: a member
+    CRT(cudaMemcpyAsync(P->cf0 + 6 * nc, &P->focal0, 8, cudaMemcpyHostToDevice, st));
+    {   // validate the CSR while the uploads run: offsets monotone, cameras in range and strictly ascending within a point
+        // (std::map order, :146).  Nothing that indexes by camera or offset is launched before this passes.
+        char msg[160]; msg[0] = 0;
+        int vrc = ba_validate_csr(nc, np, nobs, obs_cam, pt_off, &maxk, &pair_entries, msg, sizeof msg);
+        if (vrc == SFMB200_OK && maxk > 255) { snprintf(msg, sizeof msg, "a point is observed by %d views; at most 255 supported", maxk); vrc = SFMB200_ERR_UNSUPPORTED; }
+        if (vrc == SFMB200_OK) {
+            P->maxk = std::max(maxk, 1);
+            P->G = maxk <= 4 ? 4 : maxk <= 8 ? 8 : maxk <= 16 ? 16 : 32;
+            if (point_smem_bytes(P->G, P->maxk) > 200 * 1024) { snprintf(msg, sizeof msg, "observations per point (%d) exceed the shared-memory budget", maxk); vrc = SFMB200_ERR_UNSUPPORTED; }
+        }
+        if (vrc != SFMB200_OK) { cudaStreamSynchronize(st); ba_release_buffers(P); delete P; return sfmb200_fail(ctx, vrc, "%s", msg); }
+    }
     // camera-major copy (device counting sort)
     CRT(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * (nc + 1), st));
     {   // dataflow Cholesky: ready flags start at epoch 0; the grid must stay within the co-resident CTA count
