@@ -9,16 +9,21 @@
 //   * The Jacobian is never materialised.  Every pass re-evaluates the closed-form 2x(6+3+1) blocks from 8-byte
 //     observations (ba_math.cuh) -- HBM traffic per LM iteration is the observation list + the point/camera state.
 //   * ba_point_kernel   (K3a, point-major, one sub-warp group per 3D point): U_p = sum Jp^T Jp + D_p^2, its Cholesky
-//     inverse M_p, g_p, and the OFF-diagonal blocks  S[ci,cj] -= Z_i Z_j^T  (Z = Jc^T Jp M^T) of the reduced camera
-//     system, accumulated with fp64 reductions (red.global.add.f64) into a block-major upper-triangular S.
+//     inverse M_p, g_p, and per observation Z_o = Jc^T Jp M^T (Zbuf).
+//   * ba_pair_kernel    (K3c): the OFF-diagonal blocks  S[ci,cj] -= sum Z_i Z_j^T  over per-camera-pair entry lists built
+//     once per problem, one mma.sync.m8n8k4.f64 per entry, no atomics in the loop ("red" mode keeps the per-point
+//     red.global.add.f64 formulation for comparison).
 //   * ba_camera_kernel  (K3b, camera-major): everything that would be same-address contention -- the diagonal blocks,
-//     the camera-focal column, rhs and gradient -- is accumulated in registers over one camera's observation list and
-//     reduced once per CTA (the shared focal block makes every observation touch S[:,focal]).
-//   * reduced system summed over ranks with ONE NCCL all-reduce (S, rhs, gradient, diag, cost in one buffer).
-//   * ba_assemble + blocked Cholesky (right-looking, 32x32 tiles in shared memory, rhs carried as an extra row so the
-//     forward substitution is free) + back substitution: K4.
-//   * ba_backsub_eval_kernel (point-major): delta_p, candidate point, model cost change and candidate cost fused.
-//   LM control runs on the host from ~20 doubles read back once per iteration.
+//     the camera-focal column, rhs and gradient -- is accumulated in registers over the camera-sorted observation list and
+//     reduced once per (CTA, camera) (the shared focal block makes every observation touch S[:,focal]).
+//   * reduced system summed over ranks: peer-memory kernel (loads the peers' buffers over NVLink into a local summed copy)
+//     or one NCCL all-reduce (S, rhs, gradient, diag, cost in one buffer).
+//   * ba_assemble + chol.cuh (streaming dataflow tile Cholesky, rhs carried as an extra row so the forward substitution is
+//     free, staged back substitution with inverse diagonal tiles): K4.
+//   * ba_backsub_z_kernel (point-major): delta_p from the stored Z blocks, candidate point, model cost change and candidate
+//     cost fused, no Jacobian re-evaluation.
+//   LM control runs on the DEVICE (LMState, ba_lm_control_kernel); the host enqueues chunks of iterations and reads the
+//   state back once per chunk.
 #include "common.cuh"
 #include "ba_math.cuh"
 #include "chol.cuh"
