@@ -51,9 +51,14 @@ int64_t sfmb200_kernel_launches(const sfmb200_ctx* ctx);    /* number of kernels
  * matchFeatures (SfM2DFeatureUtilities.cpp:53-71): for every query row the 2 nearest train rows by Hamming
  * distance (ties -> lower train index), keep the best iff (double)d0 < ratio * (double)d1, ascending queryIdx.
  * Pass ratio = (double)0.8f to reproduce NN_MATCH_RATIO (SfM2DFeatureUtilities.cpp:35).
- * q [nq*desc_bytes], t [nt*desc_bytes] row-major bytes (ORB: desc_bytes = 32); desc_bytes % 4 == 0.
+ * q [nq*desc_bytes], t [nt*desc_bytes] row-major PACKED bytes (ORB: desc_bytes = 32); 1 <= desc_bytes <= 128.  The kernels are
+ * instantiated for 16/32/64/128 bytes; any other width is zero-padded to the next one (every distance unchanged).
+ * 32-byte descriptors run on the tcgen05 tensor-core kernel, the other widths on the XOR/POPC kernel.
  * out_q/out_t/out_d must hold nq entries; *out_n receives the number of survivors (imgIdx is always 0).
  * nt < 2 (undefined behaviour in the reference) yields *out_n = 0.
+ * The reference calls this once per image pair with the same images again and again (SfM.cpp:166-206): uploaded images
+ * stay resident in a context-owned arena keyed by (host pointer, rows, width, 64-bit content hash), so a repeated image costs
+ * neither an upload nor an expansion.  SFMB200_MATCH_CACHE=0 disables the arena.  Safe to call from several host threads.
  */
 int sfmb200_match_knn2_ratio(sfmb200_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int desc_bytes,
                              double ratio, int32_t* out_q, int32_t* out_t, float* out_d, int* out_n);
@@ -76,7 +81,9 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
                         int32_t* out_q, int32_t* out_t, float* out_d, int64_t* out_off, int32_t* out_cnt);
 /* same, results stay on the device (the benchmark's resident-input timing): d_* are DEVICE pointers, pairs is host.
  * Survivors of all pairs are written DENSELY (pair-major, ascending queryIdx) to d_out_*[0 .. *d_total);
- * d_pair_start [n_pairs] = dense position of each pair's first survivor.  Nothing is synchronised. */
+ * d_pair_start [n_pairs] = dense position of each pair's first survivor (0 for a pair without query rows).  Nothing is
+ * synchronised.  n_pairs == 0 or no query rows at all: *d_total = 0.  *d_total = -1 reports a tensor-core pipeline failure
+ * (an MMA completion barrier timed out) -- the outputs are then undefined. */
 int sfmb200_match_pairs_device(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, double ratio,
                                int32_t* d_out_q, int32_t* d_out_t, float* d_out_d, int32_t* d_pair_start, int64_t* d_total);
 

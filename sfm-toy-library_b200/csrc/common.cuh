@@ -63,6 +63,19 @@ struct BAWorkspace {
     void release() { mem.release(); gmem.release(); xbuf.release(); hpin.release(); }
 };
 
+// Descriptor images kept resident between per-call matchFeatures invocations (match.cu): one arena of packed rows, one of
+// expanded tcgen05 operand blocks, bump-allocated, flushed whole when full.
+struct MatchCacheEntry { const void* host; int rows; int desc_bytes; uint64_t hash; int row0; int blk0; };
+struct MatchCache {
+    DevBuf desc, exp;
+    int width = 0;                       // padded descriptor width (bytes) of the rows in the arena
+    int64_t rows_cap = 0, rows_used = 0;
+    int blk_cap = 0, blk_used = 0;
+    std::vector<MatchCacheEntry> entries;
+    int64_t hits = 0, misses = 0;
+    void release() { desc.release(); exp.release(); entries.clear(); rows_cap = rows_used = 0; blk_cap = blk_used = 0; }
+};
+
 struct sfmb200_ctx {
     int device = 0;
     int sm_count = 0;
@@ -74,6 +87,8 @@ struct sfmb200_ctx {
     DevBuf scratch2;            // per-call device scratch (stage outputs)
     PinBuf pinned;              // per-call pinned staging (results read-back)
     BAWorkspace ba_ws;          // cached bundle-adjustment workspace
+    MatchCache mcache;          // descriptor images resident between per-call matchFeatures invocations
+    bool tc_attr_set = false;   // cudaFuncSetAttribute(knn2_hamming_tc_kernel, max dynamic smem) done for THIS device
     CommState* comm = nullptr;
     int rank = 0, nranks = 1;
 };

@@ -44,7 +44,7 @@ void sfmb200_destroy(sfmb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     sfmb200_comm_destroy(ctx);
-    ctx->scratch.release(); ctx->scratch2.release(); ctx->pinned.release(); ctx->ba_ws.release();
+    ctx->scratch.release(); ctx->scratch2.release(); ctx->pinned.release(); ctx->ba_ws.release(); ctx->mcache.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

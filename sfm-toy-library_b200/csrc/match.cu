@@ -165,7 +165,8 @@ merge_flag_scan_kernel(const int4* __restrict__ partial, int splits, int64_t row
 }
 
 // in-place exclusive scan of block_sums[n] (single CTA, chained over chunks); total -> *grand_total
-__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t* __restrict__ sums, int n, int64_t* __restrict__ grand_total) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t* __restrict__ sums, int n, int64_t* __restrict__ grand_total,
+                                                                 const int* __restrict__ error_flag /* may be null */) {
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -180,7 +181,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t* __rest
         if (threadIdx.x == 0) carry_s = carry + total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *grand_total = carry_s;
+    // a tcgen05 pipeline error (bounded mbarrier wait expired) poisons the total: device-resident callers see -1
+    if (threadIdx.x == 0) *grand_total = (error_flag && *error_flag) ? -1 : carry_s;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -255,12 +257,16 @@ static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d
     if (!use_tc) SFM_LAUNCH_CHECK(ctx);
     merge_flag_scan_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_partial, splits, rows, ratio, 0, d_best_t, d_best_d, d_rank, d_flag, d_bsum);
     SFM_LAUNCH_CHECK(ctx);
-    scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_bsum, nblk, d_total);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_bsum, nblk, d_total, use_tc ? d_err : nullptr);
     SFM_LAUNCH_CHECK(ctx);
     scatter_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_pairs, n_pairs, rows, d_best_t, d_best_d, d_rank, d_flag, d_bsum, d_out_q, d_out_t, d_out_d, d_pair_start);
     SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
+
+static int match_pairs_host_out(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d_exp, int words, const std::vector<PairDesc>& hp,
+                                int64_t rows, int nq_max, int nt_max, double ratio,
+                                int32_t* out_q, int32_t* out_t, float* out_d, int64_t* out_off, int32_t* out_cnt);
 
 static int build_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, std::vector<PairDesc>& hp,
                        int64_t& rows, int& nq_max, int& nt_max) {
@@ -277,12 +283,25 @@ static int build_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32
     return SFMB200_OK;
 }
 
+static int supported_width(int desc_bytes) {      // the kernels are instantiated for 16/32/64/128 bytes; zero padding keeps every distance
+    for (int w : {16, 32, 64, 128}) if (desc_bytes <= w) return w;
+    return 0;
+}
+
 extern "C" {
 
 int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc, const int32_t* img_off, int n_img, int desc_bytes, sfmb200_descset** out) {
     if (!ctx || !out || !img_off || n_img < 0) return SFMB200_ERR_INVALID;
     *out = nullptr;
-    if (desc_bytes <= 0 || desc_bytes % 16) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "desc_bytes must be a multiple of 16 (got %d)", desc_bytes);
+    const int width = supported_width(desc_bytes);
+    if (desc_bytes <= 0 || !width) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "desc_bytes must be in [1, 128] (got %d)", desc_bytes);
+    std::vector<uint8_t> padded;                  // widths other than 16/32/64/128 are zero-padded (distances unchanged)
+    if (width != desc_bytes && img_off[n_img] > 0) {
+        padded.assign((size_t)img_off[n_img] * width, 0);
+        for (int64_t r = 0; r < img_off[n_img]; ++r) memcpy(padded.data() + (size_t)r * width, desc + (size_t)r * desc_bytes, desc_bytes);
+        desc = padded.data();
+    }
+    desc_bytes = width;
     std::lock_guard<std::mutex> lk(ctx->mu);
     SFM_CUDA(ctx, cudaSetDevice(ctx->device));
     sfmb200_descset* s = new sfmb200_descset();
@@ -338,11 +357,13 @@ int sfmb200_match_pairs_device(sfmb200_ctx* ctx, const sfmb200_descset* set, con
     if (!ctx || !set || (n_pairs > 0 && !pairs) || !d_pair_start || !d_total) return SFMB200_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SFM_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(int64_t), ctx->stream));
     if (n_pairs == 0) return SFMB200_OK;
+    SFM_CUDA(ctx, cudaMemsetAsync(d_pair_start, 0, sizeof(int32_t) * n_pairs, ctx->stream));   // pairs without query rows keep 0
     std::vector<PairDesc> hp; int64_t rows; int nq_max, nt_max;
     int rc = build_pairs(ctx, set, pairs, n_pairs, hp, rows, nq_max, nt_max);
     if (rc) return rc;
-    if (rows == 0) return SFMB200_OK;
+    if (rows == 0 || nt_max < 2) return SFMB200_OK;
     return match_core(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, d_out_q, d_out_t, d_out_d, d_pair_start, d_total, ctx->scratch);
 }
 
@@ -354,6 +375,17 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     std::vector<PairDesc> hp; int64_t rows; int nq_max, nt_max;
     int rc = build_pairs(ctx, set, pairs, n_pairs, hp, rows, nq_max, nt_max);
     if (rc) return rc;
+    return match_pairs_host_out(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, out_q, out_t, out_d, out_off, out_cnt);
+}
+
+}  // extern "C"
+
+// pairs described on the host, descriptors resident: run the kernels, read back only the survivors.  ctx->mu is held.
+static int match_pairs_host_out(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d_exp, int words, const std::vector<PairDesc>& hp,
+                                int64_t rows, int nq_max, int nt_max, double ratio,
+                                int32_t* out_q, int32_t* out_t, float* out_d, int64_t* out_off, int32_t* out_cnt) {
+    const int n_pairs = (int)hp.size();
+    int rc;
     for (int p = 0; p < n_pairs; ++p) { out_off[p] = hp[p].out_row; out_cnt[p] = 0; }
     if (n_pairs) out_off[n_pairs] = rows;
     if (rows == 0) return SFMB200_OK;
@@ -367,7 +399,7 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     int32_t* d_q = cv.take<int32_t>(rows); int32_t* d_t = cv.take<int32_t>(rows); float* d_d = cv.take<float>(rows);
     int32_t* d_start = cv.take<int32_t>(n_pairs + 1); int64_t* d_total = cv.take<int64_t>(1);
     int* d_tc_err = nullptr;
-    rc = match_core(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb, &d_tc_err);
+    rc = match_core(ctx, d_desc, d_exp, words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb, &d_tc_err);
     if (rc) return rc;
     // read back: pair starts + total, then only the survivors
     // (pinned staging is sized for the SURVIVORS, known after the first small read-back -- not for all query rows)
@@ -409,25 +441,110 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     return SFMB200_OK;
 }
 
+// ---- per-call path (what the reference-side shim binds: matchFeatures(const Features&, const Features&)) ------------------
+// runSfM() matches every image against every other one (SfM.cpp:166-206), so the per-call entry point sees each image
+// N-1 times.  Uploaded (and, for 32-byte descriptors, expanded) images are therefore kept in a context-owned arena keyed
+// by (host pointer, rows, width, 64-bit content hash): a pair whose two images are resident costs no cudaMalloc, no
+// upload and no expansion.  A hash mismatch (the caller reused a buffer) is a miss; a full arena is flushed whole.
+static uint64_t content_hash(const uint8_t* p, size_t n) {
+    uint64_t h0 = 0x9E3779B97F4A7C15ull, h1 = 0xC2B2AE3D27D4EB4Full, h2 = 0x165667B19E3779F9ull, h3 = 0x27D4EB2F165667C5ull;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t a, b, c, d;
+        memcpy(&a, p + i, 8); memcpy(&b, p + i + 8, 8); memcpy(&c, p + i + 16, 8); memcpy(&d, p + i + 24, 8);
+        h0 = (h0 ^ a) * 0x100000001B3ull; h0 ^= h0 >> 29;
+        h1 = (h1 ^ b) * 0x100000001B3ull; h1 ^= h1 >> 31;
+        h2 = (h2 ^ c) * 0x100000001B3ull; h2 ^= h2 >> 27;
+        h3 = (h3 ^ d) * 0x100000001B3ull; h3 ^= h3 >> 33;
+    }
+    for (; i < n; ++i) { h0 = (h0 ^ p[i]) * 0x100000001B3ull; }
+    return h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7) ^ (uint64_t)n;
+}
+
+// make `img` (rows x desc_bytes host bytes) resident; returns its first row / first expanded block in the arena
+static int cache_acquire(sfmb200_ctx* ctx, const uint8_t* img, int rows, int desc_bytes, int width, uint64_t hash, int& row0, int& blk0) {
+    MatchCache& mc = ctx->mcache;
+    for (const MatchCacheEntry& e : mc.entries)
+        if (e.host == img && e.rows == rows && e.desc_bytes == desc_bytes && e.hash == hash) { row0 = e.row0; blk0 = e.blk0; mc.hits++; return SFMB200_OK; }
+    mc.misses++;
+    const int br = match_tc_block_rows();
+    const int nblk = width == 32 ? ceil_div(rows, br) : 0;
+    row0 = (int)mc.rows_used; blk0 = mc.blk_used;
+    const size_t bytes = (size_t)rows * width;
+    if (width == desc_bytes) {
+        SFM_CUDA(ctx, cudaMemcpyAsync((char*)mc.desc.p + (size_t)row0 * width, img, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        std::vector<uint8_t> padded(bytes, 0);
+        for (int r = 0; r < rows; ++r) memcpy(padded.data() + (size_t)r * width, img + (size_t)r * desc_bytes, desc_bytes);
+        SFM_CUDA(ctx, cudaMemcpyAsync((char*)mc.desc.p + (size_t)row0 * width, padded.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+        SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // `padded` dies with this scope
+    }
+    if (nblk) {
+        std::vector<int2> blocks(nblk);
+        for (int b = 0; b < nblk; ++b) blocks[b] = make_int2(row0 + b * br, std::min(br, rows - b * br));
+        SFM_CUDA(ctx, ctx->scratch.reserve(sizeof(int2) * nblk + 256));
+        SFM_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, blocks.data(), sizeof(int2) * nblk, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = match_tc_expand(ctx, (const uint32_t*)mc.desc.p, (const int2*)ctx->scratch.p, nblk, (uint8_t*)mc.exp.p + (size_t)blk0 * match_tc_block_bytes());
+        if (rc) return rc;
+    }
+    mc.rows_used += rows; mc.blk_used += nblk;
+    mc.entries.push_back({img, rows, desc_bytes, hash, row0, blk0});
+    return SFMB200_OK;
+}
+
+extern "C" {
+
 int sfmb200_match_knn2_ratio(sfmb200_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int desc_bytes,
                              double ratio, int32_t* out_q, int32_t* out_t, float* out_d, int* out_n) {
     if (!ctx || !out_n || nq < 0 || nt < 0) return SFMB200_ERR_INVALID;
     *out_n = 0;
     if (nq == 0 || nt < 2) return SFMB200_OK;     // nt < 2: undefined behaviour in the reference (:65) -> empty
     if (!q || !t || !out_q || !out_t || !out_d) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "null buffer");
-    // a two-image descriptor set; the per-call upload is part of the drop-in cost (the reference passes cv::Mat by ref)
-    std::vector<uint8_t> both((size_t)(nq + nt) * desc_bytes);
-    memcpy(both.data(), q, (size_t)nq * desc_bytes);
-    memcpy(both.data() + (size_t)nq * desc_bytes, t, (size_t)nt * desc_bytes);
-    const int32_t off[3] = {0, nq, nq + nt};
-    sfmb200_descset* set = nullptr;
-    int rc = sfmb200_descset_create(ctx, both.data(), off, 2, desc_bytes, &set);
+    const int width = supported_width(desc_bytes);
+    if (desc_bytes <= 0 || !width) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "desc_bytes must be in [1, 128] (got %d)", desc_bytes);
+    const uint64_t hq = content_hash(q, (size_t)nq * desc_bytes), ht = content_hash(t, (size_t)nt * desc_bytes);   // outside the lock
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MatchCache& mc = ctx->mcache;
+    const char* env = getenv("SFMB200_MATCH_CACHE");
+    const bool keep = !(env && env[0] == '0');
+    const int br = match_tc_block_rows();
+    if (mc.width != width || !keep) { mc.entries.clear(); mc.rows_used = 0; mc.blk_used = 0; mc.width = width; }
+    auto resident = [&](const uint8_t* p, int rows, uint64_t h) {
+        for (const MatchCacheEntry& e : mc.entries) if (e.host == p && e.rows == rows && e.desc_bytes == desc_bytes && e.hash == h) return true;
+        return false;
+    };
+    int64_t need_rows = 0; int need_blk = 0;
+    if (!resident(q, nq, hq)) { need_rows += nq; need_blk += ceil_div(nq, br); }
+    if (!resident(t, nt, ht) && !(t == q && nt == nq && ht == hq)) { need_rows += nt; need_blk += ceil_div(nt, br); }
+    if (width != 32) need_blk = 0;
+    if (mc.rows_used + need_rows > mc.rows_cap || mc.blk_used + need_blk > mc.blk_cap) {
+        // flush everything (simple and predictable), then grow if the pair alone does not fit
+        mc.entries.clear(); mc.rows_used = 0; mc.blk_used = 0;
+        need_rows = (int64_t)nq + nt; need_blk = width == 32 ? ceil_div(nq, br) + ceil_div(nt, br) : 0;
+        const int64_t want_rows = std::max<int64_t>(need_rows, 16 * 8192);          // room for >= 16 images of 8 k features
+        if (need_rows > mc.rows_cap || (size_t)mc.rows_cap * width > mc.desc.cap) {
+            SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            SFM_CUDA(ctx, mc.desc.reserve((size_t)want_rows * width + 16));
+            mc.rows_cap = want_rows;
+        }
+        const int want_blk = width == 32 ? std::max<int>(need_blk, (int)(want_rows / br) + 32) : 0;
+        if (want_blk > mc.blk_cap) {
+            SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            SFM_CUDA(ctx, mc.exp.reserve((size_t)want_blk * match_tc_block_bytes()));
+            mc.blk_cap = want_blk;
+        }
+    }
+    PairDesc pd; pd.out_row = 0; pd.nq = nq; pd.nt = nt;
+    int rc = cache_acquire(ctx, q, nq, desc_bytes, width, hq, pd.q_row, pd.q_blk);
     if (rc) return rc;
-    const int32_t pair[2] = {0, 1};
+    rc = cache_acquire(ctx, t, nt, desc_bytes, width, ht, pd.t_row, pd.t_blk);
+    if (rc) return rc;
+    std::vector<PairDesc> hp(1, pd);
     int64_t ooff[2]; int32_t cnt[1];
-    rc = sfmb200_match_pairs(ctx, set, pair, 1, ratio, out_q, out_t, out_d, ooff, cnt);
-    sfmb200_descset_destroy(set);
-    if (rc) return rc;
+    rc = match_pairs_host_out(ctx, (const uint32_t*)mc.desc.p, width == 32 ? (const uint8_t*)mc.exp.p : nullptr, width / 4, hp, nq, nq, nt, ratio,
+                              out_q, out_t, out_d, ooff, cnt);
+    if (rc) { mc.entries.clear(); mc.rows_used = 0; mc.blk_used = 0; return rc; }
     *out_n = cnt[0];
     return SFMB200_OK;
 }
@@ -463,7 +580,7 @@ int sfmb200_match_knn2_ratio_l2(sfmb200_ctx* ctx, const float* q, int nq, const 
     SFM_LAUNCH_CHECK(ctx);
     merge_flag_scan_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>((const int4*)d_partial, splits, rows, ratio, 1, d_best_t, d_best_d, d_rank, d_flag, d_bsum);
     SFM_LAUNCH_CHECK(ctx);
-    scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_bsum, nblk, d_total);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_bsum, nblk, d_total, nullptr);
     SFM_LAUNCH_CHECK(ctx);
     scatter_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_pairs, 1, rows, d_best_t, d_best_d, d_rank, d_flag, d_bsum, d_q, d_t, d_d, d_start);
     SFM_LAUNCH_CHECK(ctx);

@@ -273,8 +273,8 @@ int match_tc_expand(sfmb200_ctx* ctx, const uint32_t* d_desc, const int2* d_bloc
 
 int match_tc_launch(sfmb200_ctx* ctx, const uint8_t* d_E, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
                     int4* d_partial, int* d_error_flag) {
-    static bool attr_set = false;
-    if (!attr_set) { SFM_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr_set = true; }
+    // the attribute is per device and the context is per device; ctx->mu is held by every caller
+    if (!ctx->tc_attr_set) { SFM_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); ctx->tc_attr_set = true; }
     const int qblocks = ceil_div(nq_max, TC_M);
     dim3 grid(qblocks * splits, n_pairs);
     knn2_hamming_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(d_E, d_pairs, qblocks, splits, d_partial, d_error_flag);

@@ -47,6 +47,7 @@ public:
     int type() const { return type_; }
     bool empty() const { return rows == 0 || cols == 0; }
     bool isContinuous() const { return true; }
+    Mat clone() const { Mat m(rows, cols, type_); if (data) std::memcpy(m.data, data, (size_t)rows * cols * elem(type_)); return m; }
     size_t elemSize() const { return elem(type_); }
     template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data)[(size_t)r * cols + c]; }
     template <typename T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data)[(size_t)r * cols + c]; }

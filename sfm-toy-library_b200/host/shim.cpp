@@ -51,8 +51,9 @@ const float kMaxReprojectionError = 10.0f;    // MIN_REPROJECTION_ERROR
 namespace sfmtoylib {
 
 Matching SfM2DFeatureUtilities::matchFeatures(const Features& featuresLeft, const Features& featuresRight) {
-    const cv::Mat& L = featuresLeft.descriptors;
-    const cv::Mat& R = featuresRight.descriptors;
+    // the ABI wants packed rows; a cv::Mat view (ROI, step > cols) is cloned first -- the reference accepts any cv::Mat
+    const cv::Mat L = featuresLeft.descriptors.isContinuous() ? featuresLeft.descriptors : featuresLeft.descriptors.clone();
+    const cv::Mat R = featuresRight.descriptors.isContinuous() ? featuresRight.descriptors : featuresRight.descriptors.clone();
     Matching out;
     if (L.rows == 0 || R.rows < 2) return out;
     const int bytes = (int)(L.cols * L.elemSize());
@@ -106,12 +107,19 @@ void SfMBundleAdjustmentUtils::adjustBundle(PointCloud& pointCloud, std::vector<
         if (dense[v] == 0) { dense[v] = (int)used.size(); used.push_back((int)v); }
     const int nc = (int)used.size(), np = (int)pointCloud.size();
     std::vector<double> cams(6 * (size_t)nc), pts(3 * (size_t)np);
-    for (int i = 0; i < nc; ++i) {
-        const Pose& pose = cameraPoses[used[i]];
+    // reference :113-135: every non-empty pose becomes a 6-vector (float angle-axis of R, widened); an empty pose
+    // (R diagonal exactly zero, :118-122) becomes CameraVector() = zeros and is never written back (:196-199)
+    auto isEmpty = [](const Pose& pose) { return pose(0, 0) == 0 && pose(1, 1) == 0 && pose(2, 2) == 0; };
+    auto toVector = [](const Pose& pose, double* v6) {
         float R[9], aa[3];
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[3 * r + c] = pose(r, c);
         sfmb200_rotmat_to_angle_axis_f32(R, aa);                       // float conversion, then widened
-        for (int k = 0; k < 3; ++k) { cams[6 * i + k] = aa[k]; cams[6 * i + 3 + k] = pose(k, 3); }
+        for (int k = 0; k < 3; ++k) { v6[k] = aa[k]; v6[3 + k] = pose(k, 3); }
+    };
+    for (int i = 0; i < nc; ++i) {
+        const Pose& pose = cameraPoses[used[i]];
+        if (isEmpty(pose)) continue;                                   // zeros, like CameraVector()
+        toVector(pose, &cams[6 * i]);
     }
     double focal = intrinsics.K.at<float>(0, 0);
     const float cx = intrinsics.K.at<float>(0, 2), cy = intrinsics.K.at<float>(1, 2);
@@ -142,11 +150,16 @@ void SfMBundleAdjustmentUtils::adjustBundle(PointCloud& pointCloud, std::vector<
     }
     intrinsics.K.at<float>(0, 0) = (float)focal;
     intrinsics.K.at<float>(1, 1) = (float)focal;
-    for (int i = 0; i < nc; ++i) {
-        Pose& pose = cameraPoses[used[i]];
-        double R[9];
-        sfmb200_angle_axis_to_rotmat(&cams[6 * i], R);
-        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) pose(r, c) = (float)R[3 * r + c]; pose(r, 3) = (float)cams[6 * i + 3 + r]; }
+    // reference :192-215: EVERY non-empty pose is rewritten from its 6-vector -- the observed ones from the optimised
+    // parameters, the unobserved ones from their own (never optimised) float angle-axis, i.e. a round trip
+    for (size_t v = 0; v < cameraPoses.size(); ++v) {
+        Pose& pose = cameraPoses[v];
+        if (isEmpty(pose)) continue;
+        double v6[6], R[9];
+        if (dense[v] >= 0) for (int k = 0; k < 6; ++k) v6[k] = cams[6 * (size_t)dense[v] + k];
+        else toVector(pose, v6);
+        sfmb200_angle_axis_to_rotmat(v6, R);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) pose(r, c) = (float)R[3 * r + c]; pose(r, 3) = (float)v6[3 + r]; }
     }
     for (int i = 0; i < np; ++i) { pointCloud[i].p.x = (float)pts[3 * i]; pointCloud[i].p.y = (float)pts[3 * i + 1]; pointCloud[i].p.z = (float)pts[3 * i + 2]; }
 }

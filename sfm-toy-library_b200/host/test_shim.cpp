@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include "../../include/sfmb200.h"
 
 using namespace sfmtoylib;
 
@@ -108,7 +109,11 @@ static void test_adjust_bundle() {
         poses[v] = makePose(Rn, truth[v](0, 3) + 0.03f * (float)N01(rng), truth[v](1, 3) + 0.03f * (float)N01(rng), truth[v](2, 3) + 0.03f * (float)N01(rng));
     }
     poses.push_back(Pose());                       // an "empty" placeholder pose nobody observes (SfMBundleAdjustmentUtils.cpp:118-122)
-    std::vector<Features> feats(nviews + 1);
+    {   // a NON-empty pose nobody observes: the reference still rewrites it from its float angle-axis (:192-215)
+        float Ru[9]; eulerDegToR(11.0, -17.0, 23.0, Ru);
+        poses.push_back(makePose(Ru, 0.25f, -0.5f, 3.0f));
+    }
+    std::vector<Features> feats(nviews + 2);
     PointCloud cloud;
     for (int i = 0; i < npts; ++i) {
         const double X = U(rng), Y = U(rng), Z = U(rng);
@@ -131,6 +136,20 @@ static void test_adjust_bundle() {
     for (int i = 0; i < npts; ++i) moved += std::fabs(cloud[i].p.x - cloud0[i].p.x);
     EXPECT(moved > 1e-3, "points were written back (CONVERGENCE)");
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT(poses[nviews](r, c) == 0.0f, "empty pose left untouched");
+    {   // unobserved non-empty pose: R -> float angle-axis -> double rotation matrix -> float (a round trip, not a copy)
+        const Pose& before = poses0[nviews + 1]; const Pose& after = poses[nviews + 1];
+        float R[9], aa[3]; double aad[3], Rd[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[3 * r + c] = before(r, c);
+        sfmb200_rotmat_to_angle_axis_f32(R, aa);
+        for (int k = 0; k < 3; ++k) aad[k] = aa[k];
+        sfmb200_angle_axis_to_rotmat(aad, Rd);
+        double maxdiff = 0;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) { EXPECT(after(r, c) == (float)Rd[3 * r + c], "unobserved pose = its own angle-axis round trip"); maxdiff = std::fmax(maxdiff, std::fabs(after(r, c) - before(r, c))); }
+            EXPECT(after(r, 3) == before(r, 3), "unobserved pose keeps its translation");
+        }
+        EXPECT(maxdiff < 1e-5, "round trip stays within float rounding");
+    }
     // reprojection RMS with the adjusted parameters ~ noise level
     double ss = 0; int n = 0;
     for (int i = 0; i < npts; ++i)

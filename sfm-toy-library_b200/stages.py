@@ -84,19 +84,28 @@ def triangulateViews(intrinsics: Intrinsics, imagePair: ImagePair, matches: np.n
     return True
 
 
-def flatten_bundle(pointCloud: PointCloud, cameraPoses: List[np.ndarray], intrinsics: Intrinsics, image2dFeatures: List[Features]):
+def pose_is_empty(pose) -> bool:
+    """The reference's "empty pose" rule (SfMBundleAdjustmentUtils.cpp:118-122, :196-199): R diagonal exactly zero."""
+    pose = np.asarray(pose, np.float32).reshape(3, 4)
+    return bool(pose[0, 0] == 0 and pose[1, 1] == 0 and pose[2, 2] == 0)
+
+
+def flatten_bundle(pointCloud: PointCloud, cameraPoses: List[np.ndarray], intrinsics: Intrinsics, image2dFeatures: List[Features],
+                   rot2aa=None):
     """The problem assembly of adjustBundle (SfMBundleAdjustmentUtils.cpp:111-166) into the flat arrays of the C ABI.
-    Cameras that are "empty" (R diagonal all zero, :118-122) or unobserved are left out (Ceres only knows parameter
-    blocks that appear in a residual block); `cam_ids` maps dense index -> view id."""
+    Only views that appear in some originatingViews become camera blocks (Ceres only knows parameter blocks that appear
+    in a residual block); `cam_ids` maps dense index -> view id.  An observed view whose pose is "empty" (:118-122) enters
+    with the all-zero CameraVector() the reference pushes for it (:120) -- and is never written back (:196-199)."""
+    rot2aa = rot2aa or capi.rotmat_to_angle_axis_f32
     K = np.asarray(intrinsics.K, np.float32)
     used = sorted({v for p in pointCloud for v in p.originatingViews})
     dense = {v: i for i, v in enumerate(used)}
     cams = np.zeros((len(used), 6))
     for v in used:
         pose = np.asarray(cameraPoses[v], np.float32).reshape(3, 4)
-        if pose[0, 0] == 0 and pose[1, 1] == 0 and pose[2, 2] == 0:
-            raise ValueError(f"view {v} is observed but its pose is empty")
-        cams[dense[v], :3] = capi.rotmat_to_angle_axis_f32(pose[:, :3])         # float conversion (:126), widened
+        if pose_is_empty(pose):
+            continue                                                             # CameraVector() = zeros (:120)
+        cams[dense[v], :3] = rot2aa(pose[:, :3])                                 # float conversion (:126), widened
         cams[dense[v], 3:] = pose[:, 3]
     focal = float(K[0, 0])                                                       # :138
     pts = np.array([p.p for p in pointCloud], np.float32).astype(np.float64).reshape(-1, 3)
@@ -112,6 +121,29 @@ def flatten_bundle(pointCloud: PointCloud, cameraPoses: List[np.ndarray], intrin
             np.asarray(pt_off, np.int32), used)
 
 
+def write_back_bundle(pointCloud, cameraPoses, intrinsics, cams, pts, focal, used, rot2aa=None, aa2rot=None):
+    """The write-back of adjustBundle (SfMBundleAdjustmentUtils.cpp:188-221), run only after CONVERGENCE.  EVERY non-empty pose
+    is rewritten from its 6-vector (:192-215): the observed ones from the optimised parameters, the unobserved ones from the
+    float angle-axis of their own rotation widened to double (their CameraVector never entered the problem) -- i.e. they
+    are round-tripped through RotationMatrixToAngleAxis<float> / AngleAxisToRotationMatrix<double>.  Empty poses are skipped."""
+    rot2aa = rot2aa or capi.rotmat_to_angle_axis_f32
+    aa2rot = aa2rot or capi.angle_axis_to_rotmat
+    intrinsics.K[0, 0] = np.float32(focal); intrinsics.K[1, 1] = np.float32(focal)     # :188-189
+    dense = {v: i for i, v in enumerate(used)}
+    for v in range(len(cameraPoses)):
+        pose = cameraPoses[v]
+        if pose_is_empty(pose):
+            continue
+        if v in dense:
+            aa = cams[dense[v], :3]; t = cams[dense[v], 3:]
+        else:
+            aa = rot2aa(np.asarray(pose, np.float32)[:, :3]).astype(np.float64); t = np.asarray(pose, np.float32)[:, 3].astype(np.float64)
+        pose[:, :3] = aa2rot(aa).astype(np.float32)
+        pose[:, 3] = np.asarray(t).astype(np.float32)
+    for i, p in enumerate(pointCloud):                                           # :217-221
+        p.p = pts[i].astype(np.float32)
+
+
 def adjustBundle(pointCloud: PointCloud, cameraPoses: List[np.ndarray], intrinsics: Intrinsics, image2dFeatures: List[Features],
                  ctx=None, options=None):
     """SfMBundleAdjustmentUtils::adjustBundle (SfMBundleAdjustmentUtils.cpp:99-222).  Mutates pointCloud, cameraPoses
@@ -122,11 +154,22 @@ def adjustBundle(pointCloud: PointCloud, cameraPoses: List[np.ndarray], intrinsi
     if summary["termination_type"] != capi.CONVERGENCE:
         print("Bundle adjustment failed.")                                       # :183
         return summary
-    intrinsics.K[0, 0] = np.float32(focal); intrinsics.K[1, 1] = np.float32(focal)     # :188-189
-    for i, v in enumerate(used):                                                 # :192-215
-        pose = cameraPoses[v]
-        pose[:, :3] = capi.angle_axis_to_rotmat(cams[i, :3]).astype(np.float32)
-        pose[:, 3] = cams[i, 3:].astype(np.float32)
-    for i, p in enumerate(pointCloud):                                           # :217-221
-        p.p = pts[i].astype(np.float32)
+    write_back_bundle(pointCloud, cameraPoses, intrinsics, cams, pts, focal, used)
     return summary
+
+
+def matchAllPairs(features: List[Features], pairs, ctx=None) -> List[np.ndarray]:
+    """The batched form of SfM::createFeatureMatchMatrix (SfM.cpp:157-212): descriptors uploaded once
+    (sfmb200_descset), every (left, right) pair matched in one launch sequence (sfmb200_match_pairs)."""
+    ctx = ctx or default_context()
+    ds = ctx.descriptor_set([f.descriptors for f in features])
+    try:
+        res = ds.match_pairs(pairs, capi.RATIO_REFERENCE)
+    finally:
+        ds.close()
+    out = []
+    for q, t, d in res:
+        m = np.zeros(len(q), DMATCH)
+        m["queryIdx"] = q; m["trainIdx"] = t; m["distance"] = d
+        out.append(m)
+    return out

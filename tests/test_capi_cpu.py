@@ -127,3 +127,38 @@ def test_ba_validate_accepts_and_rejects_like_the_nested_loop(L):
     assert capi.ba_validate(5, np.zeros(3, np.int32), np.zeros(1, np.int32))[0] != 0           # observations without points
     rc, msg = capi.ba_validate(300, np.arange(256, dtype=np.int32), np.array([0, 256], np.int32))
     assert rc != 0 and "255" in msg                                                              # more views per point than supported
+
+
+def test_write_back_rewrites_every_non_empty_pose_like_the_reference(L, oracle):
+    """SfMBundleAdjustmentUtils.cpp:192-215: after CONVERGENCE every non-empty pose is rebuilt from its 6-vector -- the
+    unobserved ones from their own float angle-axis (a round trip through RotationMatrixToAngleAxis<float> and
+    AngleAxisToRotationMatrix<double>); empty poses (:118-122, :196-199) are skipped on the way in and out."""
+    from sfm_toy_library_b200 import stages
+    rng = np.random.RandomState(3)
+
+    def pose(aa, t):
+        P = np.zeros((3, 4), np.float32); P[:, :3] = oracle.angle_axis_to_rotmat(np.asarray(aa, np.float64)); P[:, 3] = t
+        return P
+    poses = [pose([0.1, -0.2, 0.05], [0, 0, 5]), np.zeros((3, 4), np.float32), pose([0.3, 0.1, -0.4], [1, 2, 3]), pose([-0.2, 0.5, 0.1], [0.5, 0, 4])]
+    feats = [stages.Features(points=rng.rand(5, 2).astype(np.float32) * 100) for _ in poses]
+    cloud = [stages.Point3DInMap(np.array([0.1 * i, 0.2, 3.0], np.float32), {0: i, 3: i}) for i in range(4)]
+    K = np.array([[2500, 0, 512], [0, 2500, 384], [0, 0, 1]], np.float32)
+    intr = stages.Intrinsics(K.copy())
+    cams, pts, focal, obs_xy, obs_cam, pt_off, used = stages.flatten_bundle(cloud, poses, intr, feats, rot2aa=oracle.rotmat_to_angle_axis_f32)
+    assert used == [0, 3] and cams.shape == (2, 6)
+    before = [p.copy() for p in poses]
+    cams2 = cams.copy(); cams2[:, 3:] += 0.25
+    stages.write_back_bundle(cloud, poses, intr, cams2, pts + 1.0, 2400.0, used, rot2aa=oracle.rotmat_to_angle_axis_f32,
+                             aa2rot=oracle.angle_axis_to_rotmat)
+    assert intr.K[0, 0] == np.float32(2400) and intr.K[1, 1] == np.float32(2400)
+    np.testing.assert_array_equal(poses[1], 0)                                   # empty: untouched
+    np.testing.assert_allclose(poses[0][:, 3], before[0][:, 3] + 0.25, rtol=1e-6)   # observed: optimised parameters
+    aa = oracle.rotmat_to_angle_axis_f32(before[2][:, :3]).astype(np.float64)    # unobserved, non-empty: round trip
+    np.testing.assert_array_equal(poses[2][:, :3], oracle.angle_axis_to_rotmat(aa).astype(np.float32))
+    np.testing.assert_array_equal(poses[2][:, 3], before[2][:, 3])
+    assert np.abs(poses[2] - before[2]).max() < 1e-6
+    np.testing.assert_allclose([p.p for p in cloud], pts + 1.0, rtol=1e-6)
+    # an observed view with an empty pose enters as CameraVector() = zeros (:120) and is not written back
+    poses[3] = np.zeros((3, 4), np.float32)
+    cams, *_ = stages.flatten_bundle(cloud, poses, intr, feats, rot2aa=oracle.rotmat_to_angle_axis_f32)
+    np.testing.assert_array_equal(cams[1], 0)

@@ -99,3 +99,35 @@ def test_popc_and_tensor_core_paths_are_bit_identical(ctx, oracle, monkeypatch, 
     _same(ctx.match_knn2_ratio(q, t), ref)
     monkeypatch.setenv("SFMB200_MATCH", "tc")
     _same(ctx.match_knn2_ratio(q, t), ref)
+
+
+@pytest.mark.parametrize("nbytes", [61, 20, 100, 128, 16])
+def test_any_descriptor_width_up_to_128_bytes(ctx, oracle, nbytes):
+    """The reference accepts any cv::Mat width (AKAZE: 61 bytes); widths between the instantiated kernels are zero-padded."""
+    rng = np.random.RandomState(nbytes)
+    a = rng.randint(0, 256, (300, nbytes)).astype(np.uint8); b = rng.randint(0, 256, (280, nbytes)).astype(np.uint8)
+    b[::3] = a[rng.randint(0, 300, len(b[::3]))]
+    b[::3, 0] ^= 5
+    _same(ctx.match_knn2_ratio(b, a), oracle.match_hamming(b, a))
+    ds = ctx.descriptor_set([a, b])
+    _same(ds.match_pairs([(1, 0)])[0], oracle.match_hamming(b, a))
+    ds.close()
+
+
+def test_resident_image_cache_detects_reused_buffers(ctx, oracle):
+    """Per-call path keeps uploaded images resident, keyed by (pointer, rows, width, content hash): same buffer + same
+    content = hit; same buffer + new content must be re-uploaded."""
+    a = synth.make_descriptors(20, 900); b = synth.make_descriptors(21, 800, prev=a)
+    r1 = ctx.match_knn2_ratio(b, a)
+    r2 = ctx.match_knn2_ratio(b, a)                      # both images resident now
+    _same(r1, r2); _same(r1, oracle.match_hamming(b, a))
+    c = synth.make_descriptors(22, 900)
+    a[:] = c                                             # caller reuses the buffer
+    _same(ctx.match_knn2_ratio(b, a), oracle.match_hamming(b, a))
+    _same(ctx.match_knn2_ratio(a, a), oracle.match_hamming(a, a))
+
+
+def test_cache_flush_when_arena_is_full(ctx, oracle):
+    imgs = [synth.make_descriptors(100 + i, 9000) for i in range(20)]     # 180 k rows > the 128 k row arena
+    for i in range(1, 20):
+        _same(ctx.match_knn2_ratio(imgs[i][:700], imgs[i - 1]), oracle.match_hamming(imgs[i][:700], imgs[i - 1]))
