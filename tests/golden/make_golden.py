@@ -138,3 +138,51 @@ def golden_ba():
 
 if __name__ == "__main__":
     golden_match(); golden_triangulate(); golden_reprojection(); golden_ba()
+
+
+def golden_ba_cfg2():
+    """BASELINE configs[1] (cfg 2: 20 cameras / 10 k points / 80 k observations, synth.make_ba_problem(seed=0)) solved to its
+    optimum by scipy's trust-region-reflective least squares with an analytic sparse Jacobian obtained by complex-step
+    differentiation of the numpy model in oracle/dense_lm.py -- nothing shared with oracle/ba_oracle.c or the CUDA solver.
+    Stored: the optimal cost and parameters (the inputs are regenerated from the seed)."""
+    from scipy.sparse import csr_matrix
+    from oracle import dense_lm
+    p = synth.make_ba_problem(seed=0, **synth.BA_CONFIGS["cfg2"])
+    nc, npt, nobs = p["nc"], p["np"], p["nobs"]
+    oc, op, oxy = p["obs_cam"].astype(np.int64), p["obs_pt"].astype(np.int64), p["obs_xy"].astype(np.float64)
+    n = 6 * nc + 3 * npt + 1
+
+    def unpack(x):
+        return x[:6 * nc].reshape(nc, 6), x[6 * nc:6 * nc + 3 * npt].reshape(npt, 3), x[-1]
+
+    def fun(x):
+        c, q, f = unpack(x)
+        return dense_lm.residuals(c, q, f, oxy, oc, op).reshape(-1)
+
+    rows = np.arange(2 * nobs).reshape(nobs, 2)
+
+    def jac(x, h=1e-40):
+        c, q, f = unpack(x)
+        cc = c.astype(np.complex128); qc = q.astype(np.complex128)
+        ri, ci, vv = [], [], []
+        for k in range(6):
+            c2 = cc.copy(); c2[:, k] += 1j * h
+            d = dense_lm.residuals(c2, qc, f, oxy, oc, op).imag / h
+            ri.append(rows.ravel()); ci.append(np.repeat(6 * oc + k, 2)); vv.append(d.ravel())
+        for k in range(3):
+            q2 = qc.copy(); q2[:, k] += 1j * h
+            d = dense_lm.residuals(cc, q2, f, oxy, oc, op).imag / h
+            ri.append(rows.ravel()); ci.append(np.repeat(6 * nc + 3 * op + k, 2)); vv.append(d.ravel())
+        d = dense_lm.residuals(cc, qc, f + 1j * h, oxy, oc, op).imag / h
+        ri.append(rows.ravel()); ci.append(np.full(2 * nobs, n - 1)); vv.append(d.ravel())
+        return csr_matrix((np.concatenate(vv), (np.concatenate(ri), np.concatenate(ci))), shape=(2 * nobs, n))
+
+    x0 = np.concatenate([p["cams"].ravel(), p["pts"].ravel(), [p["focal"]]])
+    sol = least_squares(fun, x0, jac=jac, x_scale="jac", method="trf", ftol=1e-15, xtol=1e-15, gtol=1e-12, max_nfev=200, tr_solver="lsmr",
+                        tr_options=dict(atol=1e-14, btol=1e-14, maxiter=4000))
+    cost0 = 0.5 * np.sum(fun(x0) ** 2)
+    g = jac(sol.x).T @ fun(sol.x)
+    print("ba cfg2: cost0", cost0, "-> scipy optimum", sol.cost, "nfev", sol.nfev, "max|g|", np.abs(g).max(), sol.message)
+    c, q, f = unpack(sol.x)
+    np.savez_compressed(os.path.join(OUT, "ba_scipy_cfg2.npz"), cost0=cost0, cost_opt=sol.cost, cams=c, pts=q.astype(np.float32), focal=f,
+                        grad_max=np.abs(g).max())

@@ -107,3 +107,22 @@ def test_reduced_system_is_the_schur_complement(oracle):
     rhs = b[ic] - H[np.ix_(ic, ip)] @ Hpp_inv @ b[ip]
     np.testing.assert_allclose(out["S"], S, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(out["rhs"], rhs, rtol=1e-9, atol=1e-12)
+
+
+def test_cfg2_reaches_the_independent_scipy_optimum(oracle, golden):
+    """BASELINE configs[1] at full size: the oracle's LM + DENSE_SCHUR lands on the optimum that scipy's TRF (sparse analytic
+    Jacobian by complex-step differentiation of an independent numpy model, tests/golden/make_golden.py:golden_ba_cfg2)
+    finds -- cost to 1e-9 relative, well inside the 1e-6 the round-1 review asked for."""
+    g = golden("ba_scipy_cfg2.npz")
+    p = synth.make_ba_problem(seed=0, **synth.BA_CONFIGS["cfg2"])
+    o = oracle.ba_default_options(jacobian_mode=1, num_threads=4, max_solver_time_in_seconds=0.0, function_tolerance=1e-14,
+                                  parameter_tolerance=1e-14, max_num_iterations=60)
+    cams, pts, f, s = oracle.ba_solve(p["cams"], p["pts"], p["focal"], p["obs_xy"], p["obs_cam"], p["pt_off"], o)
+    assert abs(s["initial_cost"] - float(g["cost0"])) < 1e-10 * float(g["cost0"])
+    assert abs(s["final_cost"] - float(g["cost_opt"])) < 1e-9 * float(g["cost_opt"]), (s["final_cost"], float(g["cost_opt"]))
+    assert abs(f - float(g["focal"])) < 1e-5 * f
+    # (cameras / points are only defined up to the 7-dof similarity gauge: the cost and the focal length are the invariants)
+    # Ceres' default tolerances stop a little earlier: still within 1e-6 of the optimum
+    o = oracle.ba_default_options(jacobian_mode=1, num_threads=4, max_solver_time_in_seconds=0.0)
+    s = oracle.ba_solve(p["cams"], p["pts"], p["focal"], p["obs_xy"], p["obs_cam"], p["pt_off"], o)[3]
+    assert s["termination_type"] == 0 and 0 <= s["final_cost"] - float(g["cost_opt"]) < 1e-6 * float(g["cost_opt"]), s
