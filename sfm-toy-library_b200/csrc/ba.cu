@@ -10,12 +10,14 @@
 //     observations (ba_math.cuh) -- HBM traffic per LM iteration is the observation list + the point/camera state.
 //   * ba_point_kernel   (K3a, point-major, one sub-warp group per 3D point): U_p = sum Jp^T Jp + D_p^2, its Cholesky
 //     inverse M_p, g_p, and per observation Z_o = Jc^T Jp M^T (Zbuf).
-//   * ba_pair_kernel    (K3c): the OFF-diagonal blocks  S[ci,cj] -= sum Z_i Z_j^T  over per-camera-pair entry lists built
-//     once per problem, one mma.sync.m8n8k4.f64 per entry, no atomics in the loop ("red" mode keeps the per-point
-//     red.global.add.f64 formulation for comparison).
-//   * ba_camera_kernel  (K3b, camera-major): everything that would be same-address contention -- the diagonal blocks,
-//     the camera-focal column, rhs and gradient -- is accumulated in registers over the camera-sorted observation list and
-//     reduced once per (CTA, camera) (the shared focal block makes every observation touch S[:,focal]).
+//   * ba_row_kernel     (K3b, camera-major, ba_row.cuh): a CTA walks a slice of the STABLE camera-sorted observation list and
+//     keeps the block row S[ci, ci+1..] of the camera it is in in shared memory: the off-diagonal blocks  S[ci,cj] -= sum
+//     Z_i Z_j^T  come from the records that FOLLOW Z_i in the point-major Z buffer (one mma.sync.m8n8k4.f64 per update, no index
+//     lists, no atomics), the diagonal block, the camera-focal column the shared focal creates, rhs,
+//     gradient and J^T J diagonal from two 8x8 fp64 tensor-core products per warp.  ba_combine_kernel sums the per-(slice,
+//     camera) partial records in a fixed order: no floating-point atomics, bitwise reproducible.
+//     ("red" mode, SFMB200_BA_SCHUR=red or more cameras than a shared-memory row holds, keeps the per-point
+//     red.global.add.f64 formulation with the register-accumulating ba_camera_kernel.)
 //   * reduced system summed over ranks: peer-memory kernel (loads the peers' buffers over NVLink into a local summed copy)
 //     or one NCCL all-reduce (S, rhs, gradient, diag, cost in one buffer).
 //   * ba_assemble + chol.cuh (streaming dataflow tile Cholesky, rhs carried as an extra row so the forward substitution is
@@ -74,7 +76,38 @@ struct BAView {
     unsigned long long* gmax_pt_bits;                                 // max |g_p| (bit pattern of a non-negative double)
     int* fail;                                                        // count of non-SPD point blocks
     double min_diag, max_diag;
+    double* part4;                                                    // [grid][4] per-CTA partial sums of the point-major kernels (row mode)
+    unsigned* counters;                                               // [0] point kernel, [1] back-substitution, [2] combine: "last CTA" tickets
 };
+
+// Fixed-order reduction of per-CTA partial sums by the LAST CTA to finish (whoever that is, the order of the additions is the
+// same): every CTA stores its 4 partials, takes a ticket; the last one lets warp 0 add partials lane, lane+32, ... and then a
+// fixed shuffle tree.  Returns true in the threads of warp 0 of the last CTA, with the totals in out[0..3].  The ticket
+// counter wraps to zero, ready for the next launch.
+__device__ __forceinline__ bool last_block_sum4(double* __restrict__ part4, unsigned* __restrict__ counter, const double (&mine)[4], double (&out)[4]) {
+    __shared__ bool last_s;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) part4[4 * (size_t)blockIdx.x + q] = mine[q];
+        __threadfence();
+        last_s = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last_s || threadIdx.x >= 32) return false;
+    __threadfence();
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += __ldcg(part4 + 4 * (size_t)b + q);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        out[q] = acc[q];
+    }
+    return true;
+}
 
 // The current x of a kernel: the view's own pointers, or -- inside an LM chunk -- buffer st->cur.  run = false when the solve
 // has already terminated (the kernel is a no-op).  (Kept out of BAView: writing to the by-value parameter struct makes the
@@ -345,7 +378,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, doubl
                 W[a * 3] = w0 * M[0]; W[a * 3 + 1] = w0 * M[1] + w1 * M[2]; W[a * 3 + 2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
             }
         }
-        if (GATHER) continue;           // off-diagonal blocks are accumulated by ba_pair_kernel from Zbuf
+        if (GATHER) continue;           // off-diagonal blocks are accumulated by ba_row_kernel from Zbuf
         __syncwarp();
         // pair sweep: the whole warp handles the points of its GW groups one after the other
 #pragma unroll 1
@@ -370,167 +403,31 @@ __global__ void __launch_bounds__(PT_THREADS, 3) ba_point_kernel(BAView v, doubl
     const double c0 = warp_sum(acc_cost), c1 = warp_sum(acc_xn), c2 = warp_sum(acc_sff), c3 = warp_sum(acc_rf), c4 = warp_max(acc_gmax);
     if (lane == 0) { sred[warp][0] = c0; sred[warp][1] = c1; sred[warp][2] = c2; sred[warp][3] = c3; sred[warp][4] = c4; }
     __syncthreads();
+    double t[4] = {0, 0, 0, 0};
     if (threadIdx.x == 0) {
-        double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
-        for (int w = 0; w < PT_THREADS / 32; ++w) { t0 += sred[w][0]; t1 += sred[w][1]; t2 += sred[w][2]; t3 += sred[w][3]; t4 = fmax(t4, sred[w][4]); }
-        red_add(v.sums + 0, t0); red_add(v.sums + 1, t1);
-        red_add(v.Sff, -t2); red_add(v.rhs + 6 * v.nc, -t3);
-        atomicMax(v.gmax_pt_bits, (unsigned long long)__double_as_longlong(t4));
+        double t4 = 0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) { t[0] += sred[w][0]; t[1] += sred[w][1]; t[2] += sred[w][2]; t[3] += sred[w][3]; t4 = fmax(t4, sred[w][4]); }
+        atomicMax(v.gmax_pt_bits, (unsigned long long)__double_as_longlong(t4));     // a maximum: order-independent
+        if (!GATHER) {                                                               // "red" mode: accumulating atomics
+            red_add(v.sums + 0, t[0]); red_add(v.sums + 1, t[1]);
+            red_add(v.Sff, -t[2]); red_add(v.rhs + 6 * v.nc, -t[3]);
+        }
+    }
+    if (GATHER) {                      // row mode: fixed-order sum by the last CTA; plain stores (ba_combine_kernel adds the camera part)
+        double tot[4];
+        if (last_block_sum4(v.part4, v.counters + 0, t, tot) && threadIdx.x == 0) {
+            v.sums[0] = tot[0]; v.sums[1] = tot[1]; *v.Sff = -tot[2]; v.rhs[6 * v.nc] = -tot[3];
+        }
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// K3c (gather mode): off-diagonal blocks without atomics.  For every camera pair (ci < cj) the list of (obs_i, obs_j)
-// index pairs of the points both cameras see is built once per problem (the structure is fixed across LM iterations).
-// One warp per (pair, split): lanes stride over the list, each accumulating a full 6x6 block  sum Z_i Z_j^T  in 36
-// registers from two 144-byte reads, then a warp shuffle reduction and 36 REDs per warp (instead of 36 per entry).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int PAIR_WARPS = 4;
-// pair_off is indexed by key = blk * nseg + seg (seg = point-range segment): the grid walks the segments in the slow
-// (y) dimension, LAST segment first, so that all resident warps read the same ~24 MB slice of Zbuf -- which then lives
-// in L2 (the tail of Zbuf is still L2-resident from the point kernel that just wrote it).
-// The accumulation  S[ci,cj] -= sum_e Z_i(e) Z_j(e)^T  is a (6 x 3E)(3E x 6) product in fp64: it runs on the FP64
-// tensor pipe as one  mma.sync.m8n8k4.f64  per entry (6x6x3 padded to 8x8x4).  The operand fragments want lane l to hold
-// element (l>>2, l&3) of the 8x4 tile, i.e. double number (l>>2)*3 + (l&3) of the 18-double Z record: one coalesced
-// 8-byte load per lane per operand (18 of 32 lanes active, one 144-byte record = at most two 128-byte lines), instead
-// of 18 uncoalesced 16-byte loads per lane in a lane-per-entry SIMT formulation (which was L1-wavefront bound).
+// one FP64 tensor-core product: D(8x8) += A(8x4) B(4x8); lane l holds A[l>>2][l&3], B[l&3][l>>2], D[l>>2][2(l&3)], D[l>>2][2(l&3)+1]
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-constexpr int PAIR_UNROLL = 8;
-__global__ void __launch_bounds__(PAIR_WARPS * 32, 8) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
-                                                                   const uint2* __restrict__ pair_ent, int n_nonempty, int nseg, int splits,
-                                                                   const int32_t* __restrict__ pair_blk, double* __restrict__ Sblk, const LMState* __restrict__ st) {
-    if (st && st->status != LM_RUNNING) return;
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);       // index into the list of non-empty pairs
-    if (q >= n_nonempty) return;
-    const int seg = nseg - 1 - (int)(blockIdx.y / splits), sp = blockIdx.y % splits;
-    const int blk = pair_blk[q];
-    const int start = pair_off[(size_t)blk * nseg + seg], len = pair_off[(size_t)blk * nseg + seg + 1] - start;
-    const int b0 = start + (int)((long long)len * sp / splits), b1 = start + (int)((long long)len * (sp + 1) / splits);
-    if (b1 <= b0) return;
-    const int fr = lane >> 2, fc = lane & 3;
-    const bool valid = fr < 6 && fc < 3;
-    const int fidx = valid ? fr * 3 + fc : 0;
-    double c0[4], c1[4];               // 4 independent accumulator fragments
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { c0[u] = 0.0; c1[u] = 0.0; }
-    // Entries arrive in batches of PAIR_UNROLL: lanes 0..7 fetch the batch's index pairs with ONE coalesced 64-byte load (a
-    // broadcast load per entry cost a wavefront each) and hand them round with shuffles; the NEXT batch's indices are
-    // requested before this batch's operands are consumed, so that the index round trip and the operand round trip of
-    // consecutive batches overlap (the kernel is latency bound: 83% long-scoreboard stalls).
-    uint2 cur = make_uint2(0u, 0u);
-    if (lane < PAIR_UNROLL && b0 + lane < b1) cur = __ldg(pair_ent + b0 + lane);
-    for (int e = b0; e < b1; e += PAIR_UNROLL) {
-        uint2 nxt = make_uint2(0u, 0u);
-        const int en = e + PAIR_UNROLL;
-        if (lane < PAIR_UNROLL && en + lane < b1) nxt = __ldg(pair_ent + en + lane);
-        double a[PAIR_UNROLL], b[PAIR_UNROLL];
-#pragma unroll
-        for (int u = 0; u < PAIR_UNROLL; ++u) {
-            const unsigned ox = __shfl_sync(0xffffffffu, cur.x, u), oy = __shfl_sync(0xffffffffu, cur.y, u);
-            const bool live = valid && e + u < b1;                     // past the end: indices are 0, operands forced to 0
-            const double va = __ldg(Zbuf + (size_t)ox * 18 + fidx), vb = __ldg(Zbuf + (size_t)oy * 18 + fidx);
-            a[u] = live ? va : 0.0; b[u] = live ? vb : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < PAIR_UNROLL; ++u) dmma_m8n8k4(c0[u & 3], c1[u & 3], a[u], b[u]);
-        cur = nxt;
-    }
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { s0 += c0[u]; s1 += c1[u]; }
-    // accumulator fragment: row = lane>>2, columns 2*(lane&3) and 2*(lane&3)+1
-    const int cc = 2 * fc;
-    if (fr < 6 && cc < 6) {
-        double* dst = Sblk + (size_t)blk * 36 + fr * 6 + cc;
-        red_add(dst, -s0); red_add(dst + 1, -s1);
-    }
-}
-
-// pair-list construction (once per problem): thread per point; key = blk * nseg + seg(point)
-__device__ __forceinline__ int point_segment(int p, int np, int nseg) { return (int)((long long)p * nseg / np); }
-__global__ void __launch_bounds__(256) pair_count_kernel(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ obs_cam, int np, int nb,
-                                                         int nseg, int* __restrict__ cnt) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= np) return;
-    const int o0 = pt_off[p], o1 = pt_off[p + 1], seg = point_segment(p, np, nseg);
-    for (int i = o0; i < o1; ++i)
-        for (int j = i + 1; j < o1; ++j) atomicAdd(cnt + (size_t)blk_index(obs_cam[i], obs_cam[j], nb) * nseg + seg, 1);
-}
-// exclusive scan of cnt[nkeys] -> pair_off[nkeys+1] and cursor[nkeys]; single CTA, chained over 1024-element chunks
-__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ cnt, int nkeys, int32_t* __restrict__ pair_off, int* __restrict__ cursor) {
-    __shared__ int wsum[32], carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < nkeys; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int c = i < nkeys ? cnt[i] : 0;
-        int s = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += a; }
-        if (lane == 31) wsum[w] = s;
-        __syncthreads();
-        if (w == 0) {
-            int a = wsum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a += x; }
-            wsum[lane] = a;
-        }
-        __syncthreads();
-        const int ex = carry_s + (w ? wsum[w - 1] : 0) + s - c;
-        if (i < nkeys) { cursor[i] = ex; pair_off[i] = ex; }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += wsum[31];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) pair_off[nkeys] = carry_s;
-}
-// list of camera pairs that have at least one entry; single CTA (nblk = nc(nc+1)/2 is small)
-__global__ void __launch_bounds__(1024) pair_compact_kernel(const int32_t* __restrict__ pair_off, int nblk, int nseg, int32_t* __restrict__ pair_blk,
-                                                            int* __restrict__ n_nonempty) {
-    __shared__ int wcnt[32], carry_q;
-    if (threadIdx.x == 0) carry_q = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < nblk; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int f = i < nblk ? (pair_off[(size_t)(i + 1) * nseg] > pair_off[(size_t)i * nseg]) : 0;
-        int q = f;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int b = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) q += b; }
-        if (lane == 31) wcnt[w] = q;
-        __syncthreads();
-        if (w == 0) {
-            int b = wcnt[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, b, o); if (lane >= o) b += y; }
-            wcnt[lane] = b;
-        }
-        __syncthreads();
-        if (f) pair_blk[carry_q + (w ? wcnt[w - 1] : 0) + q - 1] = i;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_q += wcnt[31];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *n_nonempty = carry_q;
-}
-__global__ void __launch_bounds__(256) pair_fill_kernel(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ obs_cam, int np, int nb,
-                                                        int nseg, int* __restrict__ cursor, uint2* __restrict__ ent) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= np) return;
-    const int o0 = pt_off[p], o1 = pt_off[p + 1], seg = point_segment(p, np, nseg);
-    for (int i = o0; i < o1; ++i)
-        for (int j = i + 1; j < o1; ++j) {
-            const int pos = atomicAdd(cursor + (size_t)blk_index(obs_cam[i], obs_cam[j], nb) * nseg + seg, 1);
-            ent[pos] = make_uint2((unsigned)i, (unsigned)j);
-        }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3b: camera-major pass over the camera-sorted observation list.  Every CTA takes an equal, contiguous slice of the list
+// K3b ("red" mode only; the default is ba_row_kernel, ba_row.cuh): camera-major pass over the camera-sorted observation list.  Every CTA takes an equal, contiguous slice of the list
 // (grid = number of co-resident CTAs, one balanced wave; a per-camera grid left a third of the run to a ragged last wave)
 // and walks the cameras its slice touches.  Per camera: diagonal block, camera-focal column, rhs, gradient and J^T J
 // diagonal, all in registers; one reduction per (CTA, camera).
@@ -622,6 +519,8 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
     __syncthreads();            // red[] is reused by the next camera of this slice
     }
 }
+
+#include "ba_row.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // K4: dense reduced system.  A is (npad x npad) row-major, lower triangle used, npad = multiple of NB > n;
@@ -883,11 +782,10 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_z_kernel(BAView v, doub
     const double c0 = warp_sum(acc_cc), c1 = warp_sum(acc_m), c2 = warp_sum(acc_dn), c3 = warp_sum(acc_cn);
     if (lane == 0) { sred[warp][0] = c0; sred[warp][1] = c1; sred[warp][2] = c2; sred[warp][3] = c3; }
     __syncthreads();
-    if (threadIdx.x < 4) {
-        double s = 0;
-        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w][threadIdx.x];
-        red_add(post + threadIdx.x, s);
-    }
+    double t[4] = {0, 0, 0, 0};
+    if (threadIdx.x == 0) for (int w = 0; w < PT_THREADS / 32; ++w) { t[0] += sred[w][0]; t[1] += sred[w][1]; t[2] += sred[w][2]; t[3] += sred[w][3]; }
+    double tot[4];
+    if (last_block_sum4(v.part4, v.counters + 1, t, tot) && threadIdx.x == 0) { post[0] = tot[0]; post[1] = tot[1]; post[2] = tot[2]; post[3] = tot[3]; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -975,11 +873,10 @@ __global__ void __launch_bounds__(PT_THREADS) ba_backsub_eval_kernel(BAView v, c
     const double c0 = warp_sum(acc_cc), c1 = warp_sum(acc_m), c2 = warp_sum(acc_dn), c3 = warp_sum(acc_cn);
     if (lane == 0) { sred[warp][0] = c0; sred[warp][1] = c1; sred[warp][2] = c2; sred[warp][3] = c3; }
     __syncthreads();
-    if (threadIdx.x < 4) {
-        double s = 0;
-        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w][threadIdx.x];
-        red_add(post + threadIdx.x, s);
-    }
+    double t[4] = {0, 0, 0, 0};
+    if (threadIdx.x == 0) for (int w = 0; w < PT_THREADS / 32; ++w) { t[0] += sred[w][0]; t[1] += sred[w][1]; t[2] += sred[w][2]; t[3] += sred[w][3]; }
+    double tot[4];
+    if (last_block_sum4(v.part4, v.counters + 1, t, tot) && threadIdx.x == 0) { post[0] = tot[0]; post[1] = tot[1]; post[2] = tot[2]; post[3] = tot[3]; }
 }
 
 // camera-major copy of the observation list: counting sort by camera (structure is fixed across LM iterations).
@@ -1112,10 +1009,12 @@ struct sfmb200_ba_problem {
     EvSet evs[LM_CHUNK];              // profile mode: one set of events per iteration of a chunk (created on first use)
     bool have_events = false;
     LMState* d_state = nullptr; LMState* h_state = nullptr;    // device-resident LM control state + pinned read-back
-    // gather mode (K3c): Z per observation + per-camera-pair entry lists
-    bool gather = true;
-    double* Zbuf = nullptr; int32_t* pair_off = nullptr; int32_t* pair_blk = nullptr; uint2* pair_ent = nullptr;
-    int n_pairs_nonempty = 0, pair_splits = 1, pair_nseg = 1;
+    // row mode (default): Z per observation (point-major), stable camera-major list with follower counts, partial records
+    bool gather = true;               // true = row mode (ba_row_kernel), false = "red" mode
+    double* Zbuf = nullptr;
+    int32_t* obs_pt = nullptr; int32_t* cm_obs = nullptr; uint8_t* cm_np = nullptr;
+    double* row_part = nullptr; int row_grid = 0, row_per_cta = 0, row_rec_stride = 0; size_t row_smem = 0;
+    double* part4 = nullptr; double* fpart = nullptr; unsigned* counters = nullptr;
     DevBuf gmem;
     // exchange memory (its own cudaMalloc so that it can be exported with CUDA IPC): red | post.. | flags
     void* xmem = nullptr; size_t xmem_doubles = 0; double* xtmp = nullptr; unsigned long long* xflags = nullptr;
@@ -1143,7 +1042,13 @@ static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* o
     v.Sblk = P->Sblk; v.Scf = P->Scf; v.Sff = P->Sff; v.rhs = P->rhs; v.gcf = P->gcf; v.dcf = P->dcf; v.sums = P->sums;
     v.gmax_pt_bits = P->gmax_pt_bits; v.fail = P->fail;
     v.min_diag = opt->min_lm_diagonal; v.max_diag = opt->max_lm_diagonal;
+    v.part4 = P->part4; v.counters = P->counters;
     return v;
+}
+
+static RowArgs make_row_args(const sfmb200_ba_problem* P) {
+    RowArgs ra; ra.cm_obs = P->cm_obs; ra.cm_np = P->cm_np; ra.per_cta = P->row_per_cta; ra.part = P->row_part; ra.rec_stride = P->row_rec_stride;
+    return ra;
 }
 
 static size_t point_smem_bytes(int G, int maxk) {
@@ -1264,7 +1169,13 @@ static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt)
     SFM_CUDA(ctx, cudaMemsetAsync(colnorm, 0, sizeof(double) * n, ctx->stream));
     if (P->np > 0 && P->nobs > 0) {
         int rc = DISPATCH_G(P, launch_point_norm)(P, v); if (rc) return rc;
-        ba_camera_norm_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v, colnorm); SFM_LAUNCH_CHECK(ctx);
+        if (P->gather) {                 // deterministic: partial records per (slice, camera), summed in slice order
+            const RowArgs ra = make_row_args(P);
+            ba_row_kernel<true><<<P->row_grid, ROW_THREADS, P->row_smem, ctx->stream>>>(v, ra); SFM_LAUNCH_CHECK(ctx);
+            ba_combine_kernel<<<P->nc, 256, 0, ctx->stream>>>(v, ra, 1, colnorm, P->fpart, P->counters + 2); SFM_LAUNCH_CHECK(ctx);
+        } else {
+            ba_camera_norm_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v, colnorm); SFM_LAUNCH_CHECK(ctx);
+        }
     }
     int rc = ba_allreduce(P, colnorm, n, 0); if (rc) return rc;
     scale_from_norm_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(summed(P, colnorm), n, P->scale_cf); SFM_LAUNCH_CHECK(ctx);
@@ -1278,8 +1189,11 @@ static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt)
 static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, double radius, const EvSet* es, bool lm) {
     sfmb200_ctx* ctx = P->ctx;
     BAView v = make_view(P, opt, lm);
-    const LMState* st = lm ? P->d_state : nullptr;
-    SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * (P->red_n + 12), ctx->stream));   // red | locals, gmax, fail (contiguous); post is cleared by ba_cam_update_kernel
+    const bool row = P->gather && P->np > 0 && P->nobs > 0;
+    // "red" mode accumulates into the reduced system with atomics: clear all of it.  Row mode overwrites every element
+    // (ba_combine_kernel), only locals | gmax | fail need clearing.  post is cleared by ba_cam_update_kernel.
+    if (row) SFM_CUDA(ctx, cudaMemsetAsync(P->locals, 0, sizeof(double) * 12, ctx->stream));
+    else SFM_CUDA(ctx, cudaMemsetAsync(P->red, 0, sizeof(double) * (P->red_n + 12), ctx->stream));
     if (!lm && !P->camd_valid[P->cur]) {
         cam_derive_kernel<<<ceil_div(std::max(1, P->nc), 128), 128, 0, ctx->stream>>>(v.cams, P->nc, P->camd[P->cur]); SFM_LAUNCH_CHECK(ctx);
         P->camd_valid[P->cur] = true;
@@ -1288,13 +1202,13 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
         if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[0], ctx->stream));
         int rc = DISPATCH_G(P, launch_point_pass)(P, v, 1.0 / radius); if (rc) return rc;
         if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[1], ctx->stream));
-        if (P->gather && P->n_pairs_nonempty > 0) {
-            ba_pair_kernel<<<dim3(ceil_div(P->n_pairs_nonempty, PAIR_WARPS), P->pair_nseg * P->pair_splits), PAIR_WARPS * 32, 0, ctx->stream>>>(
-                P->Zbuf, P->pair_off, P->pair_ent, P->n_pairs_nonempty, P->pair_nseg, P->pair_splits, P->pair_blk, P->Sblk, st);
-            SFM_LAUNCH_CHECK(ctx);
-        }
-        if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[2], ctx->stream));
-        {
+        if (row) {
+            const RowArgs ra = make_row_args(P);
+            ba_row_kernel<false><<<P->row_grid, ROW_THREADS, P->row_smem, ctx->stream>>>(v, ra); SFM_LAUNCH_CHECK(ctx);
+            if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[2], ctx->stream));
+            ba_combine_kernel<<<P->nc, 256, 0, ctx->stream>>>(v, ra, 0, nullptr, P->fpart, P->counters + 2); SFM_LAUNCH_CHECK(ctx);
+        } else {
+            if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[2], ctx->stream));
             const int blocks = resident_grid(P, &P->grid_camera, ba_camera_kernel, CAM_THREADS, 0, ceil_div(P->nobs, CAM_THREADS), 4);
             ba_camera_kernel<<<blocks, CAM_THREADS, 0, ctx->stream>>>(v, ceil_div(P->nobs, blocks)); SFM_LAUNCH_CHECK(ctx);
         }
@@ -1423,6 +1337,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     add(8 * n); add(24 * (size_t)np); add(8 * PTB * (size_t)np); add(8 * (P->red_n + 32));
     add(8 * (size_t)P->npad * P->npad); add(8 * n); add(8 * (size_t)P->npad); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
     add(4 * (size_t)(P->npad / NB) * (P->npad / NB)); add(8 * (size_t)P->npad * NB); add(4 * (size_t)(P->npad / NB)); add(sizeof(LMState));
+    add(4 * (size_t)nobs); add((size_t)nobs); add(8 * 4 * (size_t)ctx->sm_count * 32); add(16 * (size_t)(nc + 1)); add(64);   // cm_obs, cm_np, part4, fpart, counters
     if (!ctx->ba_ws.in_use) {           // borrow the cached workspace (grown below when too small)
         P->mem = ctx->ba_ws.mem; P->gmem = ctx->ba_ws.gmem; P->xbuf = ctx->ba_ws.xbuf; P->hpin = ctx->ba_ws.hpin;
         ctx->ba_ws.mem = DevBuf(); ctx->ba_ws.gmem = DevBuf(); ctx->ba_ws.xbuf = DevBuf(); ctx->ba_ws.hpin = PinBuf();
@@ -1453,6 +1368,8 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->xflags = (unsigned long long*)(P->red + P->red_n + 24);
     P->A = cv.take<double>((size_t)P->npad * P->npad); P->y_cf = cv.take<double>(n); P->dinv = cv.take<double>(P->npad);
     int32_t* obs_pt = cv.take<int32_t>(nobs); int* cnt = cv.take<int>(2 * (size_t)(nc + 1)); int* cursor = cnt + nc + 1;
+    P->obs_pt = obs_pt; P->cm_obs = cv.take<int32_t>(nobs); P->cm_np = cv.take<uint8_t>(nobs);
+    P->part4 = cv.take<double>(4 * (size_t)ctx->sm_count * 32); P->fpart = cv.take<double>(2 * (size_t)(nc + 1)); P->counters = cv.take<unsigned>(16);
     P->chol_ready = cv.take<unsigned>((size_t)(P->npad / NB) * (P->npad / NB));
     P->Linv = cv.take<double>((size_t)P->npad * NB);
     P->chol_progress = cv.take<unsigned>((size_t)(P->npad / NB));
@@ -1504,48 +1421,65 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
             CRT(cudaFuncSetAttribute(chol_backsolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs));
         }
     }
+    CRT(cudaMemsetAsync(P->counters, 0, 64, st));
+    {   // mode: "row" (default: ba_row_kernel, deterministic) needs the block row of a camera (288 bytes per camera) in shared
+        // memory and the stable sort's per-warp counters; "red" (SFMB200_BA_SCHUR=red, or too many cameras) uses atomics
+        const char* mode = getenv("SFMB200_BA_SCHUR");
+        P->row_smem = row_smem_bytes(nc);
+        P->gather = !(mode && strcmp(mode, "red") == 0) && P->row_smem <= 110 * 1024 && (size_t)CMS_WARPS * nc * 4 <= 160 * 1024;
+    }
     if (nobs) {
+        expand_obs_pt_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, np, obs_pt);
+        ctx->launches += 1;
+    }
+    if (nobs && P->gather) {
+        // stable counting sort by camera (no arrival-order atomics): per-CTA histograms, per-camera scan over the CTAs, scatter
+        const int ncta = ceil_div(nobs, CMS_THREADS);
+        const size_t hist_bytes = Carver::pad(4 * (size_t)ncta * nc);
+        const size_t smem = sizeof(int) * (size_t)CMS_WARPS * nc;
+        // row-kernel geometry: one balanced wave of slices; partial records (slices + cameras)
+        if (P->row_smem > 48 * 1024) {
+            CRT(cudaFuncSetAttribute(ba_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->row_smem));
+            CRT(cudaFuncSetAttribute(ba_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->row_smem));
+        }
+        if (smem > 48 * 1024) {
+            CRT(cudaFuncSetAttribute(cm_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CRT(cudaFuncSetAttribute(cm_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        int per_sm = 0;
+        CRT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_row_kernel<false>, ROW_THREADS, P->row_smem));
+        const char* gm2 = getenv("SFMB200_BA_ROW_CTAS");
+        if (gm2 && atoi(gm2) > 0) per_sm = atoi(gm2);
+        P->row_grid = std::max(1, std::min(ceil_div(nobs, ROW_THREADS), std::max(1, per_sm) * ctx->sm_count));
+        P->row_per_cta = ceil_div(nobs, P->row_grid);
+        P->row_grid = ceil_div(nobs, P->row_per_cta);
+        P->row_rec_stride = ROW_HDR + 36 * nc;
+        const size_t part_bytes = Carver::pad(8 * (size_t)(P->row_grid + nc) * P->row_rec_stride);
+        const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + part_bytes + hist_bytes + 4096;
+        CRT(P->gmem.reserve(gb));
+        Carver gc(P->gmem.p);
+        P->Zbuf = gc.take<double>(18 * (size_t)nobs);
+        P->row_part = gc.take<double>((size_t)(P->row_grid + nc) * P->row_rec_stride);
+        int* hist = gc.take<int>((size_t)ncta * nc);
+        cm_sort_kernel<false><<<ncta, CMS_THREADS, smem, st>>>(P->obs_cam, P->obs_xy, obs_pt, P->pt_off, nobs, nc, hist, nullptr, nullptr, nullptr, nullptr, nullptr);
+        cm_scan_ctas_kernel<<<nc, 1024, 0, st>>>(hist, ncta, nc, cnt);
+        scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor);
+        cm_sort_kernel<true><<<ncta, CMS_THREADS, smem, st>>>(P->obs_cam, P->obs_xy, obs_pt, P->pt_off, nobs, nc, hist, P->cm_off, P->cm_xy, P->cm_pt, P->cm_obs, P->cm_np);
+        ctx->launches += 4;
+    } else if (nobs) {
         const int use_smem = (size_t)nc * 8 <= 40 * 1024;
         count_cams_kernel<<<ceil_div(nobs, SORT_THREADS), SORT_THREADS, use_smem ? nc * 4 : 0, st>>>(P->obs_cam, nobs, nc, use_smem, cnt);
         scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor);
-        expand_obs_pt_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, np, obs_pt);
         scatter_cm_kernel<<<ceil_div(nobs, SORT_THREADS), SORT_THREADS, use_smem ? nc * 8 : 0, st>>>(P->obs_cam, P->obs_xy, obs_pt, nobs, nc, use_smem, cursor, P->cm_xy, P->cm_pt);
-        ctx->launches += 4;
+        ctx->launches += 3;
     } else {
         scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor); ctx->launches += 1;
     }
     CRT(cudaGetLastError());
     CRT(P->hpin.reserve(sizeof(double) * 32 + sizeof(LMState))); P->h_scal = (double*)P->hpin.p; P->h_state = (LMState*)(P->h_scal + 32);
-    {   // off-diagonal Schur blocks: "gather" (default; per-camera-pair lists, no atomics in the hot loop) or "red"
-        const char* mode = getenv("SFMB200_BA_SCHUR");
-        P->gather = !(mode && strcmp(mode, "red") == 0);
-        const long long E = pair_entries;          // observation pairs of a point, counted by the validation sweep
-        if (E >= (1LL << 31) - 1024) P->gather = false;          // int32 offsets
-        if (P->gather && E > 0) {
-            // point-range segments: ~24 MB of Zbuf each, so that one segment stays L2-resident while it is read ~7 times
-            const int nseg = (int)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (24LL << 20) - 1) / (24LL << 20)));
-            const size_t nkeys = nblk * (size_t)nseg;
-            const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + Carver::pad(4 * (nkeys + 1)) + Carver::pad(4 * (nblk + 1)) + Carver::pad(8 * (size_t)E) +
-                              Carver::pad(4 * nkeys) * 2 + 4096;
-            CRT(P->gmem.reserve(gb));
-            Carver gc(P->gmem.p);
-            P->Zbuf = gc.take<double>(18 * (size_t)nobs); P->pair_off = gc.take<int32_t>(nkeys + 1); P->pair_blk = gc.take<int32_t>(nblk + 1);
-            P->pair_ent = gc.take<uint2>((size_t)E);
-            int* pcnt = gc.take<int>(nkeys); int* pcur = gc.take<int>(nkeys); int* d_nne = gc.take<int>(4);
-            CRT(cudaMemsetAsync(pcnt, 0, 4 * nkeys, st));
-            pair_count_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, P->obs_cam, np, nc, nseg, pcnt);
-            pair_scan_kernel<<<1, 1024, 0, st>>>(pcnt, (int)nkeys, P->pair_off, pcur);
-            pair_compact_kernel<<<1, 1024, 0, st>>>(P->pair_off, (int)nblk, nseg, P->pair_blk, d_nne);
-            pair_fill_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, P->obs_cam, np, nc, nseg, pcur, P->pair_ent);
-            ctx->launches += 4;
-            CRT(cudaGetLastError());
-            int nne = 0;
-            CRT(cudaMemcpyAsync(&nne, d_nne, 4, cudaMemcpyDeviceToHost, st));
-            CRT(cudaStreamSynchronize(st));
-            P->n_pairs_nonempty = nne; P->pair_nseg = nseg;
-            P->pair_splits = std::max(1, std::min(64, ceil_div(16 * ctx->sm_count, std::max(1, nne))));
-        } else if (P->gather) {
-            CRT(P->gmem.reserve(Carver::pad(8 * 18 * (size_t)std::max(nobs, 1)) + 256));
+    {
+        if (P->gather && !P->Zbuf) {     // no observations: a dummy Z buffer keeps the kernels' pointers valid
+            CRT(P->gmem.reserve(Carver::pad(8 * 18) + 256));
             P->Zbuf = (double*)P->gmem.p;
         }
         const char* bm = getenv("SFMB200_BA_BACKSUB");
@@ -1732,7 +1666,7 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
                 if (cudaEventElapsedTime(&ms, es.ev[4], es.ev[5]) == cudaSuccess) sum->solve_ms_total += ms;
                 if (P->np > 0 && P->nobs > 0) {
                     if (cudaEventElapsedTime(&ms, es.ev[0], es.ev[1]) == cudaSuccess) { sum->schur_ms_total += ms; sum->schur_launches++; }
-                    if (P->gather && P->n_pairs_nonempty > 0 && cudaEventElapsedTime(&ms, es.ev[1], es.ev[2]) == cudaSuccess) { sum->pair_ms_total += ms; sum->pair_launches++; }
+                    if (P->gather && cudaEventElapsedTime(&ms, es.ev[1], es.ev[2]) == cudaSuccess) { sum->pair_ms_total += ms; sum->pair_launches++; }
                     if (cudaEventElapsedTime(&ms, es.ev[2], es.ev[3]) == cudaSuccess) sum->camera_ms_total += ms;
                 }
             }
