@@ -432,7 +432,12 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 // and walks the cameras its slice touches.  Per camera: diagonal block, camera-focal column, rhs, gradient and J^T J
 // diagonal, all in registers; one reduction per (CTA, camera).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int per_cta) {
+// DET: instead of accumulating into the reduced system with atomics, every (slice, camera) segment stores ONE partial record
+// (cam_part[(slice + camera)][CAM_REC]); ba_combine_kernel adds the records of a camera in slice order (row mode: bitwise
+// reproducible).  NORM_ONLY (DET only): just the squared column norms of the UNSCALED Jacobian (Jacobi scaling at x0).
+constexpr int CAM_REC = 64;      // [0,36) diagonal block (full), [36,42) camera-focal, [42,48) rhs, [48,54) gradient, [54,60) diag J^T J, 60 Jf^T Jf, 61 Jf^T r
+template <bool DET, bool NORM_ONLY>
+__global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int per_cta, double* __restrict__ cam_part) {
     const LMX x = lm_x(v);
     if (!x.run) return;
     const int start = blockIdx.x * per_cta, stop = min(v.nobs, start + per_cta);
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (v.cm_off[mid] <= start) lo = mid; else hi = mid - 1; }
         c = lo;
     }
-    const double f = *x.focal, sf = v.scale_cf[6 * v.nc];
+    const double f = *x.focal, sf = NORM_ONLY ? 1.0 : v.scale_cf[6 * v.nc];
     __shared__ double red[CAM_THREADS / 32][48];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (; c < v.nc && v.cm_off[c] < stop; ++c) {
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
     const CamDerived d = x.camd[c];
     double sc[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) sc[a] = v.scale_cf[6 * c + a];
+    for (int a = 0; a < 6; ++a) sc[a] = NORM_ONLY ? 1.0 : v.scale_cf[6 * c + a];
     // accumulators: A[21] diag block (upper), C[6] cam-focal, R[6] rhs, Gd[6] gradient, D[6] diag, ff, gf
     double A[21], Cf[6], R[6], Gd[6], D[6], ff = 0, gf = 0;
 #pragma unroll
@@ -462,11 +467,19 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
     for (int i = begin + threadIdx.x; i < end; i += CAM_THREADS) {
         const int p = v.cm_pt[i];
         const double X[3] = {x.pts[3 * p], x.pts[3 * p + 1], x.pts[3 * p + 2]};
+        ObsJ J;
+        if (NORM_ONLY) {
+            const double one[3] = {1.0, 1.0, 1.0};
+            eval_scaled(d, X, f, v.cm_xy[i], sc, one, 1.0, J);
+            ff += J.Jf[0] * J.Jf[0] + J.Jf[1] * J.Jf[1];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) D[a] += J.Jc[a] * J.Jc[a] + J.Jc[6 + a] * J.Jc[6 + a];
+            continue;
+        }
         const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
         const double* pb = v.ptblk + (size_t)p * PTB;
         const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
         const double zg[3] = {pb[6], pb[7], pb[8]}, zf[3] = {pb[9], pb[10], pb[11]};
-        ObsJ J;
         eval_scaled(d, X, f, v.cm_xy[i], sc, sp, sf, J);
         ff += J.Jf[0] * J.Jf[0] + J.Jf[1] * J.Jf[1];
         gf += J.Jf[0] * J.r[0] + J.Jf[1] * J.r[1];
@@ -503,7 +516,13 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
         double s = 0;
         for (int w = 0; w < CAM_THREADS / 32; ++w) s += red[w][threadIdx.x];
         const int t = threadIdx.x, fidx = 6 * v.nc;
-        if (t < 21) {
+        if (DET) {
+            double* rec = cam_part + (size_t)(blockIdx.x + c) * CAM_REC;
+            if (t < 21) {
+                int a = 0, rem = t; while (rem >= 6 - a) { rem -= 6 - a; ++a; } const int b = a + rem;
+                rec[a * 6 + b] = s; rec[b * 6 + a] = s;
+            } else rec[36 + (t - 21)] = s;           // 21..26 -> 36..41, 27..32 -> 42..47, 33..38 -> 48..53, 39..44 -> 54..59, 45 -> 60, 46 -> 61
+        } else if (t < 21) {
             // upper-triangular index t -> (a,b); write both halves of the (symmetric) diagonal block
             int a = 0, rem = t; while (rem >= 6 - a) { rem -= 6 - a; ++a; } const int b = a + rem;
             double* blk = v.Sblk + blk_index(c, c, v.nc) * 36;
@@ -1013,7 +1032,9 @@ struct sfmb200_ba_problem {
     bool gather = true;               // true = row mode (ba_row_kernel), false = "red" mode
     double* Zbuf = nullptr;
     int32_t* obs_pt = nullptr; int32_t* cm_obs = nullptr; uint8_t* cm_np = nullptr;
-    double* row_part = nullptr; int row_grid = 0, row_per_cta = 0, row_rec_stride = 0; size_t row_smem = 0;
+    double* diag_part = nullptr; int diag_grid = 0, diag_per_cta = 0;
+    int32_t* pair_off = nullptr; int32_t* pair_blk = nullptr; uint2* pair_ent = nullptr; double* pair_part = nullptr;
+    int n_pairs_nonempty = 0, pair_splits = 1, pair_nseg = 1;
     double* part4 = nullptr; double* fpart = nullptr; unsigned* counters = nullptr;
     DevBuf gmem;
     // exchange memory (its own cudaMalloc so that it can be exported with CUDA IPC): red | post.. | flags
@@ -1047,7 +1068,9 @@ static BAView make_view(const sfmb200_ba_problem* P, const sfmb200_ba_options* o
 }
 
 static RowArgs make_row_args(const sfmb200_ba_problem* P) {
-    RowArgs ra; ra.cm_obs = P->cm_obs; ra.cm_np = P->cm_np; ra.per_cta = P->row_per_cta; ra.part = P->row_part; ra.rec_stride = P->row_rec_stride;
+    RowArgs ra; ra.diag_per_cta = P->diag_per_cta; ra.diag_part = P->diag_part;
+    ra.pair_off = P->pair_off; ra.pair_part = P->pair_part; ra.nseg = P->pair_nseg; ra.splits = P->pair_splits;
+    ra.pair_blk = P->pair_blk; ra.n_nonempty = P->n_pairs_nonempty;
     return ra;
 }
 
@@ -1171,8 +1194,8 @@ static int compute_scaling(sfmb200_ba_problem* P, const sfmb200_ba_options* opt)
         int rc = DISPATCH_G(P, launch_point_norm)(P, v); if (rc) return rc;
         if (P->gather) {                 // deterministic: partial records per (slice, camera), summed in slice order
             const RowArgs ra = make_row_args(P);
-            ba_row_kernel<true><<<P->row_grid, ROW_THREADS, P->row_smem, ctx->stream>>>(v, ra); SFM_LAUNCH_CHECK(ctx);
-            ba_combine_kernel<<<P->nc, 256, 0, ctx->stream>>>(v, ra, 1, colnorm, P->fpart, P->counters + 2); SFM_LAUNCH_CHECK(ctx);
+            ba_camera_kernel<true, true><<<P->diag_grid, CAM_THREADS, 0, ctx->stream>>>(v, P->diag_per_cta, P->diag_part); SFM_LAUNCH_CHECK(ctx);
+            ba_combine_kernel<<<P->nc, COMBINE_THREADS, 0, ctx->stream>>>(v, ra, 1, colnorm, P->fpart, P->counters + 2); SFM_LAUNCH_CHECK(ctx);
         } else {
             ba_camera_norm_kernel<<<camera_grid(P), CAM_THREADS, 0, ctx->stream>>>(v, colnorm); SFM_LAUNCH_CHECK(ctx);
         }
@@ -1204,13 +1227,18 @@ static int schur_pass(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, doub
         if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[1], ctx->stream));
         if (row) {
             const RowArgs ra = make_row_args(P);
-            ba_row_kernel<false><<<P->row_grid, ROW_THREADS, P->row_smem, ctx->stream>>>(v, ra); SFM_LAUNCH_CHECK(ctx);
+            if (P->n_pairs_nonempty > 0) {
+                ba_pair_kernel<<<dim3(ceil_div(P->n_pairs_nonempty, PAIR_WARPS), P->pair_nseg * P->pair_splits), PAIR_WARPS * 32, 0, ctx->stream>>>(
+                    P->Zbuf, P->pair_off, P->pair_ent, P->n_pairs_nonempty, P->pair_nseg, P->pair_splits, P->pair_blk, P->pair_part, v.st);
+                SFM_LAUNCH_CHECK(ctx);
+            }
             if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[2], ctx->stream));
-            ba_combine_kernel<<<P->nc, 256, 0, ctx->stream>>>(v, ra, 0, nullptr, P->fpart, P->counters + 2); SFM_LAUNCH_CHECK(ctx);
+            ba_camera_kernel<true, false><<<P->diag_grid, CAM_THREADS, 0, ctx->stream>>>(v, P->diag_per_cta, P->diag_part); SFM_LAUNCH_CHECK(ctx);
+            ba_combine_kernel<<<P->nc + ceil_div(P->n_pairs_nonempty, COMBINE_THREADS / 32), COMBINE_THREADS, 0, ctx->stream>>>(v, ra, 0, nullptr, P->fpart, P->counters + 2); SFM_LAUNCH_CHECK(ctx);
         } else {
             if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[2], ctx->stream));
-            const int blocks = resident_grid(P, &P->grid_camera, ba_camera_kernel, CAM_THREADS, 0, ceil_div(P->nobs, CAM_THREADS), 4);
-            ba_camera_kernel<<<blocks, CAM_THREADS, 0, ctx->stream>>>(v, ceil_div(P->nobs, blocks)); SFM_LAUNCH_CHECK(ctx);
+            const int blocks = resident_grid(P, &P->grid_camera, ba_camera_kernel<false, false>, CAM_THREADS, 0, ceil_div(P->nobs, CAM_THREADS), 4);
+            ba_camera_kernel<false, false><<<blocks, CAM_THREADS, 0, ctx->stream>>>(v, ceil_div(P->nobs, blocks), nullptr); SFM_LAUNCH_CHECK(ctx);
         }
         if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[3], ctx->stream));
     }
@@ -1425,8 +1453,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     {   // mode: "row" (default: ba_row_kernel, deterministic) needs the block row of a camera (288 bytes per camera) in shared
         // memory and the stable sort's per-warp counters; "red" (SFMB200_BA_SCHUR=red, or too many cameras) uses atomics
         const char* mode = getenv("SFMB200_BA_SCHUR");
-        P->row_smem = row_smem_bytes(nc);
-        P->gather = !(mode && strcmp(mode, "red") == 0) && P->row_smem <= 110 * 1024 && (size_t)CMS_WARPS * nc * 4 <= 160 * 1024;
+        P->gather = !(mode && strcmp(mode, "red") == 0) && (size_t)(2 * PFILL_WARPS + 1) * nc * 4 <= 160 * 1024 && pair_entries < (1LL << 31) - 1024;
     }
     if (nobs) {
         expand_obs_pt_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, np, obs_pt);
@@ -1437,35 +1464,60 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         const int ncta = ceil_div(nobs, CMS_THREADS);
         const size_t hist_bytes = Carver::pad(4 * (size_t)ncta * nc);
         const size_t smem = sizeof(int) * (size_t)CMS_WARPS * nc;
-        // row-kernel geometry: one balanced wave of slices; partial records (slices + cameras)
-        if (P->row_smem > 48 * 1024) {
-            CRT(cudaFuncSetAttribute(ba_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->row_smem));
-            CRT(cudaFuncSetAttribute(ba_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->row_smem));
-        }
+        // geometry of the camera-major kernel: one balanced wave of slices; partial records (slices + cameras)
+        const size_t fill_smem = sizeof(int) * (size_t)(2 * PFILL_WARPS + 1) * nc;
         if (smem > 48 * 1024) {
             CRT(cudaFuncSetAttribute(cm_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CRT(cudaFuncSetAttribute(cm_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        int per_sm = 0;
-        CRT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_row_kernel<false>, ROW_THREADS, P->row_smem));
-        const char* gm2 = getenv("SFMB200_BA_ROW_CTAS");
-        if (gm2 && atoi(gm2) > 0) per_sm = atoi(gm2);
-        P->row_grid = std::max(1, std::min(ceil_div(nobs, ROW_THREADS), std::max(1, per_sm) * ctx->sm_count));
-        P->row_per_cta = ceil_div(nobs, P->row_grid);
-        P->row_grid = ceil_div(nobs, P->row_per_cta);
-        P->row_rec_stride = ROW_HDR + 36 * nc;
-        const size_t part_bytes = Carver::pad(8 * (size_t)(P->row_grid + nc) * P->row_rec_stride);
-        const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + part_bytes + hist_bytes + 4096;
+        if (fill_smem > 48 * 1024) CRT(cudaFuncSetAttribute(pair_fill_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+        {
+            int per_sm = 0;
+            CRT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_camera_kernel<true, false>, CAM_THREADS, 0));
+            P->diag_grid = std::max(1, std::min(ceil_div(nobs, CAM_THREADS), std::max(1, per_sm) * ctx->sm_count));
+            P->diag_per_cta = ceil_div(nobs, P->diag_grid);
+            P->diag_grid = ceil_div(nobs, P->diag_per_cta);
+        }
+        // off-diagonal blocks: per-(camera pair, point segment) entry lists, ~24 MB of Zbuf per segment so that one segment stays
+        // L2-resident while it is read ~7 times; one partial block per (pair, segment, split) warp
+        const long long E = pair_entries;           // observation pairs of a point, counted by the validation sweep
+        const int nseg = (int)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (24LL << 20) - 1) / (24LL << 20)));
+        const size_t nkeys = nblk * (size_t)nseg;
+        // splits are fixed before the lists exist (they size the partial buffer): assume every pair is non-empty
+        P->pair_nseg = nseg;
+        P->pair_splits = std::max(1, std::min(64, ceil_div(16 * ctx->sm_count, (int)std::max<size_t>(1, nblk - nc))));
+        const size_t part_bytes = Carver::pad(8 * (size_t)(P->diag_grid + nc) * ROW_HDR) + Carver::pad(8 * 36 * nkeys * P->pair_splits);
+        const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + part_bytes + hist_bytes + Carver::pad(4 * (nkeys + 1)) + Carver::pad(4 * (nblk + 1)) +
+                          Carver::pad(8 * (size_t)std::max<long long>(E, 1)) + Carver::pad(4 * nkeys) * 2 + 8192;
         CRT(P->gmem.reserve(gb));
         Carver gc(P->gmem.p);
         P->Zbuf = gc.take<double>(18 * (size_t)nobs);
-        P->row_part = gc.take<double>((size_t)(P->row_grid + nc) * P->row_rec_stride);
+        P->diag_part = gc.take<double>((size_t)(P->diag_grid + nc) * ROW_HDR);
+        P->pair_part = gc.take<double>(36 * nkeys * P->pair_splits);
+        P->pair_off = gc.take<int32_t>(nkeys + 1); P->pair_blk = gc.take<int32_t>(nblk + 1);
+        P->pair_ent = gc.take<uint2>((size_t)std::max<long long>(E, 1));
+        int* pcnt = gc.take<int>(nkeys); int* pcur = gc.take<int>(nkeys); int* d_nne = gc.take<int>(4);
         int* hist = gc.take<int>((size_t)ncta * nc);
         cm_sort_kernel<false><<<ncta, CMS_THREADS, smem, st>>>(P->obs_cam, P->obs_xy, obs_pt, P->pt_off, nobs, nc, hist, nullptr, nullptr, nullptr, nullptr, nullptr);
         cm_scan_ctas_kernel<<<nc, 1024, 0, st>>>(hist, ncta, nc, cnt);
         scan_small_kernel<<<1, 32, 0, st>>>(cnt, nc, P->cm_off, cursor);
         cm_sort_kernel<true><<<ncta, CMS_THREADS, smem, st>>>(P->obs_cam, P->obs_xy, obs_pt, P->pt_off, nobs, nc, hist, P->cm_off, P->cm_xy, P->cm_pt, P->cm_obs, P->cm_np);
         ctx->launches += 4;
+        if (E > 0) {
+            CRT(cudaMemsetAsync(pcnt, 0, 4 * nkeys, st));
+            pair_count_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, P->obs_cam, np, nc, nseg, pcnt);
+            pair_scan_kernel<<<1, 1024, 0, st>>>(pcnt, (int)nkeys, P->pair_off, pcur);
+            pair_compact_kernel<<<1, 1024, 0, st>>>(P->pair_off, (int)nblk, nseg, P->pair_blk, d_nne);
+            pair_fill_sorted_kernel<<<nc, PFILL_THREADS, fill_smem, st>>>(P->cm_off, P->cm_obs, P->cm_np, P->obs_cam, nc, nseg, P->pair_off, P->pair_ent);
+            ctx->launches += 4;
+            CRT(cudaGetLastError());
+            int nne = 0;
+            CRT(cudaMemcpyAsync(&nne, d_nne, 4, cudaMemcpyDeviceToHost, st));
+            CRT(cudaStreamSynchronize(st));
+            P->n_pairs_nonempty = nne;
+        } else {
+            CRT(cudaMemsetAsync(P->pair_off, 0, 4 * (nkeys + 1), st));
+        }
     } else if (nobs) {
         const int use_smem = (size_t)nc * 8 <= 40 * 1024;
         count_cams_kernel<<<ceil_div(nobs, SORT_THREADS), SORT_THREADS, use_smem ? nc * 4 : 0, st>>>(P->obs_cam, nobs, nc, use_smem, cnt);
@@ -1500,7 +1552,7 @@ void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     cudaSetDevice(P->ctx->device);
     cudaStreamSynchronize(P->ctx->stream);
     for (int k = 0; k < LM_CHUNK; ++k) for (int e = 0; e < 8; ++e) if (P->evs[k].ev[e]) cudaEventDestroy(P->evs[k].ev[e]);
-    for (int r = 0; r < MAX_PEERS; ++r) if (P->peer_base[r]) cudaIpcCloseMemHandle(P->peer_base[r]);
+    // peer mappings stay open in the context's cache (ctx->ipc_cache) for the next problem; closed with the context
     ba_release_buffers(P);
     delete P;
 }
@@ -1540,20 +1592,35 @@ int sfmb200_ba_problem_ipc_handle(sfmb200_ba_problem* P, uint8_t* out) {
     return SFMB200_OK;
 }
 
+static int ba_attach_handles(sfmb200_ba_problem* P, const uint8_t* handles);
+
 int sfmb200_ba_problem_ipc_attach(sfmb200_ba_problem* P, const uint8_t* handles) {
     if (!P) return SFMB200_ERR_INVALID;
     sfmb200_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ba_attach_handles(P, handles);
+}
+
+}  // extern "C"
+
+static int ba_attach_handles(sfmb200_ba_problem* P, const uint8_t* handles) {
+    sfmb200_ctx* ctx = P->ctx;
     if (ctx->nranks <= 1) return SFMB200_OK;
     if (!handles) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "handles required");
     if (ctx->nranks > MAX_PEERS) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "at most %d ranks", MAX_PEERS);
     for (int r = 0; r < ctx->nranks; ++r) {
         void* base = P->xmem;
         if (r != ctx->rank) {
-            cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)r * SFMB200_IPC_HANDLE_BYTES, sizeof h);
-            cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) return sfmb200_fail(ctx, SFMB200_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+            std::array<uint8_t, 64> key; memcpy(key.data(), handles + (size_t)r * SFMB200_IPC_HANDLE_BYTES, 64);
+            base = nullptr;
+            for (auto& e : ctx->ipc_cache) if (e.first == key) { base = e.second; break; }
+            if (!base) {
+                cudaIpcMemHandle_t h; memcpy(&h, key.data(), sizeof h);
+                cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) return sfmb200_fail(ctx, SFMB200_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+                ctx->ipc_cache.push_back({key, base});
+            }
             P->peer_base[r] = base;
         }
         P->ptab.buf[r] = (double*)base;
@@ -1562,6 +1629,30 @@ int sfmb200_ba_problem_ipc_attach(sfmb200_ba_problem* P, const uint8_t* handles)
     P->peers = true;
     return SFMB200_OK;
 }
+
+// The one-shot solve attaches its peers itself: export this problem's exchange buffer, all-gather the 64-byte CUDA-IPC handles
+// over the library's NCCL communicator (the only NCCL call of the solve), map the peers (mappings are cached in the context).
+// SFMB200_EXCHANGE=nccl keeps the NCCL all-reduce data path.  ctx->mu is held.
+static int ba_auto_attach(sfmb200_ba_problem* P) {
+    sfmb200_ctx* ctx = P->ctx;
+    if (ctx->nranks <= 1 || P->peers) return SFMB200_OK;
+    const char* ex = getenv("SFMB200_EXCHANGE");
+    if (ex && strcmp(ex, "nccl") == 0) return SFMB200_OK;
+    if (ctx->nranks > MAX_PEERS) return SFMB200_OK;
+    cudaIpcMemHandle_t h;
+    SFM_CUDA(ctx, cudaIpcGetMemHandle(&h, P->xmem));
+    const size_t nb = SFMB200_IPC_HANDLE_BYTES;
+    SFM_CUDA(ctx, ctx->scratch.reserve(nb * (ctx->nranks + 1) + 256));
+    uint8_t* d_send = (uint8_t*)ctx->scratch.p; uint8_t* d_recv = d_send + 256;
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_send, &h, nb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = sfmb200_allgather_bytes(ctx, d_send, d_recv, nb); if (rc) return rc;
+    std::vector<uint8_t> all(nb * ctx->nranks);
+    SFM_CUDA(ctx, cudaMemcpyAsync(all.data(), d_recv, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ba_attach_handles(P, all.data());
+}
+
+extern "C" {
 
 int sfmb200_ba_problem_reduced_system(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_in, double radius,
                                       double* S, double* rhs, double* grad_cf, double* cost) {
@@ -1625,9 +1716,16 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
     if (const char* ce = getenv("SFMB200_BA_CHUNK")) chunk = std::max(1, std::min(LM_CHUNK, atoi(ce)));
     bool timed_out = false;
     int executed = 0;
+    // Multi-GPU: every rank must enqueue the SAME sequence of exchanges, so nothing rank-local may decide when the loop stops.
+    // The LM decisions are identical by construction (rank-summed inputs); the wall-clock limit is not -- each rank's flag
+    // "my clock says stop" is max-reduced over the ranks at the end of every chunk and all ranks act on the result.  The chunk
+    // size must be the same everywhere too: options (verbose) must match across ranks, the environment override is ignored.
+    const bool collective_clock = ctx->nranks > 1 && opt.max_solver_time_in_seconds > 0;
+    if (ctx->nranks > 1) chunk = opt.verbose ? 1 : LM_CHUNK;
+    double* tflag = P->post + 8;      // one of the pad doubles behind post[8] in the exchange buffer
 
     for (;;) {
-        if (executed > 0 && opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { timed_out = true; break; }
+        if (!collective_clock && executed > 0 && opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { timed_out = true; break; }
         const int n_it = std::max(1, std::min(chunk, opt.max_num_iterations - hs->iter));
         for (int k = 0; k < n_it; ++k) {
             const EvSet* es = opt.profile ? &P->evs[k] : nullptr;
@@ -1653,6 +1751,12 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
             rc = ba_allreduce(P, P->post, 7, 1); if (rc) return rc;   // sums: candidate cost, model, norms, failure counts; max: |g| of the points
             ba_lm_control_kernel<<<1, 32, 0, ctx->stream>>>(P->d_state, summed(P, P->sums), summed(P, P->post), P->locals, opt); SFM_LAUNCH_CHECK(ctx);
         }
+        if (collective_clock) {
+            P->h_scal[30] = elapsed() >= opt.max_solver_time_in_seconds ? 1.0 : 0.0;
+            SFM_CUDA(ctx, cudaMemcpyAsync(tflag, P->h_scal + 30, 8, cudaMemcpyHostToDevice, ctx->stream));
+            rc = ba_allreduce(P, tflag, 0, 1); if (rc) return rc;
+            SFM_CUDA(ctx, cudaMemcpyAsync(P->h_scal + 31, summed(P, tflag), 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         SFM_CUDA(ctx, cudaMemcpyAsync(hs, P->d_state, sizeof *hs, cudaMemcpyDeviceToHost, ctx->stream));
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         // iterations of this chunk that actually ran: all of them unless the solve terminated inside the chunk
@@ -1674,7 +1778,12 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
         if (opt.verbose) printf("iter %3d cost %.9e |g|max %.3e radius %.3e rho %.3e %s\n", hs->iter, hs->x_cost, hs->gmax, hs->radius, hs->last_rho,
                                 hs->status != LM_RUNNING ? "stop" : (hs->new_point ? "ok" : "rejected"));
         if (hs->status != LM_RUNNING) break;
+        if (collective_clock && P->h_scal[31] != 0.0) { timed_out = true; break; }
     }
+    // final hand-shake of the peer exchange: after it no rank reads this rank's exchange buffer any more, so the caller may
+    // destroy the problem (the buffer goes back to the workspace cache, is cleared by the next create, or is freed)
+    rc = ba_peer_barrier(P); if (rc) return rc;
+    if (P->peers) SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     P->cur = hs->cur;
     P->camd_valid[P->cur] = true; P->camd_valid[P->cur ^ 1] = false;
     sum->termination_type = hs->termination_type;
@@ -1704,6 +1813,13 @@ int sfmb200_ba_solve(sfmb200_ctx* ctx, const sfmb200_ba_options* opt, int nc, in
     sfmb200_ba_problem* P = nullptr;
     int rc = sfmb200_ba_problem_create(ctx, nc, np, nobs, cams6, pts3, *focal, obs_xy, obs_cam, pt_off, &P);
     if (rc) return rc;
+    if (ctx->nranks > 1) {            // peer-memory exchange instead of the NCCL all-reduce (collective: every rank is in this call)
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            rc = ba_auto_attach(P);
+        }
+        if (rc) { sfmb200_ba_problem_destroy(P); return rc; }
+    }
     rc = sfmb200_ba_problem_run(P, opt, summary);
     if (!rc) rc = sfmb200_ba_problem_download(P, cams6, pts3, focal);
     sfmb200_ba_problem_destroy(P);

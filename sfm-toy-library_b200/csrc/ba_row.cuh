@@ -23,238 +23,249 @@
 //     No floating-point atomics anywhere: two runs give bitwise identical results.
 #pragma once
 
-constexpr int ROW_THREADS = 128;
-constexpr int ROW_WARPS = ROW_THREADS / 32;
-constexpr int ROW_HDR = 64;                               // header doubles of a partial record (62 used)
-constexpr int ROW_ZSTRIDE = 3 * ROW_THREADS + 4;          // Zh row stride in doubles: = 4 (mod 32) -> conflict-free fragment loads
-constexpr int ROW_PLIST = 256;                            // per-warp list of owned (i, j) updates of a batch
-constexpr int ROW_UNROLL = 8;                             // updates in flight per warp
-
+constexpr int ROW_HDR = 64;                               // doubles of a camera partial record (= CAM_REC of ba_camera_kernel)
 struct RowArgs {
-    const int32_t* cm_obs;        // [nobs] point-major index o of each camera-major entry
-    const uint8_t* cm_np;         // [nobs] number of followers of o inside its point (observations by cameras > ci)
-    int per_cta;                  // camera-major entries per CTA slice
-    double* part;                 // [(grid + nc)] partial records of rec_stride doubles; record of (slice s, camera c) = s + c
-    int rec_stride;               // ROW_HDR + 36 * nc
+    int diag_per_cta;             // camera-major entries per CTA slice of the diagonal kernel
+    double* diag_part;            // [(diag grid + nc)][ROW_HDR]   record of (slice s, camera c) = s + c
+    const int32_t* pair_off;      // [nblk * nseg + 1] entry-list offsets of (camera pair, point segment)
+    const double* pair_part;      // [nblk * nseg * splits][36] partial blocks written by ba_pair_kernel
+    const int32_t* pair_blk;      // [n_nonempty] camera pairs that have entries
+    int nseg, splits, n_nonempty;
 };
 
-static inline size_t row_smem_bytes(int nc) {
-    return sizeof(double) * ((size_t)36 * nc + (size_t)ROW_THREADS * 2 * 8 + (size_t)8 * ROW_ZSTRIDE + (size_t)ROW_WARPS * 2 * 64) +
-           sizeof(int) * ((size_t)ROW_THREADS * 2 + (size_t)ROW_WARPS * ROW_PLIST * 2);
-}
-
-template <bool NORM_ONLY>
-__global__ void __launch_bounds__(ROW_THREADS) ba_row_kernel(BAView v, RowArgs ra) {
-    const LMX x = lm_x(v);
-    if (!x.run) return;
-    const int start = blockIdx.x * ra.per_cta, stop = min(v.nobs, start + ra.per_cta);
-    if (start >= stop) return;
-    extern __shared__ __align__(16) unsigned char row_smem[];
-    double* rowS = reinterpret_cast<double*>(row_smem);                     // [nc][36]: sum Z_i Z_j^T of blocks (c, cj)
-    double* Xs = rowS + (size_t)36 * v.nc;                                  // [2*ROW_THREADS][8]
-    double* Zh = Xs + (size_t)ROW_THREADS * 2 * 8;                          // [8][ROW_ZSTRIDE]
-    double* fragred = Zh + (size_t)8 * ROW_ZSTRIDE;                         // [ROW_WARPS][2][64]
-    int* meta_o = reinterpret_cast<int*>(fragred + ROW_WARPS * 2 * 64);     // [ROW_THREADS]
-    int* meta_np = meta_o + ROW_THREADS;                                    // [ROW_THREADS]
-    int2* plist = reinterpret_cast<int2*>(meta_np + ROW_THREADS);           // [ROW_WARPS][ROW_PLIST]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// ---------------------------------------------------------------------------------------------------------------
+// K3c: off-diagonal blocks without atomics.  For every camera pair (ci < cj) the list of (obs_i, obs_j)
+// index pairs of the points both cameras see is built once per problem (the structure is fixed across LM iterations).
+// One warp per (pair, split): lanes stride over the list, each accumulating a full 6x6 block  sum Z_i Z_j^T  in 36
+// registers from two 144-byte reads, then a warp shuffle reduction and 36 REDs per warp (instead of 36 per entry).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_WARPS = 4;
+// pair_off is indexed by key = blk * nseg + seg (seg = point-range segment): the grid walks the segments in the slow
+// (y) dimension, LAST segment first, so that all resident warps read the same ~24 MB slice of Zbuf -- which then lives
+// in L2 (the tail of Zbuf is still L2-resident from the point kernel that just wrote it).
+// The accumulation  S[ci,cj] -= sum_e Z_i(e) Z_j(e)^T  is a (6 x 3E)(3E x 6) product in fp64: it runs on the FP64
+// tensor pipe as one  mma.sync.m8n8k4.f64  per entry (6x6x3 padded to 8x8x4).  The operand fragments want lane l to hold
+// element (l>>2, l&3) of the 8x4 tile, i.e. double number (l>>2)*3 + (l&3) of the 18-double Z record: one coalesced
+// 8-byte load per lane per operand (18 of 32 lanes active, one 144-byte record = at most two 128-byte lines), instead
+// of 18 uncoalesced 16-byte loads per lane in a lane-per-entry SIMT formulation (which was L1-wavefront bound).
+constexpr int PAIR_UNROLL = 8;
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 8) ba_pair_kernel(const double* __restrict__ Zbuf, const int32_t* __restrict__ pair_off,
+                                                                   const uint2* __restrict__ pair_ent, int n_nonempty, int nseg, int splits,
+                                                                   const int32_t* __restrict__ pair_blk, double* __restrict__ pair_part, const LMState* __restrict__ st) {
+    if (st && st->status != LM_RUNNING) return;
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);       // index into the list of non-empty pairs
+    if (q >= n_nonempty) return;
+    const int seg = nseg - 1 - (int)(blockIdx.y / splits), sp = blockIdx.y % splits;
+    const int blk = pair_blk[q];
+    const int start = pair_off[(size_t)blk * nseg + seg], len = pair_off[(size_t)blk * nseg + seg + 1] - start;
+    const int b0 = start + (int)((long long)len * sp / splits), b1 = start + (int)((long long)len * (sp + 1) / splits);
+    if (b1 <= b0) return;
     const int fr = lane >> 2, fc = lane & 3;
-    const bool zvalid = fr < 6 && fc < 3;                                   // this lane holds an element of a 6x3 Z record
-    int c = 0;
-    {   // last camera whose list begins at or before `start`
-        int lo = 0, hi = v.nc - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (v.cm_off[mid] <= start) lo = mid; else hi = mid - 1; }
-        c = lo;
+    const bool valid = fr < 6 && fc < 3;
+    const int fidx = valid ? fr * 3 + fc : 0;
+    double c0[4], c1[4];               // 4 independent accumulator fragments
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c0[u] = 0.0; c1[u] = 0.0; }
+    // Entries arrive in batches of PAIR_UNROLL: lanes 0..7 fetch the batch's index pairs with ONE coalesced 64-byte load (a
+    // broadcast load per entry cost a wavefront each) and hand them round with shuffles; the NEXT batch's indices are
+    // requested before this batch's operands are consumed, so that the index round trip and the operand round trip of
+    // consecutive batches overlap (the kernel is latency bound: 83% long-scoreboard stalls).
+    uint2 cur = make_uint2(0u, 0u);
+    if (lane < PAIR_UNROLL && b0 + lane < b1) cur = __ldg(pair_ent + b0 + lane);
+    for (int e = b0; e < b1; e += PAIR_UNROLL) {
+        uint2 nxt = make_uint2(0u, 0u);
+        const int en = e + PAIR_UNROLL;
+        if (lane < PAIR_UNROLL && en + lane < b1) nxt = __ldg(pair_ent + en + lane);
+        double a[PAIR_UNROLL], b[PAIR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PAIR_UNROLL; ++u) {
+            const unsigned ox = __shfl_sync(0xffffffffu, cur.x, u), oy = __shfl_sync(0xffffffffu, cur.y, u);
+            const bool live = valid && e + u < b1;                     // past the end: indices are 0, operands forced to 0
+            const double va = __ldg(Zbuf + (size_t)ox * 18 + fidx), vb = __ldg(Zbuf + (size_t)oy * 18 + fidx);
+            a[u] = live ? va : 0.0; b[u] = live ? vb : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < PAIR_UNROLL; ++u) dmma_m8n8k4(c0[u & 3], c1[u & 3], a[u], b[u]);
+        cur = nxt;
     }
-    const double f = *x.focal, sf = NORM_ONLY ? 1.0 : v.scale_cf[6 * v.nc];
-    for (; c < v.nc && v.cm_off[c] < stop; ++c) {
-        const int begin = max(start, v.cm_off[c]), end = min(stop, v.cm_off[c + 1]);
-        if (begin >= end) continue;
-        const CamDerived d = x.camd[c];
-        double sc[6];
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) sc[a] = NORM_ONLY ? 1.0 : v.scale_cf[6 * c + a];
-        if (!NORM_ONLY) for (int i = 36 * (c + 1) + tid; i < 36 * v.nc; i += ROW_THREADS) rowS[i] = 0.0;
-        double dX0 = 0.0, dX1 = 0.0, dZ0 = 0.0, dZ1 = 0.0;                   // this warp's X^T X and Zh Zh^T accumulator fragments
-        for (int b0 = begin; b0 < end; b0 += ROW_THREADS) {
-            __syncthreads();                                               // previous batch fully consumed (and rowS zeroed)
-            // ---- step 1: one observation per thread: Jacobian blocks, Z_i, operands into shared memory
-            const int i = b0 + tid;
-            const bool valid = i < end;
-            int o = 0, npart = 0;
-            double xr0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xr1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            double Z[18], zfg[6] = {0, 0, 0, 0, 0, 0};
+    for (int u = 0; u < 4; ++u) { s0 += c0[u]; s1 += c1[u]; }
+    // accumulator fragment: row = lane>>2, columns 2*(lane&3) and 2*(lane&3)+1.  One partial block per (pair, segment, split):
+    // ba_combine_kernel adds them up in a fixed order (no atomics: bitwise reproducible)
+    const int cc = 2 * fc;
+    if (fr < 6 && cc < 6)
+        *reinterpret_cast<double2*>(pair_part + (((size_t)blk * nseg + seg) * splits + sp) * 36 + fr * 6 + cc) = make_double2(s0, s1);
+}
+
+// pair-list construction (once per problem): thread per point; key = blk * nseg + seg(point)
+__device__ __forceinline__ int point_segment(int p, int np, int nseg) { return (int)((long long)p * nseg / np); }
+__global__ void __launch_bounds__(256) pair_count_kernel(const int32_t* __restrict__ pt_off, const int32_t* __restrict__ obs_cam, int np, int nb,
+                                                         int nseg, int* __restrict__ cnt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const int o0 = pt_off[p], o1 = pt_off[p + 1], seg = point_segment(p, np, nseg);
+    for (int i = o0; i < o1; ++i)
+        for (int j = i + 1; j < o1; ++j) atomicAdd(cnt + (size_t)blk_index(obs_cam[i], obs_cam[j], nb) * nseg + seg, 1);
+}
+// exclusive scan of cnt[nkeys] -> pair_off[nkeys+1] and cursor[nkeys]; single CTA, chained over 1024-element chunks
+__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ cnt, int nkeys, int32_t* __restrict__ pair_off, int* __restrict__ cursor) {
+    __shared__ int wsum[32], carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < nkeys; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int c = i < nkeys ? cnt[i] : 0;
+        int s = c;
 #pragma unroll
-            for (int q = 0; q < 18; ++q) Z[q] = 0.0;
-            if (valid) {
-                const int p = v.cm_pt[i];
-                o = ra.cm_obs[i]; npart = ra.cm_np[i];
-                const double X[3] = {x.pts[3 * p], x.pts[3 * p + 1], x.pts[3 * p + 2]};
-                ObsJ J;
-                if (NORM_ONLY) {
-                    const double one[3] = {1.0, 1.0, 1.0};
-                    eval_scaled(d, X, f, v.cm_xy[i], sc, one, 1.0, J);
-                } else {
-                    const double sp[3] = {v.scale_pt[3 * p], v.scale_pt[3 * p + 1], v.scale_pt[3 * p + 2]};
-                    eval_scaled(d, X, f, v.cm_xy[i], sc, sp, sf, J);
-                    const double* pb = v.ptblk + (size_t)p * PTB;
-                    const double M[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]};
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) zfg[q] = pb[6 + q];          // zg (3), zf (3)
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) {
-                        const double w0 = J.Jc[a] * J.Jp[0] + J.Jc[6 + a] * J.Jp[3], w1 = J.Jc[a] * J.Jp[1] + J.Jc[6 + a] * J.Jp[4],
-                                     w2 = J.Jc[a] * J.Jp[2] + J.Jc[6 + a] * J.Jp[5];
-                        Z[a * 3] = w0 * M[0]; Z[a * 3 + 1] = w0 * M[1] + w1 * M[2]; Z[a * 3 + 2] = w0 * M[3] + w1 * M[4] + w2 * M[5];
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < 6; ++a) { xr0[a] = J.Jc[a]; xr1[a] = J.Jc[6 + a]; }
-                xr0[6] = J.Jf[0]; xr1[6] = J.Jf[1]; xr0[7] = J.r[0]; xr1[7] = J.r[1];
-            }
-            {
-                double2* xd = reinterpret_cast<double2*>(Xs + (size_t)tid * 16);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { xd[q] = make_double2(xr0[2 * q], xr0[2 * q + 1]); xd[4 + q] = make_double2(xr1[2 * q], xr1[2 * q + 1]); }
-            }
-            if (!NORM_ONLY) {
-#pragma unroll
-                for (int a = 0; a < 6; ++a)
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) Zh[a * ROW_ZSTRIDE + 3 * tid + b] = Z[a * 3 + b];
-#pragma unroll
-                for (int b = 0; b < 3; ++b) { Zh[6 * ROW_ZSTRIDE + 3 * tid + b] = zfg[3 + b]; Zh[7 * ROW_ZSTRIDE + 3 * tid + b] = zfg[b]; }
-                meta_o[tid] = o; meta_np[tid] = npart;
-            }
-            __syncthreads();
-            // ---- step 2: diagonal terms of this warp's 32 observations on the FP64 tensor pipe.  A (m8 x k4, row) wants lane l
-            // to hold A[l>>2][l&3], B (k4 x n8, col) B[l&3][l>>2]: for X^T X and Zh Zh^T both are the SAME value.
-            {
-                const double* xw = Xs + (size_t)warp * 64 * 8;
-#pragma unroll
-                for (int t = 0; t < 16; ++t) { const double xv = xw[(4 * t + fc) * 8 + fr]; dmma_m8n8k4(dX0, dX1, xv, xv); }
-                if (!NORM_ONLY) {
-                    const double* zw = Zh + (size_t)fr * ROW_ZSTRIDE + 96 * warp + fc;
-#pragma unroll
-                    for (int t = 0; t < 24; ++t) { const double zv = zw[4 * t]; dmma_m8n8k4(dZ0, dZ1, zv, zv); }
-                }
-            }
-            if (NORM_ONLY) continue;
-            // ---- step 3: off-diagonal row blocks.  Every warp scans the batch's 128 observations and collects the updates whose
-            // partner camera it owns (cj mod 4 == warp) in (group, follower index, lane) order -- a fixed order; then processes
-            // the list ROW_UNROLL at a time: operand loads first (a: Z_i from shared memory, b: Z_j from the point-major buffer,
-            // 18 lanes x 8 bytes of one contiguous record), then the DMMAs, then the read-modify-writes of the owned blocks.
-            int2* mylist = plist + warp * ROW_PLIST;
-            int nlist = 0;
-            auto flush = [&]() {
-                for (int s = 0; s < nlist; s += ROW_UNROLL) {
-                    double a[ROW_UNROLL], b[ROW_UNROLL];
-                    int cjs[ROW_UNROLL];
-#pragma unroll
-                    for (int u = 0; u < ROW_UNROLL; ++u) {
-                        const bool live = s + u < nlist;
-                        const int2 en = mylist[live ? s + u : s];
-                        const int e = en.y & 0xff;
-                        cjs[u] = live ? (en.y >> 8) : -1;
-                        const double va = zvalid ? Zh[fr * ROW_ZSTRIDE + 3 * e + fc] : 0.0;
-                        const double vb = zvalid ? __ldg(v.Zbuf + (size_t)en.x * 18 + fr * 3 + fc) : 0.0;
-                        a[u] = live ? va : 0.0; b[u] = live ? vb : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < ROW_UNROLL; ++u) {
-                        double c0 = 0.0, c1 = 0.0;
-                        dmma_m8n8k4(c0, c1, a[u], b[u]);
-                        if (cjs[u] >= 0 && fr < 6 && fc < 3) {             // accumulator fragment: row fr, columns 2*fc, 2*fc+1
-                            double2* dst = reinterpret_cast<double2*>(rowS + (size_t)cjs[u] * 36 + fr * 6 + 2 * fc);
-                            double2 cur = *dst; cur.x += c0; cur.y += c1; *dst = cur;
-                        }
-                    }
-                }
-                nlist = 0;
-                __syncwarp();
-            };
-#pragma unroll 1
-            for (int g = 0; g < ROW_WARPS; ++g) {
-                const int oe = meta_o[32 * g + lane], ne = meta_np[32 * g + lane];
-                const int maxq = (int)__reduce_max_sync(0xffffffffu, (unsigned)ne);
-#pragma unroll 1
-                for (int q = 0; q < maxq; ++q) {
-                    const int cq = q < ne ? __ldg(v.obs_cam + oe + 1 + q) : -1;
-                    const bool own = cq >= 0 && (cq & (ROW_WARPS - 1)) == warp;
-                    const unsigned m = __ballot_sync(0xffffffffu, own);
-                    if (m == 0u) continue;
-                    if (nlist + 32 > ROW_PLIST) flush();
-                    if (own) mylist[nlist + __popc(m & ((1u << lane) - 1u))] = make_int2(oe + 1 + q, (cq << 8) | (32 * g + lane));
-                    nlist += __popc(m);
-                    __syncwarp();
-                }
-            }
-            flush();
-        }
-        // ---- end of this (slice, camera) segment: combine the warps' diagonal fragments in warp order, write the partial record
+        for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += a; }
+        if (lane == 31) wsum[w] = s;
         __syncthreads();
-        {
-            double* fw = fragred + (size_t)warp * 128;
-            // accumulator fragment: row fr, columns 2*fc and 2*fc+1
-            fw[fr * 8 + 2 * fc] = dX0; fw[fr * 8 + 2 * fc + 1] = dX1;
-            fw[64 + fr * 8 + 2 * fc] = dZ0; fw[64 + fr * 8 + 2 * fc + 1] = dZ1;
+        if (w == 0) {
+            int a = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a += x; }
+            wsum[lane] = a;
         }
         __syncthreads();
-        double* rec = ra.part + (size_t)(blockIdx.x + c) * ra.rec_stride;
-        if (tid < 64) {
-            double xx = 0.0, zz = 0.0;
+        const int ex = carry_s + (w ? wsum[w - 1] : 0) + s - c;
+        if (i < nkeys) { cursor[i] = ex; pair_off[i] = ex; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += wsum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pair_off[nkeys] = carry_s;
+}
+// list of camera pairs that have at least one entry; single CTA (nblk = nc(nc+1)/2 is small)
+__global__ void __launch_bounds__(1024) pair_compact_kernel(const int32_t* __restrict__ pair_off, int nblk, int nseg, int32_t* __restrict__ pair_blk,
+                                                            int* __restrict__ n_nonempty) {
+    __shared__ int wcnt[32], carry_q;
+    if (threadIdx.x == 0) carry_q = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < nblk; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int f = i < nblk ? (pair_off[(size_t)(i + 1) * nseg] > pair_off[(size_t)i * nseg]) : 0;
+        int q = f;
 #pragma unroll
-            for (int w = 0; w < ROW_WARPS; ++w) { xx += fragred[w * 128 + tid]; zz += fragred[w * 128 + 64 + tid]; }
-            const int r = tid >> 3, q = tid & 7;
-            if (r < 6 && q < 6) rec[r * 6 + q] = xx - zz;                    // diagonal block  Jc^T Jc - Z Z^T
-            else if (r < 6 && q == 6) rec[36 + r] = xx - zz;                // camera-focal    Jc^T Jf - Z zf
-            else if (r < 6 && q == 7) { rec[42 + r] = xx - zz; rec[48 + r] = xx; }   // rhs  Jc^T r - Z zg ; gradient Jc^T r
-            else if (r == 6 && q == 6) rec[60] = xx;                        // Jf^T Jf
-            else if (r == 6 && q == 7) rec[61] = xx;                        // Jf^T r
-            if (r < 6 && q == r) rec[54 + r] = xx;                          // diag(Jc^T Jc)
+        for (int o = 1; o < 32; o <<= 1) { const int b = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) q += b; }
+        if (lane == 31) wcnt[w] = q;
+        __syncthreads();
+        if (w == 0) {
+            int b = wcnt[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, b, o); if (lane >= o) b += y; }
+            wcnt[lane] = b;
         }
-        if (!NORM_ONLY) for (int i = 36 * (c + 1) + tid; i < 36 * v.nc; i += ROW_THREADS) rec[ROW_HDR + i] = rowS[i];
+        __syncthreads();
+        if (f) pair_blk[carry_q + (w ? wcnt[w - 1] : 0) + q - 1] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_q += wcnt[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_nonempty = carry_q;
+}
+// Deterministic fill of the entry lists (once per problem): one CTA per camera ci walks ci's STABLE camera-major list (ascending
+// point) in chunks; the observations of the same point by cameras cj > ci are the records that follow it in the point-major
+// order (cm_np of them).  The position of entry (ci, cj, point) in list (ci,cj) is the number of earlier points seen by both,
+// computed without arrival-order atomics: per chunk a 32-bit lane mask per (warp, cj) (atomicOr: order-independent), a prefix
+// over the warps, a running count per cj.  The lists of (ci,cj) for all point segments are contiguous and ascending in point,
+// so the segment boundaries (pair_off, from the counting kernel) fall out by themselves.
+constexpr int PFILL_THREADS = 256;
+constexpr int PFILL_WARPS = PFILL_THREADS / 32;
+__global__ void __launch_bounds__(PFILL_THREADS) pair_fill_sorted_kernel(const int32_t* __restrict__ cm_off, const int32_t* __restrict__ cm_obs, const uint8_t* __restrict__ cm_np,
+                                                                        const int32_t* __restrict__ obs_cam, int nb, int nseg, const int32_t* __restrict__ pair_off,
+                                                                        uint2* __restrict__ ent) {
+    extern __shared__ unsigned pf_smem[];
+    unsigned* mask = pf_smem;                       // [PFILL_WARPS][nb]
+    int* running = reinterpret_cast<int*>(mask + (size_t)PFILL_WARPS * nb);   // [nb]: entries of list (ci, cj) placed so far
+    int* wbase = running + nb;                      // [PFILL_WARPS][nb]
+    const int ci = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int begin = cm_off[ci], end = cm_off[ci + 1];
+    for (int k = threadIdx.x; k < nb; k += PFILL_THREADS) running[k] = 0;
+    for (int b0 = begin; b0 < end; b0 += PFILL_THREADS) {
+        for (int k = threadIdx.x; k < PFILL_WARPS * nb; k += PFILL_THREADS) mask[k] = 0u;
+        __syncthreads();
+        const int i = b0 + threadIdx.x;
+        const int o = i < end ? cm_obs[i] : 0, ne = i < end ? (int)cm_np[i] : 0;
+        for (int q = 0; q < ne; ++q) atomicOr(mask + (size_t)warp * nb + obs_cam[o + 1 + q], 1u << lane);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nb; k += PFILL_THREADS) {
+            int run = running[k];
+#pragma unroll
+            for (int w = 0; w < PFILL_WARPS; ++w) { wbase[w * nb + k] = run; run += __popc(mask[(size_t)w * nb + k]); }
+            running[k] = run;
+        }
+        __syncthreads();
+        for (int q = 0; q < ne; ++q) {
+            const int cj = obs_cam[o + 1 + q];
+            const int pos = pair_off[(size_t)blk_index(ci, cj, nb) * nseg] + wbase[warp * nb + cj] + __popc(mask[(size_t)warp * nb + cj] & ((1u << lane) - 1u));
+            ent[pos] = make_uint2((unsigned)o, (unsigned)(o + 1 + q));
+        }
+        __syncthreads();
     }
 }
 
-// Sums the partial records of every camera in slice order and writes the reduced system in the layout the rest of the solver
-// (rank exchange, ba_assemble_kernel, ba_cam_update_kernel) reads: Sblk | Scf | Sff | rhs | gcf | dcf.  CTA c = camera c.
-// The focal terms need a sum over cameras: the last CTA to finish adds them up in camera order (fixed order whoever is last).
+// Fixed-order sums of the partial results -> the reduced system in the layout the rest of the solver (rank exchange,
+// ba_assemble_kernel, ba_cam_update_kernel) reads: Sblk | Scf | Sff | rhs | gcf | dcf.
+//   CTAs [0, nc): camera c -- the partial records of ba_camera_kernel<DET> in slice order (diagonal block, camera-focal column,
+//     rhs, gradient, J^T J diagonal).  The focal terms need a sum over cameras: the last of these CTAs to finish adds them up in
+//     camera order (fixed order whoever is last).
+//   CTAs [nc, ..): one warp per non-empty camera pair -- the partial blocks of ba_pair_kernel in (segment, split) order (a warp
+//     whose range of the list is empty wrote nothing: same arithmetic as in the kernel).  Empty pairs stay zero (never written).
 // norm_only: only the squared column norms of the unscaled Jacobian (Jacobi scaling at x0) -> colnorm [6 nc + 1].
-__global__ void __launch_bounds__(256) ba_combine_kernel(BAView v, RowArgs ra, int norm_only, double* __restrict__ colnorm,
-                                                         double* __restrict__ fpart /* [nc][2] */, unsigned* __restrict__ counter) {
+constexpr int COMBINE_THREADS = 256;
+__global__ void __launch_bounds__(COMBINE_THREADS) ba_combine_kernel(BAView v, RowArgs ra, int norm_only, double* __restrict__ colnorm,
+                                                                     double* __restrict__ fpart /* [nc][2] */, unsigned* __restrict__ counter) {
     if (v.st && v.st->status != LM_RUNNING) return;
-    const int c = blockIdx.x, nc = v.nc;
-    int first = 0, last = -1;
-    if (v.cm_off[c + 1] > v.cm_off[c]) { first = v.cm_off[c] / ra.per_cta; last = (v.cm_off[c + 1] - 1) / ra.per_cta; }
+    const int nc = v.nc;
+    if ((int)blockIdx.x >= nc) {
+        const int q = ((int)blockIdx.x - nc) * (COMBINE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+        if (q >= ra.n_nonempty) return;
+        const size_t blk = ra.pair_blk[q];
+        double s0 = 0.0, s1 = 0.0;                                          // elements lane and lane + 32 (< 36) of the block
+        for (int seg = 0; seg < ra.nseg; ++seg) {
+            const int start = ra.pair_off[blk * ra.nseg + seg], len = ra.pair_off[blk * ra.nseg + seg + 1] - start;
+            if (len <= 0) continue;
+            for (int sp = 0; sp < ra.splits; ++sp) {
+                const int b0 = start + (int)((long long)len * sp / ra.splits), b1 = start + (int)((long long)len * (sp + 1) / ra.splits);
+                if (b1 <= b0) continue;
+                const double* pb = ra.pair_part + ((blk * ra.nseg + seg) * ra.splits + sp) * 36;
+                s0 += pb[lane];
+                if (lane < 4) s1 += pb[32 + lane];
+            }
+        }
+        v.Sblk[blk * 36 + lane] = -s0;
+        if (lane < 4) v.Sblk[blk * 36 + 32 + lane] = -s1;
+        return;
+    }
+    const int c = blockIdx.x;
+    int dfirst = 0, dlast = -1;
+    if (v.cm_off[c + 1] > v.cm_off[c]) { dfirst = v.cm_off[c] / ra.diag_per_cta; dlast = (v.cm_off[c + 1] - 1) / ra.diag_per_cta; }
     auto sum = [&](int idx) {
         double s = 0.0;
-        for (int sl = first; sl <= last; ++sl) s += ra.part[(size_t)(sl + c) * ra.rec_stride + idx];
+        for (int sl = dfirst; sl <= dlast; ++sl) s += ra.diag_part[(size_t)(sl + c) * ROW_HDR + idx];
         return s;
     };
     if (norm_only) {
         if (threadIdx.x < 6) colnorm[6 * c + threadIdx.x] = sum(54 + threadIdx.x);
         if (threadIdx.x == 6) fpart[2 * c] = sum(60);
-    } else {
-        for (int t = threadIdx.x; t < 62; t += blockDim.x) {
-            const double s = sum(t);
-            if (t < 36) v.Sblk[blk_index(c, c, nc) * 36 + t] = s;
-            else if (t < 42) v.Scf[6 * c + (t - 36)] = s;
-            else if (t < 48) v.rhs[6 * c + (t - 42)] = s;
-            else if (t < 54) v.gcf[6 * c + (t - 48)] = s;
-            else if (t < 60) v.dcf[6 * c + (t - 54)] = s;
-            else fpart[2 * c + (t - 60)] = s;
-        }
-        for (int i = 36 * (c + 1) + threadIdx.x; i < 36 * nc; i += blockDim.x) {
-            const int cj = i / 36, ab = i - 36 * cj;
-            v.Sblk[blk_index(c, cj, nc) * 36 + ab] = -sum(ROW_HDR + i);
-        }
+    } else if (threadIdx.x < 62) {
+        const int t = threadIdx.x;
+        const double s = sum(t);
+        if (t < 36) v.Sblk[blk_index(c, c, nc) * 36 + t] = s;
+        else if (t < 42) v.Scf[6 * c + (t - 36)] = s;
+        else if (t < 48) v.rhs[6 * c + (t - 42)] = s;
+        else if (t < 54) v.gcf[6 * c + (t - 48)] = s;
+        else if (t < 60) v.dcf[6 * c + (t - 54)] = s;
+        else fpart[2 * c + (t - 60)] = s;
     }
     __shared__ bool is_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;    // wraps to 0: ready for the next launch
+    if (threadIdx.x == 0) is_last = atomicInc(counter, nc - 1) == (unsigned)(nc - 1);      // wraps to 0: ready for the next launch
     __syncthreads();
     if (!is_last) return;
     __threadfence();

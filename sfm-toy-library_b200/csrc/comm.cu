@@ -17,6 +17,7 @@ typedef int (*fn_get_unique_id)(nccl_unique_id*);
 typedef int (*fn_comm_init_rank)(nccl_comm_t*, int, nccl_unique_id, int);
 typedef int (*fn_comm_destroy)(nccl_comm_t);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_all_gather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t);
 typedef const char* (*fn_get_error_string)(int);
 
 struct NcclApi {
@@ -25,6 +26,7 @@ struct NcclApi {
     fn_comm_init_rank comm_init_rank = nullptr;
     fn_comm_destroy comm_destroy = nullptr;
     fn_all_reduce all_reduce = nullptr;
+    fn_all_gather all_gather = nullptr;
     fn_get_error_string get_error_string = nullptr;
     std::string err;
     bool load() {
@@ -36,6 +38,7 @@ struct NcclApi {
         comm_init_rank = (fn_comm_init_rank)dlsym(lib, "ncclCommInitRank");
         comm_destroy = (fn_comm_destroy)dlsym(lib, "ncclCommDestroy");
         all_reduce = (fn_all_reduce)dlsym(lib, "ncclAllReduce");
+        all_gather = (fn_all_gather)dlsym(lib, "ncclAllGather");
         get_error_string = (fn_get_error_string)dlsym(lib, "ncclGetErrorString");
         if (!get_unique_id || !comm_init_rank || !comm_destroy || !all_reduce) { err = "libnccl lacks a required symbol"; lib = nullptr; return false; }
         return true;
@@ -56,6 +59,16 @@ static int allreduce_f64(sfmb200_ctx* ctx, double* dbuf, size_t n, int op) {
     return SFMB200_OK;
 }
 int sfmb200_allreduce_sum_f64(sfmb200_ctx* ctx, double* dbuf, size_t n) { return allreduce_f64(ctx, dbuf, n, NCCL_SUM); }
+// all-gather of `bytes` bytes per rank (device buffers, rank order) on the ctx stream: used once per problem to hand the CUDA-IPC
+// handles of the exchange buffers around when the one-shot solve attaches its peers itself
+int sfmb200_allgather_bytes(sfmb200_ctx* ctx, const void* d_send, void* d_recv, size_t bytes) {
+    if (ctx->nranks <= 1) return SFMB200_OK;
+    if (!ctx->comm || !ctx->comm->comm || !g_nccl.all_gather) return sfmb200_fail(ctx, SFMB200_ERR_COMM, "communicator not initialised");
+    const int rc = g_nccl.all_gather(d_send, d_recv, bytes, /* ncclChar */ 0, ctx->comm->comm, ctx->stream);
+    if (rc != NCCL_SUCCESS)
+        return sfmb200_fail(ctx, SFMB200_ERR_COMM, "ncclAllGather: %s", g_nccl.get_error_string ? g_nccl.get_error_string(rc) : "error");
+    return SFMB200_OK;
+}
 int sfmb200_allreduce_max_f64(sfmb200_ctx* ctx, double* dbuf, size_t n) { return allreduce_f64(ctx, dbuf, n, NCCL_MAX); }
 
 void sfmb200_comm_destroy(sfmb200_ctx* ctx) {

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <array>
+#include <utility>
 
 #include "../../include/sfmb200.h"
 
@@ -89,6 +91,9 @@ struct sfmb200_ctx {
     BAWorkspace ba_ws;          // cached bundle-adjustment workspace
     MatchCache mcache;          // descriptor images resident between per-call matchFeatures invocations
     bool tc_attr_set = false;   // cudaFuncSetAttribute(knn2_hamming_tc_kernel, max dynamic smem) done for THIS device
+    // peer exchange buffers opened with cudaIpcOpenMemHandle, kept open across problems (the exchange buffer is part of the cached
+    // BA workspace, so the one-shot solve sees the same handles on every call): handle bytes -> mapped base
+    std::vector<std::pair<std::array<uint8_t, 64>, void*>> ipc_cache;
     CommState* comm = nullptr;
     int rank = 0, nranks = 1;
 };
@@ -117,4 +122,5 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // multi-GPU (comm.cu): in-place sum over ranks of n doubles on the ctx stream; no-op when nranks == 1
 int sfmb200_allreduce_sum_f64(sfmb200_ctx* ctx, double* dbuf, size_t n);
 int sfmb200_allreduce_max_f64(sfmb200_ctx* ctx, double* dbuf, size_t n);
+int sfmb200_allgather_bytes(sfmb200_ctx* ctx, const void* d_send, void* d_recv, size_t bytes);
 void sfmb200_comm_destroy(sfmb200_ctx* ctx);

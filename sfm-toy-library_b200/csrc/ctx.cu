@@ -43,6 +43,8 @@ void sfmb200_destroy(sfmb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& e : ctx->ipc_cache) if (e.second) cudaIpcCloseMemHandle(e.second);
+    ctx->ipc_cache.clear();
     sfmb200_comm_destroy(ctx);
     ctx->scratch.release(); ctx->scratch2.release(); ctx->pinned.release(); ctx->ba_ws.release(); ctx->mcache.release();
     cudaStreamDestroy(ctx->stream);
