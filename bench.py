@@ -5,9 +5,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference --steps 5 --warmup 1          # the reference's CPU path (oracle port; Ceres itself is not installable)
 
-Workload (config.workload): BASELINE.json configs[2] -- synthetic 100 cameras / 200k points / 1.6M observations per GPU
-(weak scaling: every rank owns its own 200k points, the 100 cameras are shared; the reduced camera system is summed over
-ranks once per LM iteration).  `--workload cfg2` selects configs[1] (20 / 10k / 80k).
+Workload (config.workload): BASELINE.json configs[2] -- ONE synthetic problem of 100 cameras / 200k points / 1.6M observations.
+`--gpus N` is STRONG scaling, as BASELINE.json states it ("1/2/4/8 x B200 NCCL-reduced camera system"): the 200k points are
+sharded over the N ranks, the 100 cameras are replicated, the reduced camera system is summed over ranks once per LM iteration.
+(Weak scaling -- 200k points per rank -- is measured too and reported under the key "weak".)  `--workload cfg2` selects
+configs[1] (20 / 10k / 80k).
 A step = ONE Levenberg-Marquardt iteration: residual+Jacobian evaluation of every observation fused with the per-point
 Schur elimination (K3a/K3b), the rank sum, the dense Cholesky solve (K4), back-substitution and evaluation of the candidate.
 Every iteration evaluates all observations, so evals/s = observations * iterations / time.
@@ -125,6 +127,7 @@ class ClockSampler:
 
 
 def make_shard(workload, rank):
+    """Weak-scaling shard: every rank its own points (rank 0 = THE problem of the strong-scaling run), shared cameras."""
     from sfm_toy_library_b200 import synth
     cfg = synth.BA_CONFIGS[workload]
     return synth.make_ba_problem(seed=0, point_seed=1000 + rank if rank else 0, **cfg)
@@ -235,12 +238,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         ctx.synchronize()
 
-    p = make_shard(args.workload, rank)
+    from sfm_toy_library_b200 import dist as sdist
+    p_full = make_shard(args.workload, 0)                 # THE problem (every rank generates the same one)
+    p = sdist.shard_ba_problem(p_full, rank, world) if world > 1 else p_full      # strong scaling: this rank's points
     a = (p["cams"], p["pts"], p["focal"], p["obs_xy"], p["obs_cam"], p["pt_off"])
     prob = ctx.ba_problem(*a)
     exchange = "none"
     if world > 1:
-        from sfm_toy_library_b200 import dist as sdist
         exchange = "nccl"
         if os.environ.get("SFMB200_EXCHANGE", "peer") == "peer":
             try:
@@ -300,9 +304,51 @@ def run_ours(args):
     dev_ms, wall_ms, dev_ms_raw = t.tolist(); nobs_total, launches_total, np_total = tot.tolist()
     value = nobs_total * iters / (dev_ms * 1e-3)
 
-    # the resident problem gives its workspace back to the context's cache: the one-shot solves below borrow it instead of
-    # paying cudaMalloc / cudaFree of ~600 MB per call (which cost 1 ms on a quiet host and 100+ ms on a busy one)
+    # ---- N-rank answer == 1-rank answer (checked here because the driver's GPU test box has one GPU): 10 LM iterations of
+    # the sharded problem on all ranks, the same 10 iterations of the whole problem on rank 0 alone (a second context without
+    # communicator), cameras + focal + cost compared; every rank must hold bit-identical cameras.
+    equivalence = None
+    if world > 1:
+        prob.reset()
+        s_eq = prob.run(fixed_iteration_options(capi, 10))
+        cams_n, _, f_n = prob.download()
+        blob = torch.from_numpy(np.concatenate([cams_n.ravel(), [f_n, s_eq["final_cost"]]])).cuda()
+        gathered = [torch.empty_like(blob) for _ in range(world)]
+        dist.all_gather(gathered, blob)
+        identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+        if rank == 0:
+            ctx1 = capi.Context(local)
+            p1 = ctx1.ba_problem(p_full["cams"], p_full["pts"], p_full["focal"], p_full["obs_xy"], p_full["obs_cam"], p_full["pt_off"])
+            s1 = p1.run(fixed_iteration_options(capi, 10)); cams_1, _, f_1 = p1.download()
+            p1.close(); ctx1.close()
+            equivalence = {"iterations": 10, "final_cost_rel_diff": abs(s_eq["final_cost"] - s1["final_cost"]) / s1["final_cost"],
+                           "max_camera_abs_diff": float(np.abs(cams_n - cams_1).max()), "focal_rel_diff": abs(f_n - f_1) / f_1,
+                           "ranks_bit_identical": identical}
+            assert equivalence["final_cost_rel_diff"] < 1e-9 and equivalence["max_camera_abs_diff"] < 1e-7 and identical, equivalence
+        barrier()
     prob.close()
+    # ---- weak scaling (secondary): every rank its own 200k points, same K iterations, same hygiene
+    weak = None
+    if world > 1:
+        pw = make_shard(args.workload, rank)
+        probw = ctx.ba_problem(pw["cams"], pw["pts"], pw["focal"], pw["obs_xy"], pw["obs_cam"], pw["pt_off"])
+        if exchange.startswith("peer"):
+            sdist.attach_peers(probw, dist)
+        run_steps(probw, capi, 40, profile=1, l2_flush_mb=L2_FLUSH_MB); probw.reset()
+        barrier()
+        w0 = torch.cuda.Event(enable_timing=True); w1 = torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        sw = run_steps(probw, capi, args.steps, profile=1, l2_flush_mb=L2_FLUSH_MB)
+        w1.record(stream)
+        barrier()
+        tw = torch.tensor([w0.elapsed_time(w1) - float(sw["flush_ms_total"])], dtype=torch.float64, device="cuda")
+        nw = torch.tensor([float(pw["nobs"])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX); dist.all_reduce(nw, op=dist.ReduceOp.SUM)
+        weak = {"value": nw.item() * sw["num_iterations"] / (tw.item() * 1e-3), "unit": UNIT, "ms_per_step": tw.item() / sw["num_iterations"],
+                "points_per_gpu": pw["np"], "observations_total": int(nw.item())}
+        probw.close()
+    # the resident problem gave its workspace back to the context's cache: the one-shot solves below borrow it instead of
+    # paying cudaMalloc / cudaFree of ~600 MB per call (which cost 1 ms on a quiet host and 100+ ms on a busy one)
     # ---- e2e: the same K iterations through the one-shot C-ABI call with pinned HOST buffers ------------------------
     def pinned(x):
         return torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
@@ -343,7 +389,7 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
     except Exception:
         pass
-    kernels = {"ba_point_kernel": k_point, "ba_pair_kernel": k_pair, "ba_camera_kernel": k_cam}
+    kernels = {"ba_point_kernel": k_point, "ba_pair_kernel": k_pair, "ba_camera_kernel+ba_combine_kernel": k_cam}
     # fp64 side of the roofline (SURVEY.md 8d asks for it next to the HBM fraction): useful flops of one LM iteration, counted from the
     # algorithm -- three closed-form Jacobian evaluations per observation (point pass, camera pass, step evaluation; ~300 flop each),
     # the per-observation Schur terms (~760 flop) and 2*6*6*3 flop per (observation pair of a point) for the off-diagonal blocks --
@@ -361,14 +407,16 @@ def run_ours(args):
     line = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": dev_ms / iters, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"BASELINE.json configs[{2 if args.workload == 'cfg3' else 1}] ({args.workload}) per GPU",
-                           "cams": p["nc"], "points_per_gpu": p["np"], "observations_per_gpu": p["nobs"],
+                "config": {"workload": f"BASELINE.json configs[{2 if args.workload == 'cfg3' else 1}] ({args.workload})",
+                           "cams": p_full["nc"], "points": p_full["np"], "observations": p_full["nobs"],
+                           "points_per_gpu": p["np"], "observations_per_gpu": p["nobs"],
                            "points_total": int(np_total), "observations_total": int(nobs_total),
                            "step": "one LM iteration: residual+Jacobian+Schur pass, rank sum, dense Cholesky, back-substitution, candidate evaluation"
                                    + (f"; the {args.steps} timed iterations are solves of {SOLVE_ITERS} restarted from x0" if args.steps > SOLVE_ITERS + 4 else ""),
-                           "parallelism": f"points sharded over {world} GPU(s), cameras replicated, reduced camera system summed over ranks ({exchange})",
+                           "parallelism": f"the problem's points sharded over {world} GPU(s) (strong scaling), cameras replicated, reduced camera system "
+                                          f"summed over ranks ({exchange}); every rank factors the 601x601 reduced system redundantly",
                            "l2": f"flushed: a {L2_FLUSH_MB} MB scratch buffer is written before every timed LM iteration (per-GPU working set ~90 MB < L2); "
                                  "the flush writes run inside the event bracket and their own event time is subtracted (ms_per_step_incl_flush keeps the raw bracket)"},
                 "wall_ms_per_step": wall_ms / iters, "ms_per_step_incl_flush": dev_ms_raw / iters,
@@ -377,10 +425,14 @@ def run_ours(args):
                         "note": f"one sfmb200_ba_solve call (create+upload from pinned host, {e2e_steps} LM iterations, download) = one step; mean of {reps}", "rep_ms": rep_ms},
                 "gpu_launches": int(launches_total),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "K3 = ba_point_kernel + ba_pair_kernel + ba_camera_kernel (one residual+Jacobian+Schur pass)",
+                             "kernel": "K3 = ba_point_kernel + ba_pair_kernel + ba_camera_kernel + ba_combine_kernel (one residual+Jacobian+Schur pass)",
                              "kernel_ms": k3_ms, "kernels_ms": kernels, "dominant": dominant, "algorithmic_bytes": int(abytes), "peak_source": peak_src,
                              "note": "not HBM-bound: fp64 arithmetic and L1/L2 request rate of the per-camera-pair accumulation dominate (DESIGN.md section 4)"},
                 "clocks": clocks}
+        if weak is not None:
+            line["weak"] = weak
+        if equivalence is not None:
+            line["equivalence"] = equivalence
         step_s = dev_ms / iters * 1e-3
         fp64["step_tflops"] = flops_iter / step_s / 1e12; fp64["step_frac"] = fp64["step_tflops"] / fp64_peak
         if k_pair > 0:
@@ -395,6 +447,22 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": p["nobs"] * so["num_iterations"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{args.workload} full problem, {it} LM iterations of the oracle (Ceres-equivalent LM+DENSE_SCHUR, dual-number Jacobians, 1 thread as the reference leaves Ceres), {dt:.1f} s"}
+    # ---- BASELINE configs[0] (crazyhorse, the only real-data configuration): stage times of the runSfM replay, GPU stages
+    # through the drop-in call shape beside the reference's own OpenCV calls / the oracle's Ceres restatement on the host cores
+    if rank == 0 and world == 1 and not args.no_stages:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import bench_cfg1
+            c1 = bench_cfg1.measure(reps=2)
+            keep = ("wall_s", "hot_path_s", "seconds", "calls", "cloud")
+            line["cfg1"] = {"workload": c1["workload"], "gpu": {k: c1["gpu_batched"][k] for k in keep},
+                            "gpu_per_call_match_s": c1["gpu_per_call"]["seconds"]["match"],
+                            "gpu_per_call_match_nocache_s": c1["gpu_per_call_nocache"]["seconds"]["match"],
+                            "cpu_all_threads": {k: c1["cpu_cv2_all_threads"][k] for k in keep}, "cpu_threads": c1["cpu_threads"],
+                            "speedup_hot_path": c1["speedup_hot_path"], "speedup_per_stage": c1["speedup_per_stage"],
+                            "note": "seconds per stage summed over the replay's calls; RANSAC stages are cv2 in both arms (SURVEY.md 8 f-2)"}
+        except Exception as e:                                  # never lose the headline line to a secondary measurement
+            line["cfg1"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -410,6 +478,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the secondary stage measurements (cfg1 replay)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

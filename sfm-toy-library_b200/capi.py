@@ -84,9 +84,19 @@ class Context:
         if rc != 0:
             raise SfmB200Error(f"sfmb200_create failed ({rc}): {lib().sfmb200_last_error(None).decode()}")
         self.device = device
+        self._children = []          # weak references to live DescriptorSets / BAProblems: they must die before the context
+
+    def _adopt(self, child):
+        import weakref
+        self._children.append(weakref.ref(child))
 
     def close(self):
         if self._h:
+            for ref in self._children:          # a problem / descriptor set destroyed after its context would touch freed memory
+                child = ref()
+                if child is not None:
+                    child.close()
+            self._children = []
             lib().sfmb200_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -239,6 +249,7 @@ class DescriptorSet:
         allrows = np.ascontiguousarray(np.concatenate(desc_list, 0)) if desc_list else np.zeros((0, nb), np.uint8)
         self._h = C.c_void_p()
         ctx._check(lib().sfmb200_descset_create(ctx._h, _p(allrows, C.c_uint8), _p(off, C.c_int32), len(desc_list), nb, C.byref(self._h)))
+        ctx._adopt(self)
 
     def close(self):
         if self._h:
@@ -281,6 +292,7 @@ class BAProblem:
         ctx._check(lib().sfmb200_ba_problem_create(ctx._h, self.nc, self.np, self.nobs, _p(cams, C.c_double), _p(pts, C.c_double),
                                                    C.c_double(float(focal)), _p(obs_xy, C.c_float), _p(obs_cam, C.c_int32),
                                                    _p(pt_off, C.c_int32), C.byref(self._h)))
+        ctx._adopt(self)
 
     def close(self):
         if self._h:

@@ -28,8 +28,16 @@ def _worker(rank, world, port, out_dir, exchange):
     if exchange == "peer":
         assert sdist.attach_peers(prob, dist)                       # CUDA-IPC mapped buffers, sums by NVLink loads
     red = prob.reduced_system(1e4)
-    s = prob.run()
-    cams, pts, f = prob.download()
+    if exchange == "oneshot":
+        # the drop-in call (sfmb200_ba_solve): attaches its peers itself (IPC handles over one ncclAllGather), no host-side
+        # exchange, no barrier before the problem is destroyed (the run ends with a peer hand-shake)
+        prob.close()
+        cams, pts, f, s = ctx.ba_solve(sh["cams"], sh["pts"], sh["focal"], sh["obs_xy"], sh["obs_cam"], sh["pt_off"])
+        cams2, pts2, f2, s2 = ctx.ba_solve(sh["cams"], sh["pts"], sh["focal"], sh["obs_xy"], sh["obs_cam"], sh["pt_off"])   # cached mappings
+        assert s2["num_iterations"] == s["num_iterations"] and np.array_equal(cams, cams2) and np.array_equal(pts, pts2)
+    else:
+        s = prob.run()
+        cams, pts, f = prob.download()
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), S=red["S"], rhs=red["rhs"], cost=red["cost"], cams=cams, pts=pts, f=f,
              iters=s["num_iterations"], term=s["termination_type"], final=s["final_cost"], b=sh["point_range"][0], e=sh["point_range"][1])
     prob.close(); ctx.close()
@@ -37,7 +45,7 @@ def _worker(rank, world, port, out_dir, exchange):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+@pytest.mark.parametrize("exchange", ["nccl", "peer", "oneshot"])
 def test_two_gpu_solve_equals_single_gpu(tmp_path, exchange):
     import torch
     if torch.cuda.device_count() < 2:
