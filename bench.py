@@ -463,6 +463,15 @@ def run_ours(args):
                             "note": "seconds per stage summed over the replay's calls; RANSAC stages are cv2 in both arms (SURVEY.md 8 f-2)"}
         except Exception as e:                                  # never lose the headline line to a secondary measurement
             line["cfg1"] = {"error": repr(e)}
+        # BASELINE configs[3] (all-pairs matching, 50 x 5000: reference-faithful ORB/Hamming and the SIFT-128/L2 wording) and
+        # configs[4] (1 M point triangulation): device-timed value, host-buffer e2e incl. descriptor upload, roofline, cv2 CPU baseline
+        try:
+            import bench_stages
+            for st in bench_stages.measure_all(reps=3, ctx=ctx):
+                key = {"match_hamming": "cfg4_hamming", "match_l2": "cfg4_sift_l2", "triangulate": "cfg5"}[st["stage"]]
+                line[key] = st
+        except Exception as e:
+            line["cfg4_cfg5"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()

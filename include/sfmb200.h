@@ -63,8 +63,11 @@ int64_t sfmb200_kernel_launches(const sfmb200_ctx* ctx);    /* number of kernels
 int sfmb200_match_knn2_ratio(sfmb200_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int desc_bytes,
                              double ratio, int32_t* out_q, int32_t* out_t, float* out_d, int* out_n);
 
-/* L2 variant (cv::BFMatcher(NORM_L2), BASELINE.json config 4 wording): float descriptors [n*dim], distance =
- * sqrtf(sum of squared differences) accumulated in float32 (exact for integer-valued descriptors such as SIFT). */
+/* L2 variant (cv::BFMatcher(NORM_L2), BASELINE.json configs[3] wording "SIFT-128"; the legacy tree's own L2 knn + ratio test is
+ * legacy/SfMToyLib_Old/GPUSURFFeatureMatcher.cpp:100-124): float descriptors [n*dim], distance = sqrtf(sum of squared
+ * differences).  Integer-valued descriptors in [0, 255] with dim <= 128 (what cv::SIFT produces) are matched EXACTLY as a
+ * u8 x u8 -> s32 GEMM on the tcgen05 tensor cores (|a-b|^2 = |a|^2 + |b|^2 - 2<a,b>, every term an exact integer < 2^24, so the
+ * float32 sum cv::batchDistance forms is reproduced bit for bit); anything else runs the fp32 SIMT kernel. */
 int sfmb200_match_knn2_ratio_l2(sfmb200_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
                                 double ratio, int32_t* out_q, int32_t* out_t, float* out_d, int* out_n);
 
@@ -73,6 +76,9 @@ int sfmb200_match_knn2_ratio_l2(sfmb200_ctx* ctx, const float* q, int nq, const 
 typedef struct sfmb200_descset sfmb200_descset;
 int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc /* concatenated rows */, const int32_t* img_off /* [n_img+1] row offsets */,
                            int n_img, int desc_bytes, sfmb200_descset** set);
+/* same for L2 matching: float descriptors [rows*dim], dim <= 128, values must be integers in [0, 255] (SFMB200_ERR_UNSUPPORTED
+ * otherwise).  sfmb200_match_pairs / _device then return float distances sqrtf(|a-b|^2) like cv::BFMatcher(NORM_L2). */
+int sfmb200_descset_create_l2(sfmb200_ctx* ctx, const float* desc, const int32_t* img_off, int n_img, int dim, sfmb200_descset** set);
 void sfmb200_descset_destroy(sfmb200_descset* set);
 /* pairs [2*n_pairs] = (left,right) image ids.  Results of pair p are written to out_*[out_off[p] .. out_off[p]+out_cnt[p])
  * where out_off[p] = sum of the LEFT image sizes of pairs < p (computed here, returned in out_off [n_pairs+1]);

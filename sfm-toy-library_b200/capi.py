@@ -141,8 +141,8 @@ class Context:
                                                       _p(oq, C.c_int32), _p(ot, C.c_int32), _p(od, C.c_float), C.byref(n)))
         return oq[:n.value].copy(), ot[:n.value].copy(), od[:n.value].copy()
 
-    def descriptor_set(self, desc_list):
-        return DescriptorSet(self, desc_list)
+    def descriptor_set(self, desc_list, norm="hamming"):
+        return DescriptorSet(self, desc_list, norm)
 
     # ------------------------------------------------------------------ a-2 triangulation
     def triangulate(self, K, Pl, Pr, pts_left, pts_right, match_q=None, match_t=None, max_reproj=MIN_REPROJECTION_ERROR):
@@ -240,15 +240,22 @@ def angle_axis_to_rotmat(aa):
 class DescriptorSet:
     """sfmb200_descset: the descriptors of all images resident in HBM; all-pairs matching in one call."""
 
-    def __init__(self, ctx, desc_list):
+    def __init__(self, ctx, desc_list, norm="hamming"):
+        """norm="hamming": uint8 rows (ORB; the reference's case).  norm="l2": float32 rows with integer values in [0, 255] and
+        dim <= 128 (SIFT): exact u8 GEMM on the tensor cores, distances like cv2.BFMatcher(NORM_L2)."""
         self.ctx = ctx
-        desc_list = [np.ascontiguousarray(d, np.uint8) for d in desc_list]
+        self.norm = norm
+        dt = np.uint8 if norm == "hamming" else np.float32
+        desc_list = [np.ascontiguousarray(d, dt) for d in desc_list]
         self.sizes = [d.shape[0] for d in desc_list]
         nb = desc_list[0].shape[1] if desc_list else 32
         off = np.zeros(len(desc_list) + 1, np.int32); off[1:] = np.cumsum(self.sizes)
-        allrows = np.ascontiguousarray(np.concatenate(desc_list, 0)) if desc_list else np.zeros((0, nb), np.uint8)
+        allrows = np.ascontiguousarray(np.concatenate(desc_list, 0)) if desc_list else np.zeros((0, nb), dt)
         self._h = C.c_void_p()
-        ctx._check(lib().sfmb200_descset_create(ctx._h, _p(allrows, C.c_uint8), _p(off, C.c_int32), len(desc_list), nb, C.byref(self._h)))
+        if norm == "hamming":
+            ctx._check(lib().sfmb200_descset_create(ctx._h, _p(allrows, C.c_uint8), _p(off, C.c_int32), len(desc_list), nb, C.byref(self._h)))
+        else:
+            ctx._check(lib().sfmb200_descset_create_l2(ctx._h, _p(allrows, C.c_float), _p(off, C.c_int32), len(desc_list), nb, C.byref(self._h)))
         ctx._adopt(self)
 
     def close(self):

@@ -135,7 +135,7 @@ merge_flag_scan_kernel(const int4* __restrict__ partial, int splits, int64_t row
     int keep = 0;
     if (g < rows) {
         float fd0, fd1; int i0 = -1, i1 = -1;
-        if (!is_l2) {
+        if (is_l2 != 1) {
             Top2 b = {INT_MAX, -1, INT_MAX, -1};
             for (int s = 0; s < splits; ++s) {
                 const int4 p = partial[(size_t)g * splits + s];
@@ -143,6 +143,8 @@ merge_flag_scan_kernel(const int4* __restrict__ partial, int splits, int64_t row
                 if (p.w >= 0) top2_insert(b, p.z, p.w);
             }
             i0 = b.i0; i1 = b.i1; fd0 = (float)b.d0; fd1 = (float)b.d1;          // DMatch.distance is float
+            // is_l2 == 2: exact integer SQUARED L2 distances (tcgen05 u8 GEMM); cv::batchDistance returns sqrt of the float sum
+            if (is_l2 == 2) { fd0 = sqrtf(fd0); fd1 = sqrtf(fd1); }
         } else {
             float d0 = 3.4e38f, d1 = 3.4e38f;
             const float4* pf = reinterpret_cast<const float4*>(partial);
@@ -214,22 +216,25 @@ struct sfmb200_descset {
     uint32_t* d_desc = nullptr;
     std::vector<int32_t> img_off;
     int n_img = 0, words = 0, max_rows = 0;
-    // tcgen05 path (32-byte descriptors): operands expanded once to signed bytes, 64 KB blocks of 256 rows
+    // tcgen05 path (32-byte Hamming descriptors, u8-valued L2 descriptors): operands expanded once, blocks of 256 rows
     uint8_t* d_exp = nullptr;
     std::vector<int32_t> img_blk;      // first block of each image
+    int kind = 0;                      // 0 = Hamming, 1 = L2 (exact u8 GEMM)
+    int32_t* d_norms = nullptr;        // L2: squared norms, [blocks][256]
 };
 
 // core: pairs already on the host as PairDesc; descriptors on the device.  Leaves the dense compacted results in
 // d_out_* (device) and per-pair dense start positions in d_pair_start [n_pairs+1].
 static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d_exp, int words, const std::vector<PairDesc>& hp, int64_t rows, int nq_max, int nt_max,
                       double ratio, int32_t* d_out_q, int32_t* d_out_t, float* d_out_d, int32_t* d_pair_start, int64_t* d_total, DevBuf& work,
-                      int** d_tc_error = nullptr) {
+                      int** d_tc_error = nullptr, const int32_t* d_norms = nullptr /* non-null: L2 set */) {
+    const bool l2 = d_norms != nullptr;
     const int n_pairs = (int)hp.size();
     const int qblocks = ceil_div(nq_max, QBLOCK);
     // 32-byte descriptors (ORB, the reference's case): exact integer GEMM on the tensor cores (match_tc.cu);
     // SFMB200_MATCH=popc forces the XOR/POPC kernel (other widths always use it)
     const char* mode = getenv("SFMB200_MATCH");
-    const bool use_tc = words == 8 && d_exp != nullptr && !(mode && strcmp(mode, "popc") == 0);
+    const bool use_tc = l2 || (words == 8 && d_exp != nullptr && !(mode && strcmp(mode, "popc") == 0));
     const int splits = use_tc ? match_tc_splits(ctx->sm_count, n_pairs, nq_max, nt_max) : choose_splits(ctx->sm_count, (int64_t)qblocks * n_pairs, nt_max);
     const int nblk = (int)ceil_div64(rows, SCAN_THREADS);
     size_t bytes = Carver::pad(sizeof(PairDesc) * n_pairs) + Carver::pad(sizeof(int4) * rows * splits) + Carver::pad(4 * rows) * 3 +
@@ -244,7 +249,7 @@ static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d
     dim3 grid(qblocks * splits, n_pairs);
     if (use_tc) {
         SFM_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
-        int rc = match_tc_launch(ctx, d_exp, d_pairs, n_pairs, nq_max, splits, d_partial, d_err);
+        int rc = match_tc_launch(ctx, l2, d_exp, d_norms, d_pairs, n_pairs, nq_max, splits, d_partial, d_err);
         if (rc) return rc;
         if (d_tc_error) *d_tc_error = d_err;
     } else switch (words) {
@@ -255,7 +260,7 @@ static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d
         default: return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "desc_bytes must be 16, 32, 64 or 128 (got %d)", words * 4);
     }
     if (!use_tc) SFM_LAUNCH_CHECK(ctx);
-    merge_flag_scan_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_partial, splits, rows, ratio, 0, d_best_t, d_best_d, d_rank, d_flag, d_bsum);
+    merge_flag_scan_kernel<<<nblk, SCAN_THREADS, 0, ctx->stream>>>(d_partial, splits, rows, ratio, l2 ? 2 : 0, d_best_t, d_best_d, d_rank, d_flag, d_bsum);
     SFM_LAUNCH_CHECK(ctx);
     scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_bsum, nblk, d_total, use_tc ? d_err : nullptr);
     SFM_LAUNCH_CHECK(ctx);
@@ -266,7 +271,7 @@ static int match_core(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d
 
 static int match_pairs_host_out(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d_exp, int words, const std::vector<PairDesc>& hp,
                                 int64_t rows, int nq_max, int nt_max, double ratio,
-                                int32_t* out_q, int32_t* out_t, float* out_d, int64_t* out_off, int32_t* out_cnt);
+                                int32_t* out_q, int32_t* out_t, float* out_d, int64_t* out_off, int32_t* out_cnt, const int32_t* d_norms = nullptr);
 
 static int build_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, std::vector<PairDesc>& hp,
                        int64_t& rows, int& nq_max, int& nt_max) {
@@ -329,7 +334,7 @@ int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc, const int32_t*
         }
         s->img_blk[n_img] = (int)blocks.size();
         int2* d_blocks = nullptr;
-        e = cudaMalloc(&s->d_exp, blocks.size() * match_tc_block_bytes());
+        e = cudaMalloc(&s->d_exp, blocks.size() * match_tc_block_bytes(false));
         if (e == cudaSuccess) e = cudaMalloc(&d_blocks, blocks.size() * sizeof(int2));
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
         int rc = e == cudaSuccess ? match_tc_expand(ctx, s->d_desc, d_blocks, (int)blocks.size(), s->d_exp) : SFMB200_ERR_NOMEM;
@@ -349,7 +354,59 @@ void sfmb200_descset_destroy(sfmb200_descset* s) {
     cudaSetDevice(s->ctx->device);
     cudaFree(s->d_desc);
     if (s->d_exp) cudaFree(s->d_exp);
+    if (s->d_norms) cudaFree(s->d_norms);
     delete s;
+}
+
+// L2 descriptor set (cv::BFMatcher(NORM_L2) semantics; BASELINE.json configs[3]: SIFT-128): float descriptors [rows][dim], dim <= 128.
+// Integer-valued descriptors in [0, 255] (what cv::SIFT produces) are matched EXACTLY on the tensor cores (u8 x u8 -> s32 GEMM,
+// match_tc.cu); anything else is refused here (SFMB200_ERR_UNSUPPORTED) -- the per-pair entry point falls back to fp32 SIMT.
+int sfmb200_descset_create_l2(sfmb200_ctx* ctx, const float* desc, const int32_t* img_off, int n_img, int dim, sfmb200_descset** out) {
+    if (!ctx || !out || !img_off || n_img < 0 || dim <= 0) return SFMB200_ERR_INVALID;
+    *out = nullptr;
+    if (dim > 128) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "L2 descriptor sets support dim <= 128 (got %d)", dim);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    sfmb200_descset* s = new sfmb200_descset();
+    s->ctx = ctx; s->n_img = n_img; s->words = 32; s->kind = 1; s->img_off.assign(img_off, img_off + n_img + 1);
+    const int br = match_tc_block_rows();
+    std::vector<int2> blocks;
+    s->img_blk.resize(n_img + 1);
+    for (int i = 0; i < n_img; ++i) {
+        if (img_off[i + 1] < img_off[i]) { delete s; return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "img_off not monotone"); }
+        s->max_rows = std::max(s->max_rows, img_off[i + 1] - img_off[i]);
+        s->img_blk[i] = (int)blocks.size();
+        const int rows = img_off[i + 1] - img_off[i];
+        for (int b0 = 0; b0 < rows; b0 += br) blocks.push_back(make_int2(img_off[i] + b0, std::min(br, rows - b0)));
+    }
+    s->img_blk[n_img] = (int)blocks.size();
+    const size_t fbytes = (size_t)img_off[n_img] * dim * sizeof(float), nb = std::max<size_t>(blocks.size(), 1);
+    float* d_f = nullptr; int2* d_blocks = nullptr; int* d_bad = nullptr;
+    cudaError_t e = cudaMalloc(&d_f, fbytes + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_exp, nb * match_tc_block_bytes(true));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_norms, nb * br * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_blocks, nb * sizeof(int2) + 16);
+    d_bad = reinterpret_cast<int*>(d_blocks + nb);
+    int h_bad = 0, rc = SFMB200_OK;
+    if (e == cudaSuccess && fbytes) e = cudaMemcpyAsync(d_f, desc, fbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
+    if (e == cudaSuccess && !blocks.empty()) {
+        e = cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) rc = match_tc_expand_l2(ctx, d_f, dim, d_blocks, (int)blocks.size(), s->d_exp, s->d_norms, d_bad);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (d_f) cudaFree(d_f);
+    if (d_blocks) cudaFree(d_blocks);
+    if (e != cudaSuccess || rc || h_bad) {
+        if (s->d_exp) cudaFree(s->d_exp);
+        if (s->d_norms) cudaFree(s->d_norms);
+        delete s;
+        if (h_bad) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "L2 descriptor set: values must be integers in [0, 255] (SIFT-like) for the exact tensor-core path");
+        return sfmb200_fail(ctx, e == cudaErrorMemoryAllocation ? SFMB200_ERR_NOMEM : SFMB200_ERR_CUDA, "L2 descriptor set: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return SFMB200_OK;
 }
 
 int sfmb200_match_pairs_device(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, double ratio,
@@ -364,7 +421,7 @@ int sfmb200_match_pairs_device(sfmb200_ctx* ctx, const sfmb200_descset* set, con
     int rc = build_pairs(ctx, set, pairs, n_pairs, hp, rows, nq_max, nt_max);
     if (rc) return rc;
     if (rows == 0 || nt_max < 2) return SFMB200_OK;
-    return match_core(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, d_out_q, d_out_t, d_out_d, d_pair_start, d_total, ctx->scratch);
+    return match_core(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, d_out_q, d_out_t, d_out_d, d_pair_start, d_total, ctx->scratch, nullptr, set->d_norms);
 }
 
 int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int32_t* pairs, int n_pairs, double ratio,
@@ -375,7 +432,7 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
     std::vector<PairDesc> hp; int64_t rows; int nq_max, nt_max;
     int rc = build_pairs(ctx, set, pairs, n_pairs, hp, rows, nq_max, nt_max);
     if (rc) return rc;
-    return match_pairs_host_out(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, out_q, out_t, out_d, out_off, out_cnt);
+    return match_pairs_host_out(ctx, set->d_desc, set->d_exp, set->words, hp, rows, nq_max, nt_max, ratio, out_q, out_t, out_d, out_off, out_cnt, set->d_norms);
 }
 
 }  // extern "C"
@@ -383,7 +440,7 @@ int sfmb200_match_pairs(sfmb200_ctx* ctx, const sfmb200_descset* set, const int3
 // pairs described on the host, descriptors resident: run the kernels, read back only the survivors.  ctx->mu is held.
 static int match_pairs_host_out(sfmb200_ctx* ctx, const uint32_t* d_desc, const uint8_t* d_exp, int words, const std::vector<PairDesc>& hp,
                                 int64_t rows, int nq_max, int nt_max, double ratio,
-                                int32_t* out_q, int32_t* out_t, float* out_d, int64_t* out_off, int32_t* out_cnt) {
+                                int32_t* out_q, int32_t* out_t, float* out_d, int64_t* out_off, int32_t* out_cnt, const int32_t* d_norms) {
     const int n_pairs = (int)hp.size();
     int rc;
     for (int p = 0; p < n_pairs; ++p) { out_off[p] = hp[p].out_row; out_cnt[p] = 0; }
@@ -399,7 +456,7 @@ static int match_pairs_host_out(sfmb200_ctx* ctx, const uint32_t* d_desc, const 
     int32_t* d_q = cv.take<int32_t>(rows); int32_t* d_t = cv.take<int32_t>(rows); float* d_d = cv.take<float>(rows);
     int32_t* d_start = cv.take<int32_t>(n_pairs + 1); int64_t* d_total = cv.take<int64_t>(1);
     int* d_tc_err = nullptr;
-    rc = match_core(ctx, d_desc, d_exp, words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb, &d_tc_err);
+    rc = match_core(ctx, d_desc, d_exp, words, hp, rows, nq_max, nt_max, ratio, d_q, d_t, d_d, d_start, d_total, outb, &d_tc_err, d_norms);
     if (rc) return rc;
     // read back: pair starts + total, then only the survivors
     // (pinned staging is sized for the SURVIVORS, known after the first small read-back -- not for all query rows)
@@ -484,7 +541,7 @@ static int cache_acquire(sfmb200_ctx* ctx, const uint8_t* img, int rows, int des
         for (int b = 0; b < nblk; ++b) blocks[b] = make_int2(row0 + b * br, std::min(br, rows - b * br));
         SFM_CUDA(ctx, ctx->scratch.reserve(sizeof(int2) * nblk + 256));
         SFM_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, blocks.data(), sizeof(int2) * nblk, cudaMemcpyHostToDevice, ctx->stream));
-        int rc = match_tc_expand(ctx, (const uint32_t*)mc.desc.p, (const int2*)ctx->scratch.p, nblk, (uint8_t*)mc.exp.p + (size_t)blk0 * match_tc_block_bytes());
+        int rc = match_tc_expand(ctx, (const uint32_t*)mc.desc.p, (const int2*)ctx->scratch.p, nblk, (uint8_t*)mc.exp.p + (size_t)blk0 * match_tc_block_bytes(false));
         if (rc) return rc;
     }
     mc.rows_used += rows; mc.blk_used += nblk;
@@ -531,7 +588,7 @@ int sfmb200_match_knn2_ratio(sfmb200_ctx* ctx, const uint8_t* q, int nq, const u
         const int want_blk = width == 32 ? std::max<int>(need_blk, (int)(want_rows / br) + 32) : 0;
         if (want_blk > mc.blk_cap) {
             SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            SFM_CUDA(ctx, mc.exp.reserve((size_t)want_blk * match_tc_block_bytes()));
+            SFM_CUDA(ctx, mc.exp.reserve((size_t)want_blk * match_tc_block_bytes(false)));
             mc.blk_cap = want_blk;
         }
     }
@@ -555,6 +612,25 @@ int sfmb200_match_knn2_ratio_l2(sfmb200_ctx* ctx, const float* q, int nq, const 
     *out_n = 0;
     if (nq == 0 || nt < 2) return SFMB200_OK;
     if (!q || !t || !out_q || !out_t || !out_d) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "null buffer");
+    if (dim <= 128 && !(getenv("SFMB200_MATCH_L2") && strcmp(getenv("SFMB200_MATCH_L2"), "simt") == 0)) {
+        // exact integer GEMM on the tensor cores when the descriptors are u8-valued (SIFT): a two-image descriptor set
+        std::vector<float> both((size_t)(nq + nt) * dim);
+        memcpy(both.data(), q, sizeof(float) * (size_t)nq * dim);
+        memcpy(both.data() + (size_t)nq * dim, t, sizeof(float) * (size_t)nt * dim);
+        const int32_t off[3] = {0, nq, nq + nt};
+        sfmb200_descset* set = nullptr;
+        int rc = sfmb200_descset_create_l2(ctx, both.data(), off, 2, dim, &set);
+        if (rc == SFMB200_OK) {
+            const int32_t pair[2] = {0, 1};
+            int64_t ooff[2]; int32_t cnt[1];
+            rc = sfmb200_match_pairs(ctx, set, pair, 1, ratio, out_q, out_t, out_d, ooff, cnt);
+            sfmb200_descset_destroy(set);
+            if (rc) return rc;
+            *out_n = cnt[0];
+            return SFMB200_OK;
+        }
+        if (rc != SFMB200_ERR_UNSUPPORTED) return rc;          // not u8-valued: fp32 SIMT kernel below
+    }
     std::lock_guard<std::mutex> lk(ctx->mu);
     SFM_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t rows = nq;

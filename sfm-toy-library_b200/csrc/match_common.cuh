@@ -18,10 +18,11 @@ __device__ __forceinline__ void top2_insert(Top2& b, int d, int j) {
     else if (d < b.d1) { b.d1 = d; b.i1 = j; }
 }
 
-// tcgen05 path (match_tc.cu), 32-byte descriptors only
+// tcgen05 path (match_tc.cu): Hamming on 32-byte descriptors, L2 on u8-valued descriptors of dimension <= 128
 int match_tc_splits(int sm_count, int n_pairs, int nq_max, int nt_max);
-size_t match_tc_block_bytes();
+size_t match_tc_block_bytes(bool l2);
 int match_tc_block_rows();
 int match_tc_expand(sfmb200_ctx* ctx, const uint32_t* d_desc, const int2* d_blocks, int n_blocks, uint8_t* d_E);
-int match_tc_launch(sfmb200_ctx* ctx, const uint8_t* d_E, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
+int match_tc_expand_l2(sfmb200_ctx* ctx, const float* d_desc, int dim, const int2* d_blocks, int n_blocks, uint8_t* d_E, int32_t* d_norms, int* d_bad);
+int match_tc_launch(sfmb200_ctx* ctx, bool l2, const uint8_t* d_E, const int32_t* d_norms, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
                     int4* d_partial, int* d_error_flag);

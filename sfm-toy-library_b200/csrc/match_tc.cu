@@ -1,21 +1,25 @@
-// match_tc.cu -- K1 on the 5th-generation tensor cores: Hamming knn2 as an exact integer GEMM (tcgen05 + TMEM).
+// match_tc.cu -- K1 on the 5th-generation tensor cores: knn2 as an exact integer GEMM (tcgen05 + TMEM), two instantiations.
 //
-// For 256-bit descriptors  ham(q,t) = popc(q) + popc(t) - 2 * <q,t>  with q,t in {0,1}^256: the
-// inner products of a 128-query x 256-train tile are ONE accumulator tile of  tcgen05.mma.kind::i8  (u8 x u8 -> s32,
-// exact: every sum <= 256), M=128 N=256 K=32 per instruction, 8 instructions per tile, accumulators in TMEM.
-//   * operands: bits are mapped to SIGNED bytes +1/-1, so that  <a,b> = 256 - 2*hamming  and the epilogue needs one compare
-//     per element and no popcount terms.  The expansion happens ONCE per descriptor set (expand_blocks_kernel) into 64 KB
-//     blocks of 256 rows laid out in the UMMA K-major, no-swizzle ("interleaved") canonical form: core matrix = 8 rows x
-//     16 bytes, LBO = distance between the two 16-byte K chunks of one instruction, SBO = distance between 8-row groups
-//     (cute/arch/mma_sm100_desc.hpp, make_umma_desc<Major::K>).  A tile then travels HBM -> shared memory as plain
-//     cp.async.bulk copies completing on an mbarrier (no tensor map needed: a block is contiguous).
-//   * warp-specialised pipeline: a loader thread (3 shared-memory stages of the train operand), an MMA thread (8
-//     tcgen05.mma per tile, two 256-column accumulator stages = all 512 TMEM columns; tcgen05.commit releases the smem
-//     stage and publishes the accumulator), and 4 epilogue warps (one per TMEM lane quarter, thread = query row) that pull
-//     the accumulators with tcgen05.ld.32x32b.x32 and keep the running top-2 in registers with exactly the ordering of
-//     the XOR/POPC kernel (strict '<', ascending train index) -> bit-identical results, same merge / ratio-test /
-//     compaction epilogue (match.cu).
-// Only descriptor width 32 bytes (ORB, the reference's case); other widths use the XOR/POPC kernel.
+// HAMMING (the reference's ORB case, SfM2DFeatureUtilities.cpp:39-40, 59-60).  For 256-bit descriptors
+//   ham(q,t) = popc(q) + popc(t) - 2 <q,t>  with q,t in {0,1}^256; bits are mapped to SIGNED bytes +1/-1 so that
+//   <a,b> = 256 - 2*hamming: one accumulator tile of  tcgen05.mma.kind::i8  (s8 x s8 -> s32, exact), M=128 N=256 K=32 per
+//   instruction, 8 instructions per tile.
+// L2 (BASELINE.json configs[3] wording: SIFT-128; cv::BFMatcher(NORM_L2)).  SIFT descriptors are integer-valued 0..255, so
+//   |a-b|^2 = |a|^2 + |b|^2 - 2 <a,b>  with <a,b> <= 128*255^2 < 2^31 is EXACT in u8 x u8 -> s32: 4 instructions per tile; the
+//   train norms ride along in shared memory, the epilogue ranks  e = |b|^2 - 2<a,b>  and adds |a|^2 at the end.
+//
+//   * operands: expanded ONCE per descriptor set (expand kernels) into blocks of 256 rows in the UMMA K-major, no-swizzle
+//     ("interleaved") canonical form: core matrix = 8 rows x 16 bytes, LBO = distance between the 16-byte K chunks, SBO =
+//     distance between 8-row groups (cute/arch/mma_sm100_desc.hpp, make_umma_desc<Major::K>).  A tile travels HBM -> shared
+//     memory as plain cp.async.bulk copies completing on an mbarrier (no tensor map needed: a block is contiguous).
+//   * warp-specialised pipeline: a loader thread, an MMA thread (two 256-column accumulator stages = all 512 TMEM columns;
+//     tcgen05.commit releases the smem stage and publishes the accumulator) and 8 epilogue warps (two per TMEM lane quarter,
+//     thread = query row) that pull the accumulators with tcgen05.ld.32x32b.x32.
+//   * epilogue = the bound (round 1: ALU pipe 70 % busy, tensor pipe idle).  Hamming now keeps the running top-2 as two PACKED
+//     KEYS  key = (256 - 2 ham) << 16 | (0xFFFF - index)  -- larger is better, ties go to the lower index exactly like
+//     cv::batchDistance -- so an insert is a 3-instruction max/min network (no compare/select chains, no separate index
+//     registers), groups of 8 columns are skipped when no lane's group maximum (3-input max, DPX) beats its second best.
+// Bit-exact against the XOR/POPC kernel, the oracle and cv2 (tests/test_gpu_match.py); same merge / ratio / compaction epilogue.
 #include "common.cuh"
 #include "match_common.cuh"
 
@@ -23,16 +27,21 @@ namespace {
 
 constexpr int TC_M = 128;            // query rows per CTA  (UMMA M, TMEM lanes)
 constexpr int TC_N = 256;            // train rows per tile (UMMA N, TMEM columns per accumulator stage) = rows per expanded block
-constexpr int TC_K = 256;            // descriptor bits = K elements (one signed byte each after expansion)
-constexpr int TC_BLOCK_BYTES = TC_N * TC_K;              // 64 KB: one 256-row block of expanded operands
-constexpr int TC_A_BYTES = TC_M * TC_K;                  // 32 KB
-constexpr int TC_BSTAGES = 3;                            // shared-memory stages of the train operand
-constexpr int TC_EPI_WARPS = 8;                          // two per TMEM lane quarter: warps 0-3 take columns [0,128), warps 4-7 [128,256)
+constexpr int TC_EPI_WARPS = 8;      // two per TMEM lane quarter: warps 0-3 take columns [0,128), warps 4-7 [128,256)
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;      // + warp 8: loader, warp 9: MMA issuer
-constexpr int TC_SMEM = TC_A_BYTES + TC_BSTAGES * TC_BLOCK_BYTES + 256;
-// instruction descriptor (UMMA::InstrDescriptor): c_format S32 (2) @bit4, a/b format signed INT8 (1) @bits 7/10, K-major both,
-// n_dim = N>>3 @bit17, m_dim = M>>4 @bit24
-constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+constexpr int TC_NORM_SLOTS = 6;     // L2: ring of train-norm tiles (1 KB each); a slot is reused 6 tiles later, when its epilogue is long done
+
+template <bool L2> struct TcCfg {
+    static constexpr int KB = L2 ? 128 : 256;                  // operand bytes per row = K elements
+    static constexpr int BLOCK_BYTES = TC_N * KB;              // one 256-row block of expanded operands
+    static constexpr int A_BYTES = TC_M * KB;
+    static constexpr int BSTAGES = L2 ? 4 : 3;                 // shared-memory stages of the train operand
+    static constexpr int NORM_BYTES = L2 ? TC_NORM_SLOTS * TC_N * 4 : 0;
+    static constexpr int SMEM = A_BYTES + BSTAGES * BLOCK_BYTES + NORM_BYTES + 256;
+    // instruction descriptor (UMMA::InstrDescriptor): c_format S32 (2) @bit4, a/b format @bits 7/10 (0 = unsigned, 1 = signed int8),
+    // K-major both, n_dim = N>>3 @bit17, m_dim = M>>4 @bit24
+    static constexpr uint32_t IDESC = (2u << 4) | ((L2 ? 0u : 1u) << 7) | ((L2 ? 0u : 1u) << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -51,14 +60,14 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits16) {
     return make_uint4(pm1(bits16 & 0xF), pm1((bits16 >> 4) & 0xF), pm1((bits16 >> 8) & 0xF), pm1((bits16 >> 12) & 0xF));
 }
 
-// Expanded operand store (built once per descriptor set): per 256-row block 64 KB in the UMMA K-major no-swizzle canonical
-// layout  [16-byte K chunk kc 0..15][row group r/8][r%8][16 B]  ->  LBO = 4096 B between K chunks, SBO = 128 B between
-// 8-row groups.  A 128-row half of a block is the same layout at start offset +2048 B per chunk, so one store serves
-// both the query (M=128) and the train (N=256) operand.  Rows beyond the image are zero (contribute nothing).
+// Expanded operand store (built once per descriptor set): per 256-row block the UMMA K-major no-swizzle canonical layout
+//   [16-byte K chunk kc][row group r/8][r%8][16 B]   ->  LBO = 4096 B between K chunks, SBO = 128 B between 8-row groups.
+// A 128-row half of a block is the same layout at start offset +2048 B per chunk, so one store serves both the query (M=128)
+// and the train (N=256) operand.  Rows beyond the image are zero (contribute nothing).
 __global__ void __launch_bounds__(256) expand_blocks_kernel(const uint32_t* __restrict__ desc, const int2* __restrict__ blocks /* (first row, valid rows) */,
                                                             uint8_t* __restrict__ E) {
     const int2 b = blocks[blockIdx.x];
-    uint8_t* out = E + (size_t)blockIdx.x * TC_BLOCK_BYTES;
+    uint8_t* out = E + (size_t)blockIdx.x * TcCfg<false>::BLOCK_BYTES;
     for (int it = threadIdx.x; it < TC_N * 8; it += 256) {
         const int w = it / TC_N, r = it - w * TC_N;
         const bool valid = r < b.y;
@@ -68,6 +77,34 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const uint32_t* __re
         *reinterpret_cast<uint4*>(out + (size_t)(2 * w) * (TC_N * 16) + off) = lo;
         *reinterpret_cast<uint4*>(out + (size_t)(2 * w + 1) * (TC_N * 16) + off) = hi;
     }
+}
+// L2: float descriptors [rows][dim] (dim <= 128, zero-padded to 128) -> u8 operand blocks + squared norms.  *bad is raised when
+// a value is not an integer in [0, 255] (then the exact-GEMM formulation does not apply and the caller falls back to fp32).
+__global__ void __launch_bounds__(256) expand_l2_blocks_kernel(const float* __restrict__ desc, int dim, const int2* __restrict__ blocks,
+                                                               uint8_t* __restrict__ E, int32_t* __restrict__ norms, int* __restrict__ bad) {
+    const int2 b = blocks[blockIdx.x];
+    uint8_t* out = E + (size_t)blockIdx.x * TcCfg<true>::BLOCK_BYTES;
+    const int r = threadIdx.x;                                              // one row per thread
+    const bool valid = r < b.y;
+    const float* src = desc + (size_t)(b.x + (valid ? r : 0)) * dim;
+    int nrm = 0; bool ok = true;
+    const uint32_t off = (uint32_t)(r >> 3) * 128 + (uint32_t)(r & 7) * 16;
+    for (int kc = 0; kc < 8; ++kc) {
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int k = kc * 16 + j;
+            float f = (valid && k < dim) ? __ldg(src + k) : 0.f;
+            const int iv = (int)f;
+            ok = ok && (f == (float)iv) && iv >= 0 && iv <= 255;
+            const int c = min(max(iv, 0), 255);
+            nrm += c * c;
+            w[j >> 2] |= (uint32_t)c << (8 * (j & 3));
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)kc * (TC_N * 16) + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    norms[(size_t)blockIdx.x * TC_N + r] = valid ? nrm : 0;
+    if (!ok) atomicExch(bad, 1);
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -87,11 +124,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes),
                  "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+template <bool L2> __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate), "r"(0u) : "memory");
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TcCfg<L2>::IDESC), "r"(accumulate), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -104,20 +141,52 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  : "r"(taddr) : "memory");
 }
 
-// Warp-specialised: loader thread (cp.async.bulk of pre-expanded 64 KB blocks, 3 stages) -> MMA thread (8 x tcgen05.mma per
-// tile into one of 2 TMEM accumulator stages, commits release the smem stage and publish the accumulator) -> 4 epilogue
-// warps (tcgen05.ld, running top-2 per query row in registers).
-__global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8_t* __restrict__ E, const PairDesc* __restrict__ pairs, int qblocks,
-                                                                     int splits, int4* __restrict__ partial, int* __restrict__ error_flag) {
+// Hamming key: (256 - 2 ham) in the high half, 0xFFFF - (train index inside this CTA's split) in the low half.  The split of a
+// CTA covers at most 256 tiles = 65536 rows (match_tc_splits), so the index fits.  EMPTY = INT_MIN sorts below every key.
+constexpr int KEY_EMPTY = INT_MIN;
+
+// One 32-column chunk of the Hamming epilogue.  v = 256 - 2 ham (s32 accumulators of this lane's query row).  Per group of 8
+// columns: a 3-input-max tree, one vote, and -- only when SOME lane of the warp has a candidate above its second best -- the
+// insert network on packed keys: {k0, k1, key} -> the two largest (2 min/max per element + a 3-input max per two elements).
+// PART: columns >= ncols are zero padding of the image's last tile and must not become candidates.
+template <bool PART>
+__device__ __forceinline__ void hamming_chunk(const uint32_t (&v)[32], int cb, int ncols, int& k0, int& k1, int& thr) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        int m = __vimax3_s32((int)v[8 * g], (int)v[8 * g + 1], (int)v[8 * g + 2]);
+        m = __vimax3_s32(m, (int)v[8 * g + 3], (int)v[8 * g + 4]);
+        m = __vimax3_s32(m, (int)v[8 * g + 5], (int)v[8 * g + 6]);
+        m = max(m, (int)v[8 * g + 7]);
+        if (PART || __any_sync(0xffffffffu, m > thr)) {
+#pragma unroll
+            for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                int key = (int)v[j] * 65536 + (cb - j);
+                if (PART && j >= ncols) key = KEY_EMPTY;
+                const int hi = max(k0, key), lo = min(k0, key);
+                k1 = max(k1, lo); k0 = hi;
+            }
+            thr = k1 >> 16;             // a later candidate needs a strictly larger v: with equal v its index loses
+        }
+    }
+}
+
+// Warp-specialised: loader thread (cp.async.bulk of pre-expanded blocks) -> MMA thread (KB/32 x tcgen05.mma per tile into one
+// of 2 TMEM accumulator stages, commits release the smem stage and publish the accumulator) -> 8 epilogue warps (tcgen05.ld,
+// running top-2 per query row in registers).
+template <bool L2>
+__global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __restrict__ E, const int32_t* __restrict__ norms, const PairDesc* __restrict__ pairs,
+                                                             int qblocks, int splits, int4* __restrict__ partial, int* __restrict__ error_flag) {
+    using C = TcCfg<L2>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
-    uint8_t* sB = smem + TC_A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES + TC_BSTAGES * TC_BLOCK_BYTES);
+    uint8_t* sB = smem + C::A_BYTES;
+    int32_t* sNorm = reinterpret_cast<int32_t*>(smem + C::A_BYTES + C::BSTAGES * C::BLOCK_BYTES);      // [TC_NORM_SLOTS][TC_N]   (L2)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::A_BYTES + C::BSTAGES * C::BLOCK_BYTES + C::NORM_BYTES);
     uint64_t* a_full = bars;                 // [1]
-    uint64_t* full = bars + 1;               // [TC_BSTAGES] bytes of a B stage have landed
-    uint64_t* smem_free = full + TC_BSTAGES; // [TC_BSTAGES] the MMAs that read the stage have completed
-    uint64_t* acc_full = smem_free + TC_BSTAGES;   // [2] accumulator stage holds a finished tile
-    uint64_t* acc_empty = acc_full + 2;      // [2] the 4 epilogue warps have drained the stage
+    uint64_t* full = bars + 1;               // [BSTAGES] bytes of a B stage have landed
+    uint64_t* smem_free = full + C::BSTAGES; // [BSTAGES] the MMAs that read the stage have completed
+    uint64_t* acc_full = smem_free + C::BSTAGES;   // [2] accumulator stage holds a finished tile
+    uint64_t* acc_empty = acc_full + 2;      // [2] the epilogue warps have drained the stage
     __shared__ uint32_t tmem_base_s;
 
     const PairDesc pd = pairs[blockIdx.y];
@@ -131,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
-        for (int i = 0; i < TC_BSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(smem_free + i, 1); }
+        for (int i = 0; i < C::BSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(smem_free + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -145,6 +214,8 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     const uint32_t tmem_base = tmem_base_s;
     bool ok = true;
 
+    // Hamming: packed keys; L2: (e = |b|^2 - 2<a,b>, global index) pairs
+    int k0 = KEY_EMPTY, k1 = KEY_EMPTY;
     Top2 best = {INT_MAX, -1, INT_MAX, -1};
     // top-2 of the upper column half, merged by the lower-half warp at the end.  Lives in B stage 0: every bulk copy into a B
     // stage is consumed (waited on) before the last accumulator is published, whereas the query-tile copy into sA may still
@@ -152,16 +223,17 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
     int4* half_best = reinterpret_cast<int4*>(sB);
     if (warp == TC_EPI_WARPS) {
         if (lane == 0) {
-            // ---- loader: query tile (a 128-row half of a block: 16 chunks of 2 KB), then the train blocks
-            const uint8_t* qsrc = E + (size_t)(pd.q_blk + q_row0 / TC_N) * TC_BLOCK_BYTES + (size_t)((q_row0 / TC_M) & 1) * (TC_M * 16);
-            mbar_expect_tx(a_full, TC_A_BYTES);
-            for (int kc = 0; kc < 16; ++kc) bulk_g2s(sA + kc * (TC_M * 16), qsrc + (size_t)kc * (TC_N * 16), TC_M * 16, a_full);
+            // ---- loader: query tile (a 128-row half of a block: KB/16 chunks of 2 KB), then the train blocks (+ their norms)
+            const uint8_t* qsrc = E + (size_t)(pd.q_blk + q_row0 / TC_N) * C::BLOCK_BYTES + (size_t)((q_row0 / TC_M) & 1) * (TC_M * 16);
+            mbar_expect_tx(a_full, C::A_BYTES);
+            for (int kc = 0; kc < C::KB / 16; ++kc) bulk_g2s(sA + kc * (TC_M * 16), qsrc + (size_t)kc * (TC_N * 16), TC_M * 16, a_full);
             for (int t = 0; t < ntiles && ok; ++t) {
-                const int s = t % TC_BSTAGES, u = t / TC_BSTAGES;
+                const int s = t % C::BSTAGES, u = t / C::BSTAGES;
                 if (u > 0 && !mbar_wait(smem_free + s, (u - 1) & 1)) { ok = false; break; }
-                const uint8_t* src = E + (size_t)(pd.t_blk + tile0 + t) * TC_BLOCK_BYTES;
-                mbar_expect_tx(full + s, TC_BLOCK_BYTES);
-                for (int c = 0; c < 4; ++c) bulk_g2s(sB + s * TC_BLOCK_BYTES + c * (TC_BLOCK_BYTES / 4), src + c * (TC_BLOCK_BYTES / 4), TC_BLOCK_BYTES / 4, full + s);
+                const uint8_t* src = E + (size_t)(pd.t_blk + tile0 + t) * C::BLOCK_BYTES;
+                mbar_expect_tx(full + s, C::BLOCK_BYTES + (L2 ? TC_N * 4 : 0));
+                for (int c = 0; c < 4; ++c) bulk_g2s(sB + s * C::BLOCK_BYTES + c * (C::BLOCK_BYTES / 4), src + c * (C::BLOCK_BYTES / 4), C::BLOCK_BYTES / 4, full + s);
+                if (L2) bulk_g2s(sNorm + (t % TC_NORM_SLOTS) * TC_N, norms + (size_t)(pd.t_blk + tile0 + t) * TC_N, TC_N * 4, full + s);
             }
         }
     } else if (warp == TC_EPI_WARPS + 1) {
@@ -170,16 +242,16 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
             if (!mbar_wait(a_full, 0)) ok = false;
             const uint32_t a0 = smem_u32(sA);
             for (int t = 0; t < ntiles && ok; ++t) {
-                const int s = t % TC_BSTAGES, u = t / TC_BSTAGES, a = t & 1, ua = t >> 1;
+                const int s = t % C::BSTAGES, u = t / C::BSTAGES, a = t & 1, ua = t >> 1;
                 if (!mbar_wait(full + s, u & 1)) { ok = false; break; }
                 if (ua > 0 && !mbar_wait(acc_empty + a, (ua - 1) & 1)) { ok = false; break; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t b0 = smem_u32(sB + s * TC_BLOCK_BYTES), d = tmem_base + (uint32_t)a * TC_N;
+                const uint32_t b0 = smem_u32(sB + s * C::BLOCK_BYTES), d = tmem_base + (uint32_t)a * TC_N;
 #pragma unroll
-                for (int kk = 0; kk < TC_K / 32; ++kk) {                 // K = 32 bytes per instruction = two 16-byte chunks
+                for (int kk = 0; kk < C::KB / 32; ++kk) {                // K = 32 bytes per instruction = two 16-byte chunks
                     const uint64_t ad = make_smem_desc(a0 + 2 * kk * (TC_M * 16), TC_M * 16, 128);
                     const uint64_t bd = make_smem_desc(b0 + 2 * kk * (TC_N * 16), TC_N * 16, 128);
-                    tc_mma_i8(d, ad, bd, kk > 0 ? 1u : 0u);
+                    tc_mma_i8<L2>(d, ad, bd, kk > 0 ? 1u : 0u);
                 }
                 tc_commit(smem_free + s);          // B stage reusable once these MMAs have read it
                 tc_commit(acc_full + a);           // accumulator stage complete
@@ -187,17 +259,18 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
         }
     } else {
         // ---- epilogue warps.  Lane quarter q = warp & 3 (hardware rule: a warp reads TMEM lanes 32*(warp%4)..+31), column
-        // half h = warp >> 2.  v = 256 - 2*hamming, so "hamming < best.d1" is "v > thr".  Per 32-column chunk: one
-        // tcgen05.ld, then per 8-column group a max and a WARP-UNIFORM branch into a predicated (branch-free) insert
-        // sequence.  (Per-element branches made the first version epilogue-bound: 8.7 k warp instructions per tile.)
+        // half h = warp >> 2.  Per 32-column chunk: one tcgen05.ld, then per 8-column group a 3-input-max tree and a
+        // WARP-UNIFORM branch: only groups in which SOME lane has a candidate better than its current second best run the
+        // insert sequence (expected: a third of the groups over a 5000-row image).
         const int q = warp & 3, h = warp >> 2;
-        int thr = INT_MIN;
+        int thr = L2 ? INT_MAX : INT_MIN;                                 // Hamming: v must exceed it; L2: e must be below it
         for (int t = 0; t < ntiles && ok; ++t) {
             const int a = t & 1, ua = t >> 1;
             if (!mbar_wait(acc_full + a, ua & 1)) { ok = false; break; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int t_row0 = (tile0 + t) * TC_N, t_rows = min(TC_N, pd.nt - t_row0);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * TC_N + (uint32_t)h * (TC_N / 2);
+            const int32_t* nrm = sNorm + (t % TC_NORM_SLOTS) * TC_N;
 #pragma unroll 1
             for (int cc = 0; cc < TC_N / 2; cc += 32) {
                 const int c0 = h * (TC_N / 2) + cc;
@@ -205,25 +278,30 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
                 uint32_t v[32];
                 tc_ld32(taddr + cc, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // two-level filter: 8-wide group maxima, one vote per group; only groups in which SOME lane has a candidate
-                // better than its current second-best run the predicated insert sequence (expected: a fraction of a group
-                // per chunk once a few hundred candidates have been seen)
-                const bool partial = c0 + 32 > t_rows;                    // zero-padded rows would look like hamming 128
+                const bool part = c0 + 32 > t_rows;                       // zero-padded rows must not become candidates
+                if (!L2) {
+                    const int cb = 0xFFFF - (t * TC_N + c0);              // low half of the key of column 0 of this chunk
+                    if (!part) hamming_chunk<false>(v, cb, 32, k0, k1, thr);
+                    else hamming_chunk<true>(v, cb, t_rows - c0, k0, k1, thr);      // last tile of the image only
+                } else {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    int m = (int)v[8 * g];
+                    for (int g = 0; g < 4; ++g) {
+                        const int4 n0 = *reinterpret_cast<const int4*>(nrm + c0 + 8 * g), n1 = *reinterpret_cast<const int4*>(nrm + c0 + 8 * g + 4);
+                        int e[8] = {n0.x - 2 * (int)v[8 * g], n0.y - 2 * (int)v[8 * g + 1], n0.z - 2 * (int)v[8 * g + 2], n0.w - 2 * (int)v[8 * g + 3],
+                                    n1.x - 2 * (int)v[8 * g + 4], n1.y - 2 * (int)v[8 * g + 5], n1.z - 2 * (int)v[8 * g + 6], n1.w - 2 * (int)v[8 * g + 7]};
+                        int m = __vimin3_s32(e[0], e[1], e[2]);
+                        m = __vimin3_s32(m, e[3], e[4]); m = __vimin3_s32(m, e[5], e[6]); m = min(m, e[7]);
+                        if (__any_sync(0xffffffffu, m < thr) || part) {
 #pragma unroll
-                    for (int j = 1; j < 8; ++j) m = max(m, (int)v[8 * g + j]);
-                    if (__any_sync(0xffffffffu, m > thr) || partial) {
-#pragma unroll
-                        for (int j = 8 * g; j < 8 * g + 8; ++j) {
-                            const int d = (TC_K - (int)v[j]) >> 1, idx = t_row0 + c0 + j;
-                            const bool valid = !partial || (c0 + j < t_rows);
-                            const bool lt0 = valid && d < best.d0, lt1 = valid && d < best.d1;
-                            const int nd1 = lt0 ? best.d0 : (lt1 ? d : best.d1), ni1 = lt0 ? best.i0 : (lt1 ? idx : best.i1);
-                            best.d0 = lt0 ? d : best.d0; best.i0 = lt0 ? idx : best.i0; best.d1 = nd1; best.i1 = ni1;
+                            for (int j = 0; j < 8; ++j) {
+                                const int d = e[j], idx = t_row0 + c0 + 8 * g + j;
+                                const bool valid = !part || (c0 + 8 * g + j < t_rows);
+                                const bool lt0 = valid && d < best.d0, lt1 = valid && d < best.d1;
+                                const int nd1 = lt0 ? best.d0 : (lt1 ? d : best.d1), ni1 = lt0 ? best.i0 : (lt1 ? idx : best.i1);
+                                best.d0 = lt0 ? d : best.d0; best.i0 = lt0 ? idx : best.i0; best.d1 = nd1; best.i1 = ni1;
+                            }
+                            thr = best.d1;
                         }
-                        thr = best.d1 == INT_MAX ? INT_MIN : TC_K - 2 * best.d1;
                     }
                 }
             }
@@ -231,23 +309,39 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_hamming_tc_kernel(const uint8
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + a);
         }
-        if (h == 1) half_best[q * 32 + lane] = make_int4(best.d0, best.i0, best.d1, best.i1);
+        if (h == 1) half_best[q * 32 + lane] = L2 ? make_int4(best.d0, best.i0, best.d1, best.i1) : make_int4(k0, k1, 0, 0);
     }
     if (!ok) atomicExch(error_flag, 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp < 4) {
-        // merge the two column halves: lexicographic (distance, index), the order candidates would have arrived in
         const int4 o = half_best[warp * 32 + lane];
-        auto lex_lt = [](int d, int i, int d2, int i2) { return d < d2 || (d == d2 && i < i2); };
-        auto ins = [&](int d, int i) {
-            if (i < 0) return;
-            if (best.i0 < 0 || lex_lt(d, i, best.d0, best.i0)) { best.d1 = best.d0; best.i1 = best.i0; best.d0 = d; best.i0 = i; }
-            else if (best.i1 < 0 || lex_lt(d, i, best.d1, best.i1)) { best.d1 = d; best.i1 = i; }
-        };
-        ins(o.x, o.y); ins(o.z, o.w);
         const int row = q_row0 + warp * 32 + lane;
-        if (row < pd.nq) partial[(size_t)(pd.out_row + row) * splits + sp] = make_int4(best.d0, best.i0, best.d1, best.i1);
+        if (!L2) {
+            // merge the two column halves with the same network, then unpack
+            int hi = max(k0, o.x), lo = min(k0, o.x); k1 = max(k1, lo); k0 = hi;
+            hi = max(k0, o.y); lo = min(k0, o.y); k1 = max(k1, lo); k0 = hi;
+            auto unpack = [&](int key, int& d, int& i) {
+                if (key == KEY_EMPTY) { d = INT_MAX; i = -1; return; }
+                d = (256 - (key >> 16)) >> 1; i = tile0 * TC_N + (0xFFFF - (key & 0xFFFF));
+            };
+            int d0, i0, d1, i1; unpack(k0, d0, i0); unpack(k1, d1, i1);
+            if (row < pd.nq) partial[(size_t)(pd.out_row + row) * splits + sp] = make_int4(d0, i0, d1, i1);
+        } else {
+            // lexicographic (e, index) merge, then |a|^2 + e = squared distance (exact integer)
+            auto lex_lt = [](int d, int i, int d2, int i2) { return d < d2 || (d == d2 && i < i2); };
+            auto ins = [&](int d, int i) {
+                if (i < 0) return;
+                if (best.i0 < 0 || lex_lt(d, i, best.d0, best.i0)) { best.d1 = best.d0; best.i1 = best.i0; best.d0 = d; best.i0 = i; }
+                else if (best.i1 < 0 || lex_lt(d, i, best.d1, best.i1)) { best.d1 = d; best.i1 = i; }
+            };
+            ins(o.x, o.y); ins(o.z, o.w);
+            if (row < pd.nq) {
+                const int na = norms[(size_t)(pd.q_blk + q_row0 / TC_N) * TC_N + (q_row0 % TC_N) + warp * 32 + lane];
+                partial[(size_t)(pd.out_row + row) * splits + sp] =
+                    make_int4(best.i0 >= 0 ? na + best.d0 : INT_MAX, best.i0, best.i1 >= 0 ? na + best.d1 : INT_MAX, best.i1);
+            }
+        }
     }
     if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
@@ -258,10 +352,11 @@ int match_tc_splits(int sm_count, int n_pairs, int nq_max, int nt_max) {
     const int qblocks = ceil_div(nq_max, TC_M), tiles = ceil_div(nt_max, TC_N);
     int splits = 1;
     while ((int64_t)qblocks * n_pairs * splits < 2LL * sm_count && splits * 2 <= tiles && splits < 16) splits *= 2;
+    while (ceil_div(tiles, splits) > 256) splits *= 2;       // the 16-bit index field of the Hamming key: <= 256 tiles per split
     return splits;
 }
 
-size_t match_tc_block_bytes() { return TC_BLOCK_BYTES; }
+size_t match_tc_block_bytes(bool l2) { return l2 ? TcCfg<true>::BLOCK_BYTES : TcCfg<false>::BLOCK_BYTES; }
 int match_tc_block_rows() { return TC_N; }
 
 int match_tc_expand(sfmb200_ctx* ctx, const uint32_t* d_desc, const int2* d_blocks, int n_blocks, uint8_t* d_E) {
@@ -270,14 +365,25 @@ int match_tc_expand(sfmb200_ctx* ctx, const uint32_t* d_desc, const int2* d_bloc
     SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }
+int match_tc_expand_l2(sfmb200_ctx* ctx, const float* d_desc, int dim, const int2* d_blocks, int n_blocks, uint8_t* d_E, int32_t* d_norms, int* d_bad) {
+    if (n_blocks == 0) return SFMB200_OK;
+    expand_l2_blocks_kernel<<<n_blocks, 256, 0, ctx->stream>>>(d_desc, dim, d_blocks, d_E, d_norms, d_bad);
+    SFM_LAUNCH_CHECK(ctx);
+    return SFMB200_OK;
+}
 
-int match_tc_launch(sfmb200_ctx* ctx, const uint8_t* d_E, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
+int match_tc_launch(sfmb200_ctx* ctx, bool l2, const uint8_t* d_E, const int32_t* d_norms, const PairDesc* d_pairs, int n_pairs, int nq_max, int splits,
                     int4* d_partial, int* d_error_flag) {
     // the attribute is per device and the context is per device; ctx->mu is held by every caller
-    if (!ctx->tc_attr_set) { SFM_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); ctx->tc_attr_set = true; }
+    if (!ctx->tc_attr_set) {
+        SFM_CUDA(ctx, cudaFuncSetAttribute(knn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<false>::SMEM));
+        SFM_CUDA(ctx, cudaFuncSetAttribute(knn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<true>::SMEM));
+        ctx->tc_attr_set = true;
+    }
     const int qblocks = ceil_div(nq_max, TC_M);
     dim3 grid(qblocks * splits, n_pairs);
-    knn2_hamming_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(d_E, d_pairs, qblocks, splits, d_partial, d_error_flag);
+    if (l2) knn2_tc_kernel<true><<<grid, TC_THREADS, TcCfg<true>::SMEM, ctx->stream>>>(d_E, d_norms, d_pairs, qblocks, splits, d_partial, d_error_flag);
+    else knn2_tc_kernel<false><<<grid, TC_THREADS, TcCfg<false>::SMEM, ctx->stream>>>(d_E, d_norms, d_pairs, qblocks, splits, d_partial, d_error_flag);
     SFM_LAUNCH_CHECK(ctx);
     return SFMB200_OK;
 }

@@ -93,5 +93,23 @@ def main():
                   s["message"], s["num_iterations"], s["initial_cost"], s["final_cost"]))
 
 
+def sift_golden():
+    """Real SIFT descriptors of two crazyhorse images (the reference's legacy matcher, legacy/SfMToyLib_Old/GPUSURFFeatureMatcher.cpp:
+    100-124, is an L2 knn + ratio test; BASELINE.json configs[3] says SIFT-128) + cv2.BFMatcher(NORM_L2) knnMatch with the ratio test."""
+    from oracle import cv2_reference as ref
+    files = sorted(glob.glob(os.path.join(DATASET, "*.JPG")))
+    descs = []
+    for f in files[:2]:
+        img = cv2.imread(f, cv2.IMREAD_GRAYSCALE)
+        kps, d = cv2.SIFT_create(3000).detectAndCompute(img, None)
+        assert np.array_equal(d, np.round(d)) and d.min() >= 0 and d.max() <= 255       # SIFT output is u8-valued
+        descs.append(d[:3000].astype(np.float32))
+    q, t = descs
+    mq, mt, md = ref.match_features(q, t, norm="l2"); rq, rt, rd = ref.match_features(t, q, norm="l2")
+    np.savez_compressed(os.path.join(OUT, "sift_crazyhorse.npz"), q=q.astype(np.uint8), t=t.astype(np.uint8), mq=mq, mt=mt, md=md, rq=rq, rt=rt, rd=rd)
+    print("sift:", q.shape, t.shape, "survivors", len(mq), len(rq))
+
+
 if __name__ == "__main__":
     main()
+    sift_golden()

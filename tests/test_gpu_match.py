@@ -131,3 +131,46 @@ def test_cache_flush_when_arena_is_full(ctx, oracle):
     imgs = [synth.make_descriptors(100 + i, 9000) for i in range(20)]     # 180 k rows > the 128 k row arena
     for i in range(1, 20):
         _same(ctx.match_knn2_ratio(imgs[i][:700], imgs[i - 1]), oracle.match_hamming(imgs[i][:700], imgs[i - 1]))
+
+
+@pytest.mark.parametrize("nq,nt,dim", [(1, 2, 128), (300, 257, 128), (2000, 2100, 128), (5000, 5000, 128), (700, 650, 64), (129, 1000, 100)])
+def test_l2_exact_u8_gemm_vs_oracle(ctx, oracle, nq, nt, dim):
+    """SIFT-like (integer-valued) descriptors: the tcgen05 u8 x u8 -> s32 GEMM path (|a-b|^2 = |a|^2 + |b|^2 - 2<a,b>, exact)
+    gives the indices AND float distances of cv::BFMatcher(NORM_L2) (= the oracle's float loop, pinned to cv2 by the golden)."""
+    t = synth.make_sift_like(nt % 50, nt, dim=dim); q = synth.make_sift_like(nq % 40 + 60, nq, dim=dim, prev=t)
+    q[::7] = t[np.arange(len(q[::7])) % nt]                                   # exact duplicates: distance 0 and ties
+    _same(ctx.match_knn2_ratio_l2(q, t), oracle.match_l2(q, t))
+    _same(ctx.match_knn2_ratio_l2(q, t, ratio=2.0), oracle.match_l2(q, t, ratio=2.0))    # every row survives: all 2-NN distances checked
+
+
+def test_l2_batched_all_pairs_and_simt_fallback(ctx, oracle, monkeypatch):
+    imgs = [synth.make_sift_like(i, 900 + 37 * i, prev=None if i == 0 else None) for i in range(4)]
+    for i in range(1, 4):
+        imgs[i][::5] = imgs[i - 1][:len(imgs[i][::5])]
+    ds = ctx.descriptor_set(imgs, norm="l2")
+    pairs = [(i, j) for i in range(4) for j in range(i + 1, 4)]
+    for (i, j), got in zip(pairs, ds.match_pairs(pairs)):
+        _same(got, oracle.match_l2(imgs[i], imgs[j]))
+    ds.close()
+    # non-integer descriptors cannot use the exact GEMM: the set is refused, the per-pair call falls back to the fp32 SIMT kernel
+    a = imgs[0][:300] + 0.25; b = imgs[1][:280] * 0.5
+    with pytest.raises(capi.SfmB200Error):
+        ctx.descriptor_set([a, b], norm="l2")
+    q, t, d = ctx.match_knn2_ratio_l2(b, a, ratio=2.0)
+    oq, ot, od = oracle.match_l2(b, a, ratio=2.0)
+    np.testing.assert_array_equal(q, oq); np.testing.assert_array_equal(t, ot); np.testing.assert_allclose(d, od, rtol=1e-6)
+    monkeypatch.setenv("SFMB200_MATCH_L2", "simt")                             # the SIMT kernel on integer data: same answer
+    _same(ctx.match_knn2_ratio_l2(imgs[1], imgs[0]), oracle.match_l2(imgs[1], imgs[0]))
+
+
+def test_l2_real_sift_golden(ctx, golden):
+    """Real SIFT descriptors (cv2.SIFT_create on two crazyhorse images, tests/golden/make_cfg1.py) vs cv2.BFMatcher(NORM_L2)."""
+    g = golden("sift_crazyhorse.npz")
+    _same(ctx.match_knn2_ratio_l2(g["q"], g["t"]), (g["mq"], g["mt"], g["md"]))
+    _same(ctx.match_knn2_ratio_l2(g["t"], g["q"]), (g["rq"], g["rt"], g["rd"]))
+
+
+def test_hamming_many_tiles_per_split(ctx, oracle):
+    """One query block against 70 000 train rows: the packed-key epilogue's 16-bit index field (<= 256 tiles per split)."""
+    t = synth.make_descriptors(3, 70000); q = synth.make_descriptors(4, 100, prev=t)
+    _same(ctx.match_knn2_ratio(q, t), oracle.match_hamming(q, t))

@@ -47,3 +47,12 @@ def test_match_hamming_vs_cv2_live(oracle):
         rq, rt, rd = ref.match_features(q, t)
         np.testing.assert_array_equal(mq, rq); np.testing.assert_array_equal(mt, rt); np.testing.assert_array_equal(md, rd)
         assert len(mq) > 20
+
+
+def test_match_l2_real_sift_golden(oracle, golden):
+    """Real SIFT descriptors of two crazyhorse images vs cv2.BFMatcher(NORM_L2) + ratio test (tests/golden/make_cfg1.py:sift_golden)."""
+    g = golden("sift_crazyhorse.npz")
+    q = g["q"].astype(np.float32); t = g["t"].astype(np.float32)
+    for got, want in ((oracle.match_l2(q, t), ("mq", "mt", "md")), (oracle.match_l2(t, q), ("rq", "rt", "rd"))):
+        for a, k in zip(got, want):
+            np.testing.assert_array_equal(a, g[k])
