@@ -240,6 +240,20 @@ def angle_axis_to_rotmat(aa):
 class DescriptorSet:
     """sfmb200_descset: the descriptors of all images resident in HBM; all-pairs matching in one call."""
 
+    @classmethod
+    def from_packed(cls, ctx, allrows, sizes, norm="hamming"):
+        """Rows of all images already concatenated (what a C++ host hands to sfmb200_descset_create): no per-call numpy copy."""
+        self = cls.__new__(cls)
+        self.ctx = ctx; self.norm = norm; self.sizes = [int(x) for x in sizes]
+        off = np.zeros(len(self.sizes) + 1, np.int32); off[1:] = np.cumsum(self.sizes)
+        self._h = C.c_void_p()
+        if norm == "hamming":
+            ctx._check(lib().sfmb200_descset_create(ctx._h, _p(allrows, C.c_uint8), _p(off, C.c_int32), len(self.sizes), allrows.shape[1], C.byref(self._h)))
+        else:
+            ctx._check(lib().sfmb200_descset_create_l2(ctx._h, _p(allrows, C.c_float), _p(off, C.c_int32), len(self.sizes), allrows.shape[1], C.byref(self._h)))
+        ctx._adopt(self)
+        return self
+
     def __init__(self, ctx, desc_list, norm="hamming"):
         """norm="hamming": uint8 rows (ORB; the reference's case).  norm="l2": float32 rows with integer values in [0, 255] and
         dim <= 128 (SIFT): exact u8 GEMM on the tensor cores, distances like cv2.BFMatcher(NORM_L2)."""

@@ -381,12 +381,16 @@ int sfmb200_descset_create_l2(sfmb200_ctx* ctx, const float* desc, const int32_t
     }
     s->img_blk[n_img] = (int)blocks.size();
     const size_t fbytes = (size_t)img_off[n_img] * dim * sizeof(float), nb = std::max<size_t>(blocks.size(), 1);
+    // float staging + block list live in the context's reusable scratch (no cudaMalloc / cudaFree of 100+ MB per set)
     float* d_f = nullptr; int2* d_blocks = nullptr; int* d_bad = nullptr;
-    cudaError_t e = cudaMalloc(&d_f, fbytes + 16);
+    cudaError_t e = ctx->scratch2.reserve(Carver::pad(fbytes + 16) + Carver::pad(nb * sizeof(int2) + 16) + 512);
+    if (e == cudaSuccess) {
+        Carver cv(ctx->scratch2.p);
+        d_f = cv.take<float>((size_t)img_off[n_img] * dim + 4); d_blocks = cv.take<int2>(nb + 2);
+        d_bad = reinterpret_cast<int*>(d_blocks + nb);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&s->d_exp, nb * match_tc_block_bytes(true));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_norms, nb * br * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_blocks, nb * sizeof(int2) + 16);
-    d_bad = reinterpret_cast<int*>(d_blocks + nb);
     int h_bad = 0, rc = SFMB200_OK;
     if (e == cudaSuccess && fbytes) e = cudaMemcpyAsync(d_f, desc, fbytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
@@ -396,8 +400,6 @@ int sfmb200_descset_create_l2(sfmb200_ctx* ctx, const float* desc, const int32_t
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (d_f) cudaFree(d_f);
-    if (d_blocks) cudaFree(d_blocks);
     if (e != cudaSuccess || rc || h_bad) {
         if (s->d_exp) cudaFree(s->d_exp);
         if (s->d_norms) cudaFree(s->d_norms);

@@ -271,13 +271,9 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
             const int t_row0 = (tile0 + t) * TC_N, t_rows = min(TC_N, pd.nt - t_row0);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * TC_N + (uint32_t)h * (TC_N / 2);
             const int32_t* nrm = sNorm + (t % TC_NORM_SLOTS) * TC_N;
-#pragma unroll 1
-            for (int cc = 0; cc < TC_N / 2; cc += 32) {
+            // one 32-column chunk of this warp's column half
+            auto chunk = [&](const uint32_t (&v)[32], int cc) {
                 const int c0 = h * (TC_N / 2) + cc;
-                if (c0 >= t_rows) break;                                  // warp-uniform
-                uint32_t v[32];
-                tc_ld32(taddr + cc, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const bool part = c0 + 32 > t_rows;                       // zero-padded rows must not become candidates
                 if (!L2) {
                     const int cb = 0xFFFF - (t * TC_N + c0);              // low half of the key of column 0 of this chunk
@@ -304,7 +300,16 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
                         }
                     }
                 }
-            }
+            };
+            // software pipeline over the 4 chunks: the tcgen05.ld of the next chunk is in flight while this one is ranked
+            const int nch = min(4, (t_rows - h * (TC_N / 2) + 31) / 32);  // chunks of this column half that hold real rows (warp-uniform)
+            uint32_t va[32], vb[32];
+            if (nch > 0) { tc_ld32(taddr, va); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+            if (nch > 1) tc_ld32(taddr + 32, vb);
+            if (nch > 0) chunk(va, 0);
+            if (nch > 1) { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); if (nch > 2) tc_ld32(taddr + 64, va); chunk(vb, 32); }
+            if (nch > 2) { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); if (nch > 3) tc_ld32(taddr + 96, vb); chunk(va, 64); }
+            if (nch > 3) { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); chunk(vb, 96); }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + a);

