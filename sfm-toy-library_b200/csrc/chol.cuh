@@ -117,7 +117,9 @@ __device__ __forceinline__ bool chol_tile_factor2(double (&col)[NB / (2 * PANEL_
                 if (lane == j1) invd[j1] = inv1;
             }
             chol_factor_barrier<true>();
-            if ((ow & 1) && groups_done && threadIdx.x == 0) { __threadfence_block(); *groups_done = (j1 + 1) / PANEL_WARPS; }
+            // a 4-column group is final: warp 0 hands it to the streaming warp through the group's named barrier (ids 2..9,
+            // 32 + 32 threads; warp 0 only arrives) -- the hand-over compute-sanitizer's racecheck can see
+            if ((ow & 1) && groups_done && w == 0) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(2 + (j1 + 1) / PANEL_WARPS - 1) : "memory"); }
             const double m0 = cb[pp][0][lane], m1 = cb[pp][1][lane];
 #pragma unroll
             for (int q = 0; q < NB / (2 * PANEL_WARPS); ++q) {
@@ -556,12 +558,11 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
                         Ls[lane][PANEL_WARPS * g] = v0.x; Ls[lane][PANEL_WARPS * g + 1] = v0.y; Ls[lane][PANEL_WARPS * g + 2] = v1.x; Ls[lane][PANEL_WARPS * g + 3] = v1.y;
                     }
                     if (lane < PANEL_WARPS) invd[PANEL_WARPS * g + lane] = __ldcg(dinv + c * NB + PANEL_WARPS * g + lane);
-                    __syncwarp();
-                    if (lane == 0) {
-                        while (*(volatile int*)&ls_groups != g) { }
-                        __threadfence_block();
-                        *(volatile int*)&ls_groups = g + 1;
-                    }
+                    // hand group g to the solver warp: a named barrier per group (ids 2..9, this warp + the solver warp = 64
+                    // threads): the loader arrives and goes on, the solver syncs on the groups in order.  (A spin on a shared-memory
+                    // counter did the same job; the barrier is what compute-sanitizer's racecheck understands.)
+                    __threadfence_block();
+                    asm volatile("bar.arrive %0, 64;" ::"r"(2 + g) : "memory");
                 }
                 if (!ok) abort_flag = 1;
             } else {
@@ -570,12 +571,9 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
                 for (int q = 0; q < NB; q += 2) { const double2 v = *reinterpret_cast<const double2*>(&Xs[lane][q]); b[q] = v.x; b[q + 1] = v.y; }
 #pragma unroll 1
                 for (int g = 0; g < NB / PANEL_WARPS; ++g) {
-                    while (*(volatile int*)&ls_groups <= g) { }
-                    __threadfence_block();
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + g) : "memory");
                     chol_tile_trsm_group(b, Ls, invd, PANEL_WARPS * g);
                 }
-                __syncwarp();
-                if (lane == 0) ls_groups = 0;                       // the loaders are done (they set 8)
                 if (!merged) {
                     double* dst = A + (size_t)(i * NB + lane) * npad + c * NB;
 #pragma unroll
@@ -623,8 +621,7 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
             } else {
 #pragma unroll 1
                 for (int g = 0; g < NB / PANEL_WARPS; ++g) {
-                    while (*(volatile int*)&groups_done <= g) __nanosleep(40);      // a hot spin would share warp 0's issue slots
-                    __threadfence_block();
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + g) : "memory");         // group g of the factor is in Ls / invd
                     if (lane >= PANEL_WARPS * g) {
                         double* dst = A + (size_t)(i * NB + lane) * npad + i * NB + PANEL_WARPS * g;
                         *reinterpret_cast<double2*>(dst) = make_double2(Ls[lane][PANEL_WARPS * g], Ls[lane][PANEL_WARPS * g + 1]);
@@ -635,7 +632,6 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
                     if (lane == 0) { __threadfence(); st_relaxed_gpu_u32(progress + i, pbase + g + 1); }
                 }
                 CHOL_TRACE_W4(6);
-                if (lane == 0) groups_done = 0;                     // for this CTA's next diagonal tile (the factor warps are done)
                 if (Linv) {             // off the critical path: L(i,i)^-1 (row-major) for the back substitution.  X L^T = I, X = L^-T
                     double b[NB];
 #pragma unroll
