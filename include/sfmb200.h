@@ -208,6 +208,26 @@ int sfmb200_ba_solve(sfmb200_ctx* ctx, const sfmb200_ba_options* opt, int nc, in
 void sfmb200_rotmat_to_angle_axis_f32(const float* R_rowmajor, float* angle_axis);
 void sfmb200_angle_axis_to_rotmat(const double* angle_axis, double* R_rowmajor);
 
+/* ---- f-2 ("next" row of SURVEY.md 8): batched RANSAC hypothesis scoring ----------------------------------- */
+/*
+ * The three RANSAC stages on either side of triangulation in the reference driver:
+ *   findHomographyInliers        SfMStereoUtilities.cpp:51-72   cv::findHomography(RANSAC, RANSAC_THRESHOLD = 10 px) -> countNonZero(mask)
+ *   findCameraMatricesFromMatch  SfMStereoUtilities.cpp:74-118  cv::findEssentialMat(focal, pp, RANSAC, 0.999, 1.0) -> mask prunes the matches
+ *   findCameraPoseFrom2D3DMatch  SfMStereoUtilities.cpp:208-243 cv::solvePnPRansac(100 iterations, 10 px, 0.99) -> inlier ratio test
+ * OpenCV scores one hypothesis at a time; this scores ALL `nh` hypotheses of a run against all `n` correspondences in one launch
+ * sequence, with OpenCV's error formulas and arithmetic types (float transfer error for H, double Sampson error for E, squared
+ * float reprojection error for a pose) and its inlier rule  err <= (float)(threshold^2).  Hypotheses are generated on the host.
+ *   model      SFMB200_MODEL_HOMOGRAPHY: a = left points [n*2], b = right points [n*2], hyp [nh*9] row-major H (any scale; normalised to h22 = 1)
+ *              SFMB200_MODEL_ESSENTIAL:  a, b as above (PIXELS), hyp [nh*9] E, aux9 = {focal, cx, cy, ...}: points are normalised
+ *                                        (x - cx)/focal in double like cv::findEssentialMat(points, focal, pp); pass threshold / focal
+ *              SFMB200_MODEL_POSE:       a = 3D points [n*3], b = image points [n*2], hyp [nh*12] row-major [R|t], aux9 = K (row-major 3x3)
+ *   outputs    inlier_counts [nh] (may be NULL); *best_index = hypothesis with the most inliers (ties -> lowest index, the one
+ *              OpenCV's sequential loop would have kept), -1 when nh == 0; best_mask [n] (may be NULL) = its inlier mask.
+ */
+enum { SFMB200_MODEL_HOMOGRAPHY = 0, SFMB200_MODEL_ESSENTIAL = 1, SFMB200_MODEL_POSE = 2 };
+int sfmb200_ransac_score(sfmb200_ctx* ctx, int model, const float* a, const float* b, int n, const double* hyp, int nh, const double* aux9,
+                         double threshold, int32_t* inlier_counts, int32_t* best_index, uint8_t* best_mask);
+
 /* ---- multi-GPU plumbing (NCCL, one process per GPU) ------------------------------------------------------ */
 #define SFMB200_UNIQUE_ID_BYTES 128
 int sfmb200_comm_unique_id(uint8_t* id /* [SFMB200_UNIQUE_ID_BYTES] */);       /* rank 0, then broadcast by the host */

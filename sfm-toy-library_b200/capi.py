@@ -15,6 +15,7 @@ UNIQUE_ID_BYTES = 128
 RATIO_REFERENCE = float(np.float64(np.float32(0.8)))     # NN_MATCH_RATIO = (double)0.8f, SfM2DFeatureUtilities.cpp:35
 MIN_REPROJECTION_ERROR = 10.0                            # SfMStereoUtilities.cpp:42
 CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
+MODEL_HOMOGRAPHY, MODEL_ESSENTIAL, MODEL_POSE = 0, 1, 2
 
 _lib = None
 
@@ -188,6 +189,21 @@ class Context:
                                            _p(pts, C.c_double), C.byref(f), _p(obs_xy, C.c_float), _p(obs_cam, C.c_int32),
                                            _p(pt_off, C.c_int32), C.byref(s)))
         return cams, pts, f.value, s.as_dict()
+
+    # ------------------------------------------------------------------ f-2 RANSAC hypothesis scoring
+    def ransac_score(self, model, a, b, hyps, aux=None, threshold=10.0, want_mask=True):
+        """sfmb200_ransac_score: model 0 homography / 1 essential / 2 pose.  Returns (inlier counts [nh], best index, best mask [n])."""
+        a = np.ascontiguousarray(a, np.float32).reshape(-1, 3 if model == 2 else 2); b = np.ascontiguousarray(b, np.float32).reshape(-1, 2)
+        hd = 12 if model == 2 else 9
+        hyps = np.ascontiguousarray(hyps, np.float64).reshape(-1, hd)
+        n, nh = b.shape[0], hyps.shape[0]
+        aux9 = np.zeros(9)
+        if aux is not None:
+            av = np.asarray(aux, np.float64).reshape(-1); aux9[:len(av)] = av
+        counts = np.zeros(max(nh, 1), np.int32); best = C.c_int32(-1); mask = np.zeros(max(n, 1), np.uint8)
+        self._check(lib().sfmb200_ransac_score(self._h, int(model), _p(a, C.c_float), _p(b, C.c_float), n, _p(hyps, C.c_double), nh, _p(aux9, C.c_double),
+                                               C.c_double(float(threshold)), _p(counts, C.c_int32), C.byref(best), _p(mask, C.c_uint8) if want_mask else None))
+        return counts[:nh], int(best.value), mask[:n]
 
     # ------------------------------------------------------------------ multi-GPU
     def comm_init(self, unique_id, rank, nranks):
