@@ -100,5 +100,8 @@ def test_stage_functions_and_whole_replay(ctx, cfg1):
                      findCameraMatricesFromMatch=lambda *a: ransac.findCameraMatricesFromMatch(*a, ctx=ctx),
                      findCameraPoseFrom2D3DMatch=lambda *a: ransac.findCameraPoseFrom2D3DMatch(*a, ctx=ctx))
     sfm.runSfM()
-    assert len(sfm.mDoneViews) == 7 and len(sfm.mReconstructionCloud) > 600
-    assert abs(float(sfm.mIntrinsics.K[0, 0]) - 2500) < 800
+    # statistical agreement with the cv2-RANSAC replay of the fixture (1430 points, focal refined from 2500 to 965.6 by the six
+    # bundle adjustments): all 7 views registered, cloud within 30 %, focal within 10 %
+    assert len(sfm.mDoneViews) == 7
+    assert abs(len(sfm.mReconstructionCloud) - len(cfg1.g["final_cloud"])) < 0.3 * len(cfg1.g["final_cloud"])
+    assert abs(float(sfm.mIntrinsics.K[0, 0]) - float(cfg1.g["final_K"][0, 0])) < 0.1 * float(cfg1.g["final_K"][0, 0])
