@@ -384,9 +384,17 @@ def run_ours(args):
     k3_ms = k_point + k_pair + k_cam
     abytes = algorithmic_bytes(p["nc"], p["np"], p["nobs"])
     achieved = abytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
-    traffic = None
+    # DRAM bytes of the K3 kernels from the committed ncu --set full capture -- only if it was taken on THESE sources
+    # (profiles/traffic.json carries a hash of csrc/, tools/update_traffic.py); a stale figure is reported as null
+    traffic, traffic_note = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import update_traffic
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("source_id") == update_traffic.source_id():
+            traffic = tj.get(args.workload)
+        else:
+            traffic_note = "profiles/traffic.json was captured on other sources (source_id mismatch): not reported"
     except Exception:
         pass
     kernels = {"ba_point_kernel": k_point, "ba_pair_kernel": k_pair, "ba_camera_kernel+ba_combine_kernel": k_cam}
@@ -427,6 +435,7 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": "K3 = ba_point_kernel + ba_pair_kernel + ba_camera_kernel + ba_combine_kernel (one residual+Jacobian+Schur pass)",
                              "kernel_ms": k3_ms, "kernels_ms": kernels, "dominant": dominant, "algorithmic_bytes": int(abytes), "peak_source": peak_src,
+                             "traffic_note": traffic_note,
                              "note": "not HBM-bound: fp64 arithmetic and L1/L2 request rate of the per-camera-pair accumulation dominate (DESIGN.md section 4)"},
                 "clocks": clocks}
         if weak is not None:

@@ -27,7 +27,9 @@ namespace {
 
 constexpr int TC_M = 128;            // query rows per CTA  (UMMA M, TMEM lanes)
 constexpr int TC_N = 256;            // train rows per tile (UMMA N, TMEM columns per accumulator stage) = rows per expanded block
-constexpr int TC_EPI_WARPS = 8;      // two per TMEM lane quarter: warps 0-3 take columns [0,128), warps 4-7 [128,256)
+constexpr int TC_EPI_PARTS = 4;      // column parts of a 256-column accumulator tile, one epilogue warp per (TMEM lane quarter, part)
+constexpr int TC_EPI_WARPS = 4 * TC_EPI_PARTS;      // 16 warps: the epilogue is latency-bound (tcgen05.ld, votes), more warps hide it
+constexpr int TC_PART_COLS = TC_N / TC_EPI_PARTS;   // 64 columns = 2 chunks of 32 per warp and tile
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;      // + warp 8: loader, warp 9: MMA issuer
 constexpr int TC_NORM_SLOTS = 6;     // L2: ring of train-norm tiles (1 KB each); a slot is reused 6 tiles later, when its epilogue is long done
 
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
         }
     } else {
         // ---- epilogue warps.  Lane quarter q = warp & 3 (hardware rule: a warp reads TMEM lanes 32*(warp%4)..+31), column
-        // half h = warp >> 2.  Per 32-column chunk: one tcgen05.ld, then per 8-column group a 3-input-max tree and a
+        // part h = warp >> 2.  Per 32-column chunk: one tcgen05.ld, then per 8-column group a 3-input-max tree and a
         // WARP-UNIFORM branch: only groups in which SOME lane has a candidate better than its current second best run the
         // insert sequence (expected: a third of the groups over a 5000-row image).
         const int q = warp & 3, h = warp >> 2;
@@ -269,11 +271,11 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
             if (!mbar_wait(acc_full + a, ua & 1)) { ok = false; break; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int t_row0 = (tile0 + t) * TC_N, t_rows = min(TC_N, pd.nt - t_row0);
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * TC_N + (uint32_t)h * (TC_N / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * TC_N + (uint32_t)h * TC_PART_COLS;
             const int32_t* nrm = sNorm + (t % TC_NORM_SLOTS) * TC_N;
             // one 32-column chunk of this warp's column half
             auto chunk = [&](const uint32_t (&v)[32], int cc) {
-                const int c0 = h * (TC_N / 2) + cc;
+                const int c0 = h * TC_PART_COLS + cc;
                 const bool part = c0 + 32 > t_rows;                       // zero-padded rows must not become candidates
                 if (!L2) {
                     const int cb = 0xFFFF - (t * TC_N + c0);              // low half of the key of column 0 of this chunk
@@ -302,30 +304,32 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
                 }
             };
             // software pipeline over the 4 chunks: the tcgen05.ld of the next chunk is in flight while this one is ranked
-            const int nch = min(4, (t_rows - h * (TC_N / 2) + 31) / 32);  // chunks of this column half that hold real rows (warp-uniform)
+            const int nch = min(TC_PART_COLS / 32, (t_rows - h * TC_PART_COLS + 31) / 32);  // chunks of this column part that hold real rows (warp-uniform)
             uint32_t va[32], vb[32];
+            static_assert(TC_PART_COLS == 64, "the pipeline below is written for two chunks per warp and tile");
             if (nch > 0) { tc_ld32(taddr, va); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
             if (nch > 1) tc_ld32(taddr + 32, vb);
             if (nch > 0) chunk(va, 0);
-            if (nch > 1) { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); if (nch > 2) tc_ld32(taddr + 64, va); chunk(vb, 32); }
-            if (nch > 2) { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); if (nch > 3) tc_ld32(taddr + 96, vb); chunk(va, 64); }
-            if (nch > 3) { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); chunk(vb, 96); }
+            if (nch > 1) { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); chunk(vb, 32); }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + a);
         }
-        if (h == 1) half_best[q * 32 + lane] = L2 ? make_int4(best.d0, best.i0, best.d1, best.i1) : make_int4(k0, k1, 0, 0);
+        if (h > 0) half_best[(h - 1) * TC_M + q * 32 + lane] = L2 ? make_int4(best.d0, best.i0, best.d1, best.i1) : make_int4(k0, k1, 0, 0);
     }
     if (!ok) atomicExch(error_flag, 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp < 4) {
-        const int4 o = half_best[warp * 32 + lane];
         const int row = q_row0 + warp * 32 + lane;
         if (!L2) {
-            // merge the two column halves with the same network, then unpack
-            int hi = max(k0, o.x), lo = min(k0, o.x); k1 = max(k1, lo); k0 = hi;
-            hi = max(k0, o.y); lo = min(k0, o.y); k1 = max(k1, lo); k0 = hi;
+            // merge the column parts with the same network, then unpack
+#pragma unroll
+            for (int part = 1; part < TC_EPI_PARTS; ++part) {
+                const int4 o = half_best[(part - 1) * TC_M + warp * 32 + lane];
+                int hi = max(k0, o.x), lo = min(k0, o.x); k1 = max(k1, lo); k0 = hi;
+                hi = max(k0, o.y); lo = min(k0, o.y); k1 = max(k1, lo); k0 = hi;
+            }
             auto unpack = [&](int key, int& d, int& i) {
                 if (key == KEY_EMPTY) { d = INT_MAX; i = -1; return; }
                 d = (256 - (key >> 16)) >> 1; i = tile0 * TC_N + (0xFFFF - (key & 0xFFFF));
@@ -340,7 +344,11 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
                 if (best.i0 < 0 || lex_lt(d, i, best.d0, best.i0)) { best.d1 = best.d0; best.i1 = best.i0; best.d0 = d; best.i0 = i; }
                 else if (best.i1 < 0 || lex_lt(d, i, best.d1, best.i1)) { best.d1 = d; best.i1 = i; }
             };
-            ins(o.x, o.y); ins(o.z, o.w);
+#pragma unroll
+            for (int part = 1; part < TC_EPI_PARTS; ++part) {
+                const int4 o = half_best[(part - 1) * TC_M + warp * 32 + lane];
+                ins(o.x, o.y); ins(o.z, o.w);
+            }
             if (row < pd.nq) {
                 const int na = norms[(size_t)(pd.q_blk + q_row0 / TC_N) * TC_N + (q_row0 % TC_N) + warp * 32 + lane];
                 partial[(size_t)(pd.out_row + row) * splits + sp] =
