@@ -547,8 +547,12 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_camera_kernel(BAView v, int pe
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void ba_assemble_kernel(const double* __restrict__ Sblk, const double* __restrict__ Scf, const double* __restrict__ Sff,
                                    const double* __restrict__ rhs, const double* __restrict__ dcf, int nc, int npad,
-                                   double inv_radius, double min_diag, double max_diag, double* __restrict__ A, const LMState* __restrict__ st) {
+                                   double inv_radius, double min_diag, double max_diag, double* __restrict__ A, const LMState* __restrict__ st,
+                                   unsigned* __restrict__ solve_counter) {
     if (st) { if (st->status != LM_RUNNING) return; inv_radius = 1.0 / st->radius; }
+    // number of the dense solve that follows (the dataflow Cholesky's flags carry it): kept on the device so that a replayed
+    // CUDA graph, whose kernel arguments are frozen, still sees a new number every time
+    if (solve_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *solve_counter += 1u;
     const int n = 6 * nc + 1;
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c >= npad || c > r) return;
@@ -996,7 +1000,9 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(PeerTable t, size_t of
 
 // =================================================================================================================
 // events of one LM iteration: 0 point start, 1 point end, 2 pair end, 3 camera end, 4 solve start, 5 solve end, 6/7 flush
-constexpr int LM_CHUNK = 4;            // LM iterations enqueued per host read-back
+constexpr int LM_CHUNK = 4;            // LM iterations enqueued per host read-back (large problems)
+constexpr int LM_CHUNK_MAX = 16;       // small problems (adjustBundle inside runSfM: a few thousand observations, ~100 iterations): their
+                                       // iteration is a chain of launch-bound kernels, the read-back + sync per chunk is a visible share
 struct EvSet { cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
 
 struct sfmb200_ba_problem {
@@ -1021,11 +1027,12 @@ struct sfmb200_ba_problem {
     bool backsolve_staged = false;
     unsigned* chol_progress = nullptr; int chol_grid_stream = 0; bool chol_stream = true;
     unsigned* chol_ready = nullptr; unsigned chol_epoch = 0; int chol_grid = 0; bool chol_fused = true, chol_lookahead = false;   // dataflow Cholesky (K4)
+    unsigned* solve_counter = nullptr;   // device-side number of the current dense solve (incremented by ba_assemble_kernel)
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
     bool have_scale = false;
     bool backsub_from_z = false;      // back-substitution + model cost from the stored Z blocks (gather mode) instead of re-evaluated Jacobians
     bool camd_valid[2] = {false, false};   // camd[i] matches cf[i] (written by cam_derive or, for the candidate, by ba_cam_update_kernel)
-    EvSet evs[LM_CHUNK];              // profile mode: one set of events per iteration of a chunk (created on first use)
+    EvSet evs[LM_CHUNK_MAX];              // profile mode: one set of events per iteration of a chunk (created on first use)
     bool have_events = false;
     LMState* d_state = nullptr; LMState* h_state = nullptr;    // device-resident LM control state + pinned read-back
     // row mode (default): Z per observation (point-major), stable camera-major list with follower counts, partial records
@@ -1251,16 +1258,16 @@ static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, dou
     const LMState* st = lm ? P->d_state : nullptr;
     const int* skip = lm ? &P->d_state->status : nullptr;
     ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(summed(P, P->Sblk), summed(P, P->Scf), summed(P, P->Sff), summed(P, P->rhs), summed(P, P->dcf), P->nc, npad, 1.0 / radius,
-                                                                                 opt->min_lm_diagonal, opt->max_lm_diagonal, P->A, st);
+                                                                                 opt->min_lm_diagonal, opt->max_lm_diagonal, P->A, st, P->solve_counter);
     SFM_LAUNCH_CHECK(ctx);
     if (P->chol_fused) {
         const bool la = P->chol_lookahead || P->chol_stream;
         const int ntasks = chol_fused_tasks(nbk, la);
         const int grid = std::min(ntasks, P->chol_grid);
         if (P->chol_stream) chol_stream_kernel<<<std::min(ntasks, P->chol_grid_stream), CS_THREADS, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, P->chol_progress,
-                                                                                                                   ++P->chol_epoch, P->Linv, nullptr, skip);
-        else if (la) chol_fused_kernel<true><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, ++P->chol_epoch, P->Linv, nullptr, skip);
-        else chol_fused_kernel<false><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, ++P->chol_epoch, P->Linv, nullptr, skip);
+                                                                                                                   0u, P->Linv, nullptr, skip, P->solve_counter);
+        else if (la) chol_fused_kernel<true><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, 0u, P->Linv, nullptr, skip, P->solve_counter);
+        else chol_fused_kernel<false><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, 0u, P->Linv, nullptr, skip, P->solve_counter);
         SFM_LAUNCH_CHECK(ctx);
     } else {
         for (int k = 0; k < nbk; ++k) {
@@ -1398,6 +1405,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     int32_t* obs_pt = cv.take<int32_t>(nobs); int* cnt = cv.take<int>(2 * (size_t)(nc + 1)); int* cursor = cnt + nc + 1;
     P->obs_pt = obs_pt; P->cm_obs = cv.take<int32_t>(nobs); P->cm_np = cv.take<uint8_t>(nobs);
     P->part4 = cv.take<double>(4 * (size_t)ctx->sm_count * 32); P->fpart = cv.take<double>(2 * (size_t)(nc + 1)); P->counters = cv.take<unsigned>(16);
+    P->solve_counter = P->counters + 8;
     P->chol_ready = cv.take<unsigned>((size_t)(P->npad / NB) * (P->npad / NB));
     P->Linv = cv.take<double>((size_t)P->npad * NB);
     P->chol_progress = cv.take<unsigned>((size_t)(P->npad / NB));
@@ -1486,6 +1494,9 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         // splits are fixed before the lists exist (they size the partial buffer): assume every pair is non-empty
         P->pair_nseg = nseg;
         P->pair_splits = std::max(1, std::min(64, ceil_div(16 * ctx->sm_count, (int)std::max<size_t>(1, nblk - nc))));
+        // ...but a list is not worth splitting below ~64 entries per warp (tiny problems: 64 splits of a 100-entry list made the
+        // combine kernel the longest of the iteration)
+        P->pair_splits = (int)std::max<long long>(1, std::min<long long>(P->pair_splits, E / (64 * (long long)std::max<size_t>(1, (nblk - nc) * (size_t)nseg))));
         const size_t part_bytes = Carver::pad(8 * (size_t)(P->diag_grid + nc) * ROW_HDR) + Carver::pad(8 * 36 * nkeys * P->pair_splits);
         const size_t gb = Carver::pad(8 * 18 * (size_t)nobs) + part_bytes + hist_bytes + Carver::pad(4 * (nkeys + 1)) + Carver::pad(4 * (nblk + 1)) +
                           Carver::pad(8 * (size_t)std::max<long long>(E, 1)) + Carver::pad(4 * nkeys) * 2 + 8192;
@@ -1551,7 +1562,7 @@ void sfmb200_ba_problem_destroy(sfmb200_ba_problem* P) {
     std::lock_guard<std::mutex> lk(P->ctx->mu);
     cudaSetDevice(P->ctx->device);
     cudaStreamSynchronize(P->ctx->stream);
-    for (int k = 0; k < LM_CHUNK; ++k) for (int e = 0; e < 8; ++e) if (P->evs[k].ev[e]) cudaEventDestroy(P->evs[k].ev[e]);
+    for (int k = 0; k < LM_CHUNK_MAX; ++k) for (int e = 0; e < 8; ++e) if (P->evs[k].ev[e]) cudaEventDestroy(P->evs[k].ev[e]);
     // peer mappings stay open in the context's cache (ctx->ipc_cache) for the next problem; closed with the context
     ba_release_buffers(P);
     delete P;
@@ -1666,7 +1677,7 @@ int sfmb200_ba_problem_reduced_system(sfmb200_ba_problem* P, const sfmb200_ba_op
     rc = schur_pass(P, &opt, radius, nullptr, false); if (rc) return rc;
     const int n = P->n, npad = P->npad;
     ba_assemble_kernel<<<dim3(ceil_div(npad, 128), npad), 128, 0, ctx->stream>>>(summed(P, P->Sblk), summed(P, P->Scf), summed(P, P->Sff), summed(P, P->rhs), summed(P, P->dcf), P->nc, npad, 1.0 / radius,
-                                                                                 opt.min_lm_diagonal, opt.max_lm_diagonal, P->A, nullptr);
+                                                                                 opt.min_lm_diagonal, opt.max_lm_diagonal, P->A, nullptr, nullptr);
     SFM_LAUNCH_CHECK(ctx);
     std::vector<double> hA((size_t)npad * npad), hg(n), hs(n), hsum(8);
     SFM_CUDA(ctx, cudaMemcpyAsync(hA.data(), P->A, 8 * hA.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1699,7 +1710,7 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
     const int64_t launches0 = ctx->launches;
     int rc = compute_scaling(P, &opt); if (rc) return rc;
     if (opt.profile && !P->have_events) {
-        for (int k = 0; k < LM_CHUNK; ++k) for (int e = 0; e < 8; ++e) SFM_CUDA(ctx, cudaEventCreate(&P->evs[k].ev[e]));
+        for (int k = 0; k < LM_CHUNK_MAX; ++k) for (int e = 0; e < 8; ++e) SFM_CUDA(ctx, cudaEventCreate(&P->evs[k].ev[e]));
         P->have_events = true;
     }
     if (!P->camd_valid[P->cur]) {       // inside the loop the table of an accepted candidate comes from ba_cam_update_kernel
@@ -1712,8 +1723,9 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
     hs->status = LM_RUNNING; hs->termination_type = SFMB200_BA_NO_CONVERGENCE;
     SFM_CUDA(ctx, cudaMemcpyAsync(P->d_state, hs, sizeof *hs, cudaMemcpyHostToDevice, ctx->stream));
     SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                 // hs is reused for the read-back
-    int chunk = opt.verbose ? 1 : LM_CHUNK;
-    if (const char* ce = getenv("SFMB200_BA_CHUNK")) chunk = std::max(1, std::min(LM_CHUNK, atoi(ce)));
+    const int chunk_default = P->nobs < 100000 ? LM_CHUNK_MAX : LM_CHUNK;
+    int chunk = opt.verbose ? 1 : chunk_default;
+    if (const char* ce = getenv("SFMB200_BA_CHUNK")) chunk = std::max(1, std::min(LM_CHUNK_MAX, atoi(ce)));
     bool timed_out = false;
     int executed = 0;
     // Multi-GPU: every rank must enqueue the SAME sequence of exchanges, so nothing rank-local may decide when the loop stops.
@@ -1721,35 +1733,71 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
     // "my clock says stop" is max-reduced over the ranks at the end of every chunk and all ranks act on the result.  The chunk
     // size must be the same everywhere too: options (verbose) must match across ranks, the environment override is ignored.
     const bool collective_clock = ctx->nranks > 1 && opt.max_solver_time_in_seconds > 0;
-    if (ctx->nranks > 1) chunk = opt.verbose ? 1 : LM_CHUNK;
+    if (ctx->nranks > 1) chunk = opt.verbose ? 1 : LM_CHUNK;       // (per-rank shard sizes differ: no size-dependent choice here)
     double* tflag = P->post + 8;      // one of the pad doubles behind post[8] in the exchange buffer
+
+    // one LM iteration on the device: pass at x, dense solve, candidate, evaluation, decision
+    auto enqueue_iteration = [&](const EvSet* es) -> int {
+        if (opt.l2_flush_mb > 0) {      // benchmark hygiene: evict the working set from L2 between iterations
+            SFM_CUDA(ctx, ctx->scratch2.reserve((size_t)opt.l2_flush_mb << 20));
+            if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[6], ctx->stream));
+            SFM_CUDA(ctx, cudaMemsetAsync(ctx->scratch2.p, 0, (size_t)opt.l2_flush_mb << 20, ctx->stream));
+            if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[7], ctx->stream));
+        }
+        int r = schur_pass(P, &opt, 0.0, es, true); if (r) return r;
+        if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[4], ctx->stream));
+        r = dense_solve(P, &opt, 0.0, true); if (r) return r;
+        if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[5], ctx->stream));
+        BAView v = make_view(P, &opt, true);
+        {
+            BAView vc = v; vc.dcf = summed(P, P->dcf);              // the rank-summed J^T J diagonal and gradient
+            ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(vc, 0.0, P->backsub_from_z ? 1 : 0, nullptr, P->y_cf, P->scale_cf, summed(P, P->gcf), P->nc, nullptr, nullptr, P->locals,
+                                                             P->post, P->gmax_pt_bits, P->fail);
+        }
+        SFM_LAUNCH_CHECK(ctx);
+        if (P->np > 0 && P->nobs > 0) { r = DISPATCH_G(P, launch_backsub)(P, v); if (r) return r; }
+        r = ba_allreduce(P, P->post, 7, 1); if (r) return r;   // sums: candidate cost, model, norms, failure counts; max: |g| of the points
+        ba_lm_control_kernel<<<1, 32, 0, ctx->stream>>>(P->d_state, summed(P, P->sums), summed(P, P->post), P->locals, opt); SFM_LAUNCH_CHECK(ctx);
+        return SFMB200_OK;
+    };
+    // Small problems (adjustBundle inside runSfM: hundreds to a few thousand observations, up to ~100 iterations) are bound by the
+    // host's launch rate -- ~14 launches of microsecond kernels per iteration.  After a first ordinary chunk the remaining
+    // iterations are replayed from a CUDA graph of GRAPH_ITERS iterations (one launch per replay; every kernel takes x, the
+    // radius, the early-out and the dense-solve number from device memory, so frozen arguments are fine).  Single GPU, no
+    // profiling / flushing / verbose output; SFMB200_BA_GRAPH=0 disables it.
+    constexpr int GRAPH_ITERS = 8, GRAPH_AFTER = 4;      // the first ordinary chunk also warms every code path; solves that end inside it never build a graph
+    const char* genv = getenv("SFMB200_BA_GRAPH");
+    const bool graph_ok = ctx->nranks == 1 && !opt.profile && opt.l2_flush_mb <= 0 && !opt.verbose && P->gather && P->nobs < 100000 &&
+                          !(genv && genv[0] == '0');
+    if (graph_ok) chunk = std::min(chunk, LM_CHUNK);
+    cudaGraphExec_t gexec = nullptr;
+    int64_t graph_launches = 0;
+    struct GraphGuard { cudaGraphExec_t* g; ~GraphGuard() { if (*g) cudaGraphExecDestroy(*g); } } graph_guard{&gexec};
 
     for (;;) {
         if (!collective_clock && executed > 0 && opt.max_solver_time_in_seconds > 0 && elapsed() >= opt.max_solver_time_in_seconds) { timed_out = true; break; }
-        const int n_it = std::max(1, std::min(chunk, opt.max_num_iterations - hs->iter));
-        for (int k = 0; k < n_it; ++k) {
-            const EvSet* es = opt.profile ? &P->evs[k] : nullptr;
-            if (opt.l2_flush_mb > 0) {      // benchmark hygiene: evict the working set from L2 between iterations
-                SFM_CUDA(ctx, ctx->scratch2.reserve((size_t)opt.l2_flush_mb << 20));
-                if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[6], ctx->stream));
-                SFM_CUDA(ctx, cudaMemsetAsync(ctx->scratch2.p, 0, (size_t)opt.l2_flush_mb << 20, ctx->stream));
-                if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[7], ctx->stream));
+        int n_it = std::max(1, std::min(chunk, opt.max_num_iterations - hs->iter));
+        if (graph_ok && executed >= GRAPH_AFTER) {
+            if (!gexec) {
+                const int64_t l0 = ctx->launches;
+                cudaGraph_t graph = nullptr;
+                SFM_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                int crc = SFMB200_OK;
+                for (int k = 0; k < GRAPH_ITERS && crc == SFMB200_OK; ++k) crc = enqueue_iteration(nullptr);
+                if (crc == SFMB200_OK && cudaMemcpyAsync(hs, P->d_state, sizeof *hs, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) crc = SFMB200_ERR_CUDA;
+                const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                if (crc != SFMB200_OK || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return crc ? crc : sfmb200_fail(ctx, SFMB200_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce)); }
+                const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+                graph_launches = ctx->launches - l0;                      // counted while capturing: subtract, add per replay
+                ctx->launches = l0;
             }
-            // ---- one LM iteration on the device: pass at x, dense solve, candidate, evaluation, decision ----------
-            rc = schur_pass(P, &opt, 0.0, es, true); if (rc) return rc;
-            if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[4], ctx->stream));
-            rc = dense_solve(P, &opt, 0.0, true); if (rc) return rc;
-            if (es) SFM_CUDA(ctx, cudaEventRecord(es->ev[5], ctx->stream));
-            BAView v = make_view(P, &opt, true);
-            {
-                BAView vc = v; vc.dcf = summed(P, P->dcf);              // the rank-summed J^T J diagonal and gradient
-                ba_cam_update_kernel<<<1, 256, 0, ctx->stream>>>(vc, 0.0, P->backsub_from_z ? 1 : 0, nullptr, P->y_cf, P->scale_cf, summed(P, P->gcf), P->nc, nullptr, nullptr, P->locals,
-                                                                 P->post, P->gmax_pt_bits, P->fail);
-            }
-            SFM_LAUNCH_CHECK(ctx);
-            if (P->np > 0 && P->nobs > 0) { rc = DISPATCH_G(P, launch_backsub)(P, v); if (rc) return rc; }
-            rc = ba_allreduce(P, P->post, 7, 1); if (rc) return rc;   // sums: candidate cost, model, norms, failure counts; max: |g| of the points
-            ba_lm_control_kernel<<<1, 32, 0, ctx->stream>>>(P->d_state, summed(P, P->sums), summed(P, P->post), P->locals, opt); SFM_LAUNCH_CHECK(ctx);
+            n_it = GRAPH_ITERS;
+            SFM_CUDA(ctx, cudaGraphLaunch(gexec, ctx->stream));
+            ctx->launches += graph_launches;
+        } else {
+            for (int k = 0; k < n_it; ++k) { rc = enqueue_iteration(opt.profile ? &P->evs[k] : nullptr); if (rc) return rc; }
         }
         if (collective_clock) {
             P->h_scal[30] = elapsed() >= opt.max_solver_time_in_seconds ? 1.0 : 0.0;
@@ -1757,7 +1805,7 @@ int sfmb200_ba_problem_run(sfmb200_ba_problem* P, const sfmb200_ba_options* opt_
             rc = ba_allreduce(P, tflag, 0, 1); if (rc) return rc;
             SFM_CUDA(ctx, cudaMemcpyAsync(P->h_scal + 31, summed(P, tflag), 8, cudaMemcpyDeviceToHost, ctx->stream));
         }
-        SFM_CUDA(ctx, cudaMemcpyAsync(hs, P->d_state, sizeof *hs, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!gexec) SFM_CUDA(ctx, cudaMemcpyAsync(hs, P->d_state, sizeof *hs, cudaMemcpyDeviceToHost, ctx->stream));   // (part of the graph otherwise)
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         // iterations of this chunk that actually ran: all of them unless the solve terminated inside the chunk
         const int ran = hs->status == LM_RUNNING ? n_it : std::max(1, std::min(n_it, hs->passes - executed));

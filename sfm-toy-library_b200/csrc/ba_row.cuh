@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 8) ba_pair_kernel(const doubl
     const int seg = nseg - 1 - (int)(blockIdx.y / splits), sp = blockIdx.y % splits;
     const int blk = pair_blk[q];
     const int start = pair_off[(size_t)blk * nseg + seg], len = pair_off[(size_t)blk * nseg + seg + 1] - start;
-    const int b0 = start + (int)((long long)len * sp / splits), b1 = start + (int)((long long)len * (sp + 1) / splits);
+    // split sp of the list: [start + floor(len*sp/splits), start + floor(len*(sp+1)/splits)), in 32-bit arithmetic
+    const int lq = len / splits, lr = len - lq * splits;
+    const int b0 = start + lq * sp + lr * sp / splits, b1 = start + lq * (sp + 1) + lr * (sp + 1) / splits;
     if (b1 <= b0) return;
     const int fr = lane >> 2, fc = lane & 3;
     const bool valid = fr < 6 && fc < 3;
@@ -229,10 +231,10 @@ __global__ void __launch_bounds__(COMBINE_THREADS) ba_combine_kernel(BAView v, R
         for (int seg = 0; seg < ra.nseg; ++seg) {
             const int start = ra.pair_off[blk * ra.nseg + seg], len = ra.pair_off[blk * ra.nseg + seg + 1] - start;
             if (len <= 0) continue;
-            for (int sp = 0; sp < ra.splits; ++sp) {
-                const int b0 = start + (int)((long long)len * sp / ra.splits), b1 = start + (int)((long long)len * (sp + 1) / ra.splits);
-                if (b1 <= b0) continue;
-                const double* pb = ra.pair_part + ((blk * ra.nseg + seg) * ra.splits + sp) * 36;
+            const int lq = len / ra.splits, lr = len - lq * ra.splits;
+            const double* pb = ra.pair_part + (blk * ra.nseg + seg) * ra.splits * 36;
+            for (int sp = 0; sp < ra.splits; ++sp, pb += 36) {
+                if (lq == 0 && lr * sp / ra.splits == lr * (sp + 1) / ra.splits) continue;     // this split's range is empty: nothing was written
                 s0 += pb[lane];
                 if (lane < 4) s1 += pb[32 + lane];
             }

@@ -324,8 +324,9 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) chol_fused_kernel(double* __
                                                                       double* __restrict__ dinv, int* __restrict__ fail,
                                                                       unsigned* __restrict__ ready, unsigned epoch,
                                                                       double* __restrict__ Linv, unsigned long long* __restrict__ trace,
-                                                                      const int* __restrict__ skip = nullptr) {
+                                                                      const int* __restrict__ skip = nullptr, const unsigned* __restrict__ epoch_dev = nullptr) {
     if (skip && *skip) return;
+    if (epoch_dev) epoch = *epoch_dev;       // CUDA-graph replays: the solve number lives on the device (kernel arguments are frozen)
     __shared__ double Ps[NB][NB + 1], Qs[NB][NB + 1];
     __shared__ double colbuf[2][NB];
     __shared__ double invd[NB];
@@ -486,8 +487,9 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
                                                                  double* __restrict__ dinv, int* __restrict__ fail,
                                                                  unsigned* __restrict__ ready, unsigned* __restrict__ progress, unsigned epoch,
                                                                  double* __restrict__ Linv, unsigned long long* __restrict__ trace,
-                                                                 const int* __restrict__ skip = nullptr) {
+                                                                 const int* __restrict__ skip = nullptr, const unsigned* __restrict__ epoch_dev = nullptr) {
     if (skip && *skip) return;
+    if (epoch_dev) epoch = *epoch_dev;       // CUDA-graph replays: the solve number lives on the device (kernel arguments are frozen)
     __shared__ __align__(16) double Pt[NB][TS], Qt[NB][TS], Xs[NB][TS];
     __shared__ double Ls[NB][NB + 1];
     __shared__ __align__(16) double colbuf[2][2][NB];
