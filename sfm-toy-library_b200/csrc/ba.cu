@@ -1461,7 +1461,11 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     {   // mode: "row" (default: ba_row_kernel, deterministic) needs the block row of a camera (288 bytes per camera) in shared
         // memory and the stable sort's per-warp counters; "red" (SFMB200_BA_SCHUR=red, or too many cameras) uses atomics
         const char* mode = getenv("SFMB200_BA_SCHUR");
-        P->gather = !(mode && strcmp(mode, "red") == 0) && (size_t)(2 * PFILL_WARPS + 1) * nc * 4 <= 160 * 1024 && pair_entries < (1LL << 31) - 1024;
+        // partial blocks of the pair kernel: one 288-byte block per (camera pair, point segment[, split]); with thousands of cameras
+        // that buffer (and the per-key offset tables) outgrow their use -- such problems take the atomics path
+        const size_t nseg_est = (size_t)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (24LL << 20) - 1) / (24LL << 20)));
+        const bool partials_fit = nblk * nseg_est * 288 <= ((size_t)768 << 20);
+        P->gather = !(mode && strcmp(mode, "red") == 0) && (size_t)(2 * PFILL_WARPS + 1) * nc * 4 <= 160 * 1024 && pair_entries < (1LL << 31) - 1024 && partials_fit;
     }
     if (nobs) {
         expand_obs_pt_kernel<<<ceil_div(np, 256), 256, 0, st>>>(P->pt_off, np, obs_pt);

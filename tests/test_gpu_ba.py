@@ -312,3 +312,14 @@ def test_two_runs_are_bitwise_identical(ctx):
     for o in outs[1:]:
         assert o[0] == outs[0][0] and o[1] == outs[0][1]
         assert np.array_equal(o[2], outs[0][2]) and np.array_equal(o[3], outs[0][3]) and o[4] == outs[0][4]
+
+
+def test_many_cameras_take_the_atomics_path_and_agree(ctx, oracle):
+    """1200 cameras: the per-(camera pair) partial blocks of the deterministic mode would need > 768 MB, so the solver switches to
+    the atomics ("red") formulation by itself; the reduced system still matches the oracle."""
+    p = synth.make_ba_problem(n_cams=1200, n_pts=3000, obs_per_pt=4, seed=31)
+    prob = ctx.ba_problem(*_args(p))
+    g = prob.reduced_system(1e4); o = oracle.ba_reduced_system(*_args(p), radius=1e4)
+    np.testing.assert_allclose(g["S"], o["S"], rtol=0, atol=2e-11 * np.abs(o["S"]).max())
+    np.testing.assert_allclose(g["rhs"], o["rhs"], rtol=0, atol=1e-10 * np.abs(o["rhs"]).max())
+    prob.close()
