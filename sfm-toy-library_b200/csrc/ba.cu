@@ -1464,7 +1464,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         // partial blocks of the pair kernel: one 288-byte block per (camera pair, point segment[, split]); with thousands of cameras
         // that buffer (and the per-key offset tables) outgrow their use -- such problems take the atomics path
         const size_t nseg_est = (size_t)std::max<long long>(1, std::min<long long>(64, (144LL * nobs + (24LL << 20) - 1) / (24LL << 20)));
-        const bool partials_fit = nblk * nseg_est * 288 <= ((size_t)768 << 20);
+        const bool partials_fit = nblk * nseg_est * 288 <= ((size_t)256 << 20);
         P->gather = !(mode && strcmp(mode, "red") == 0) && (size_t)(2 * PFILL_WARPS + 1) * nc * 4 <= 160 * 1024 && pair_entries < (1LL << 31) - 1024 && partials_fit;
     }
     if (nobs) {

@@ -315,9 +315,9 @@ def test_two_runs_are_bitwise_identical(ctx):
 
 
 def test_many_cameras_take_the_atomics_path_and_agree(ctx, oracle):
-    """1200 cameras: the per-(camera pair) partial blocks of the deterministic mode would need > 768 MB, so the solver switches to
+    """1400 cameras: the per-(camera pair) partial blocks of the deterministic mode would need > 256 MB, so the solver switches to
     the atomics ("red") formulation by itself; the reduced system still matches the oracle."""
-    p = synth.make_ba_problem(n_cams=1200, n_pts=3000, obs_per_pt=4, seed=31)
+    p = synth.make_ba_problem(n_cams=1400, n_pts=3000, obs_per_pt=4, seed=31)
     prob = ctx.ba_problem(*_args(p))
     g = prob.reduced_system(1e4); o = oracle.ba_reduced_system(*_args(p), radius=1e4)
     np.testing.assert_allclose(g["S"], o["S"], rtol=0, atol=2e-11 * np.abs(o["S"]).max())
