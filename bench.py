@@ -481,6 +481,56 @@ def run_ours(args):
                 line[key] = st
         except Exception as e:
             line["cfg4_cfg5"] = {"error": repr(e)}
+    # ---- BASELINE configs[1] (cfg 2: 20 cameras / 10 k points / 80 k observations), N = 1: the same step, resident and one-shot
+    if rank == 0 and world == 1 and not args.no_stages and args.workload != "cfg2":
+        try:
+            from sfm_toy_library_b200 import synth
+            p2 = synth.make_ba_problem(seed=0, **synth.BA_CONFIGS["cfg2"])
+            a2 = (p2["cams"], p2["pts"], p2["focal"], p2["obs_xy"], p2["obs_cam"], p2["pt_off"])
+            pr2 = ctx.ba_problem(*a2)
+            run_steps(pr2, capi, 40); pr2.reset()
+            g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+            ctx.synchronize(); g0.record(stream); s2 = run_steps(pr2, capi, 20); g1.record(stream); ctx.synchronize(); torch.cuda.synchronize()
+            ms2 = g0.elapsed_time(g1) / s2["num_iterations"]
+            pr2.close()
+            ctx.ba_solve(*a2, fixed_iteration_options(capi, 20))
+            t1 = time.perf_counter(); ctx.ba_solve(*a2, fixed_iteration_options(capi, 20)); e2 = time.perf_counter() - t1
+            line["cfg2"] = {"workload": "BASELINE.json configs[1]: 20 cams / 10000 points / 80000 observations", "ms_per_step": ms2,
+                            "value": p2["nobs"] / (ms2 * 1e-3), "unit": UNIT, "e2e": {"value": p2["nobs"] * 20 / e2, "unit": UNIT, "seconds_per_20_iteration_solve": e2},
+                            "note": "no L2 flush between iterations (working set 5 MB); launch-latency regime"}
+        except Exception as e:
+            line["cfg2"] = {"error": repr(e)}
+    # ---- all-pairs matching sharded over the ranks (image pairs are independent, no collective): every rank holds all
+    # descriptors and matches its round-robin share of the 1225 pairs of cfg 4 (H); device time, max over ranks
+    if world > 1 and not args.no_stages:
+        try:
+            from sfm_toy_library_b200 import synth
+            descs = synth.make_descriptor_set(50, n=5000)
+            allp = [(i, j) for i in range(50) for j in range(i + 1, 50)]
+            mine = sdist.shard_pairs(allp, rank, world)
+            dsm = ctx.descriptor_set(descs)
+            rows = 5000 * len(mine)
+            dq = torch.empty(rows, dtype=torch.int32, device="cuda"); dt_ = torch.empty(rows, dtype=torch.int32, device="cuda")
+            dd = torch.empty(rows, dtype=torch.float32, device="cuda"); dst = torch.empty(len(mine) + 1, dtype=torch.int32, device="cuda")
+            dtot = torch.empty(1, dtype=torch.int64, device="cuda")
+            for _ in range(2):
+                dsm.match_pairs_device(mine, dq.data_ptr(), dt_.data_ptr(), dd.data_ptr(), dst.data_ptr(), dtot.data_ptr())
+            barrier()
+            m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
+            m0.record(stream)
+            for _ in range(3):
+                dsm.match_pairs_device(mine, dq.data_ptr(), dt_.data_ptr(), dd.data_ptr(), dst.data_ptr(), dtot.data_ptr())
+            m1.record(stream)
+            barrier()
+            tm = torch.tensor([m0.elapsed_time(m1) / 3.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dsm.close()
+            if rank == 0:
+                line["cfg4_hamming_sharded"] = {"pairs": len(allp), "ranks": world, "ms_per_step": tm.item(), "value": len(allp) / (tm.item() * 1e-3), "unit": "pairs/s",
+                                                "note": "pairs dealt round-robin to the ranks, descriptors replicated, no collective; max over ranks of the device time"}
+        except Exception as e:
+            if rank == 0:
+                line["cfg4_hamming_sharded"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
