@@ -1025,7 +1025,7 @@ struct sfmb200_ba_problem {
     int grid_point = 0, grid_backsub = 0, grid_camera = 0; bool one_wave = true;   // persistent grids = co-resident CTA count
     double* Linv = nullptr;           // [npad/NB][NB][NB] inverses of the diagonal tiles (dataflow Cholesky -> back substitution)
     bool backsolve_staged = false;
-    unsigned* chol_progress = nullptr; int chol_grid_stream = 0; bool chol_stream = true;
+    uint4* chol_ll = nullptr; int chol_grid_stream = 0; bool chol_stream = true;
     unsigned* chol_ready = nullptr; unsigned chol_epoch = 0; int chol_grid = 0; bool chol_fused = true, chol_lookahead = false;   // dataflow Cholesky (K4)
     unsigned* solve_counter = nullptr;   // device-side number of the current dense solve (incremented by ba_assemble_kernel)
     double* h_scal = nullptr;         // pinned read-back: sums[8] post[8] locals[8] gmax fail
@@ -1264,7 +1264,7 @@ static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, dou
         const bool la = P->chol_lookahead || P->chol_stream;
         const int ntasks = chol_fused_tasks(nbk, la);
         const int grid = std::min(ntasks, P->chol_grid);
-        if (P->chol_stream) chol_stream_kernel<<<std::min(ntasks, P->chol_grid_stream), CS_THREADS, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, P->chol_progress,
+        if (P->chol_stream) chol_stream_kernel<<<std::min(ntasks, P->chol_grid_stream), CS_THREADS, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, P->chol_ll,
                                                                                                                    0u, P->Linv, nullptr, skip, P->solve_counter);
         else if (la) chol_fused_kernel<true><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, 0u, P->Linv, nullptr, skip, P->solve_counter);
         else chol_fused_kernel<false><<<grid, PANEL_WARPS * 32, 0, ctx->stream>>>(P->A, npad, P->n, nbk, ntasks, P->dinv, P->fail + 1, P->chol_ready, 0u, P->Linv, nullptr, skip, P->solve_counter);
@@ -1371,7 +1371,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     add(sizeof(CamDerived) * (size_t)nc); add(sizeof(CamDerived) * (size_t)nc);
     add(8 * n); add(24 * (size_t)np); add(8 * PTB * (size_t)np); add(8 * (P->red_n + 32));
     add(8 * (size_t)P->npad * P->npad); add(8 * n); add(8 * (size_t)P->npad); add(4 * (size_t)nobs); add(8 * (size_t)(nc + 1));
-    add(4 * (size_t)(P->npad / NB) * (P->npad / NB)); add(8 * (size_t)P->npad * NB); add(4 * (size_t)(P->npad / NB)); add(sizeof(LMState));
+    add(4 * (size_t)(P->npad / NB) * (P->npad / NB)); add(8 * (size_t)P->npad * NB); add(chol_ll_bytes(P->npad / NB)); add(sizeof(LMState));
     add(4 * (size_t)nobs); add((size_t)nobs); add(8 * 4 * (size_t)ctx->sm_count * 32); add(16 * (size_t)(nc + 1)); add(64);   // cm_obs, cm_np, part4, fpart, counters
     if (!ctx->ba_ws.in_use) {           // borrow the cached workspace (grown below when too small)
         P->mem = ctx->ba_ws.mem; P->gmem = ctx->ba_ws.gmem; P->xbuf = ctx->ba_ws.xbuf; P->hpin = ctx->ba_ws.hpin;
@@ -1408,7 +1408,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     P->solve_counter = P->counters + 8;
     P->chol_ready = cv.take<unsigned>((size_t)(P->npad / NB) * (P->npad / NB));
     P->Linv = cv.take<double>((size_t)P->npad * NB);
-    P->chol_progress = cv.take<unsigned>((size_t)(P->npad / NB));
+    P->chol_ll = cv.take<uint4>(chol_ll_bytes(P->npad / NB) / sizeof(uint4));
     P->d_state = cv.take<LMState>(1);
 
     cudaStream_t st = ctx->stream;
@@ -1435,7 +1435,7 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
     {   // dataflow Cholesky: ready flags start at epoch 0; the grid must stay within the co-resident CTA count
         const int nbk = P->npad / NB;
         CRT(cudaMemsetAsync(P->chol_ready, 0, 4 * (size_t)nbk * nbk, st));
-        CRT(cudaMemsetAsync(P->chol_progress, 0, 4 * (size_t)nbk, st));
+        CRT(cudaMemsetAsync(P->chol_ll, 0, chol_ll_bytes(nbk), st));
         int per_sm = 0;
         CRT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_fused_kernel<false>, PANEL_WARPS * 32, 0));
         P->chol_grid = std::max(1, per_sm * ctx->sm_count);

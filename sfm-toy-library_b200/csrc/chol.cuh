@@ -77,63 +77,132 @@ __device__ __forceinline__ bool chol_tile_factor(double (&col)[NB / PANEL_WARPS]
     return *bad_flag != 0;
 }
 
-// Pair-pivot variant of phase 1 (used by the streaming dataflow kernel).  The chain of phase 1 is one barrier + shared-memory
-// round trip per pivot (owner warps alternate), ~350 cycles per pivot.  Here warp w owns the column PAIRS 8q+2w, 8q+2w+1
-// (col[q][h]), so two consecutive pivots are produced inside one warp from three shuffles issued together -- d0, a(j1,j0),
-// d1 -- and one barrier serves two pivots; the validity tests are selects and the reciprocal square root is the
-// MUFU seed + one cubic refinement without the library's range branches (a non-finite result marks the pivot bad).
-// Finished columns go to Ls at once; groups_done counts published 4-column groups.
+// Quad-pivot variant of phase 1 (the one the streaming dataflow kernel runs).  History of the chain, per 32-column tile:
+// one barrier per pivot 6.2 us -> pair pivots 4.1 us -> this.  A cycle-stamped trace (tools/chol_microbench.cu built with
+// -DCHOL_FINE_TRACE) showed that the cost of a round is the NUMBER of instructions the owning warp executes between two
+// barriers (a single warp of mostly dependent fp64 code runs at ~5 cycles per instruction), not the depth of the pivot
+// recurrence, so the round is built to be short:
+//   * warp w owns the column QUADS 16q+4w .. 16q+4w+3 (col[q][h], lane = row): one barrier and one shared-memory round trip
+//     serve FOUR pivots;
+//   * the owner fetches the 10 entries of the quad's 4x4 diagonal block with shuffles issued together and every lane
+//     factors that block redundantly; two pivots share one reciprocal-square-root latency: with D2 = a00 a11 - a10^2 (the
+//     leading 2x2 minor, the same cancellation as a11 - a10^2/a00), 1/L11 = rsqrt(D2) sqrt(a00), so both MUFU seeds are in
+//     flight together;
+//   * no validity or padding selects on the chain: a non-positive pivot only raises `bad` (off the chain) and lets NaNs run
+//     through a factor that is thrown away; the padded last tile (pivots >= n forced to 1, zero column) takes the
+//     select-carrying TAIL instantiation;
+//   * the column vectors are computed for all lanes alike: rows inside the 4x4 block come out right by themselves (the tile
+//     is kept fully symmetric), rows above it hold round-off that nothing reads -- whoever stores the factor masks them;
+//   * the factor is published TRANSPOSED (LT[j][row], conflict-free, one store per column): the same array serves the
+//     update (broadcast LDS of LT[j][c]), the streaming warp and the inverse for the back substitution; nothing is
+//     overwritten, so no ping-pong.
 __device__ __forceinline__ double chol_rsqrt_fast(double d) {
     double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
     const double t = y * y, e = fma(-d, t, 1.0), p2 = fma(e, 0.375, 0.5), q = y * e;
     return fma(p2, q, y);
 }
-__device__ __forceinline__ void chol_pivot(double d, double cval, int lane, int j, bool pad, double& l, double& inv, bool& bad) {
-    const double r = chol_rsqrt_fast(d);
-    const bool good = d > 0.0 && r > 0.0 && r < 1.7976931348623157e308;
-    inv = pad ? 0.0 : (good ? r : 1.0);
-    const double ljj = pad ? 1.0 : (good ? d * r : 1.0);
-    bad = bad || (!pad && !good);
-    l = lane == j ? ljj : (lane > j ? cval * inv : 0.0);
+// Two consecutive pivots of a 2x2 block [a00 .; a10 a11] from two INDEPENDENT reciprocal square roots.
+template <bool TAIL>
+__device__ __forceinline__ void chol_pivot_pair(double a00, double a10, double a11, bool pad0, bool pad1, double& inv0, double& inv1, bool& bad) {
+    const double D2 = fma(a00, a11, -(a10 * a10));
+    const double s1 = chol_rsqrt_fast(a00), s2 = chol_rsqrt_fast(D2);
+    const double sq0 = a00 * s1;                               // sqrt(a00)
+    const bool good0 = a00 > 0.0 && a00 < 1.7976931348623157e308, good1 = D2 > 0.0 && D2 < 1.7976931348623157e308;
+    if (!TAIL) {
+        inv0 = s1; inv1 = s2 * sq0;
+        bad = bad || !good0 || !good1;
+    } else {
+        inv0 = pad0 ? 0.0 : (good0 ? s1 : 1.0);
+        inv1 = pad1 ? 0.0 : (good0 && good1 ? s2 * sq0 : 1.0);
+        bad = bad || (!pad0 && !good0) || (!pad1 && !good1);
+    }
 }
-__device__ __forceinline__ bool chol_tile_factor2(double (&col)[NB / (2 * PANEL_WARPS)][2], double (*Ls)[NB + 1], double (*cb)[2][NB], double* invd,
-                                                  int lane, int w, int gbase, int n, volatile int* groups_done, int* bad_flag) {
+#ifdef CHOL_FINE_TRACE
+__device__ unsigned long long g_chol_fine[64], g_chol_fine2[64];
+#define CHOL_FINE(k) do { if (gbase == 10 * NB && lane == 0) g_chol_fine[k] = (unsigned long long)clock64(); } while (0)
+#define CHOL_FINE2(k) do { if (gbase == 10 * NB && lane == 0) g_chol_fine2[(j0 / 4) * 8 + (k)] = (unsigned long long)clock64(); } while (0)
+#else
+#define CHOL_FINE(k) do { } while (0)
+#define CHOL_FINE2(k) do { } while (0)
+#endif
+// The owner's part of a round: factor the quad j0..j0+3 held in a[0..3] (lane = row), publish LT[j0+k][lane] and invd[j0+k].
+template <bool TAIL>
+__device__ __forceinline__ void chol_quad_owner(const double (&a)[4], double (*LT)[NB], double* invd, int lane, int j0, int gbase, int n, bool& bad) {
+    const double a00 = __shfl_sync(0xffffffffu, a[0], j0), a10 = __shfl_sync(0xffffffffu, a[0], j0 + 1),
+                 a20 = __shfl_sync(0xffffffffu, a[0], j0 + 2), a30 = __shfl_sync(0xffffffffu, a[0], j0 + 3),
+                 a11 = __shfl_sync(0xffffffffu, a[1], j0 + 1), a21 = __shfl_sync(0xffffffffu, a[1], j0 + 2),
+                 a31 = __shfl_sync(0xffffffffu, a[1], j0 + 3), a22 = __shfl_sync(0xffffffffu, a[2], j0 + 2),
+                 a32 = __shfl_sync(0xffffffffu, a[2], j0 + 3), a33 = __shfl_sync(0xffffffffu, a[3], j0 + 3);
+    CHOL_FINE2(0);
+    const int g0 = gbase + j0;
+    double i0, i1, i2, i3;
+    chol_pivot_pair<TAIL>(a00, a10, a11, g0 >= n, g0 + 1 >= n, i0, i1, bad);
+    const double l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
+    const double l21 = fma(-l20, l10, a21) * i1, l31 = fma(-l30, l10, a31) * i1;
+    const double b22 = fma(-l21, l21, fma(-l20, l20, a22)), b32 = fma(-l31, l21, fma(-l30, l20, a32)), b33 = fma(-l31, l31, fma(-l30, l30, a33));
+    chol_pivot_pair<TAIL>(b22, b32, b33, g0 + 2 >= n, g0 + 3 >= n, i2, i3, bad);
+    const double l32 = b32 * i2;
+    CHOL_FINE2(1);
+    // the four columns for this lane's row
+    double v0 = a[0] * i0;
+    double v1 = fma(-v0, l10, a[1]) * i1;
+    double v2 = fma(-v1, l21, fma(-v0, l20, a[2])) * i2;
+    double v3 = fma(-v2, l32, fma(-v1, l31, fma(-v0, l30, a[3]))) * i3;
+    if (TAIL) {                                                       // forced pivots: 1 on the diagonal, zero column
+        if (g0 >= n) v0 = lane == j0 ? 1.0 : 0.0;
+        if (g0 + 1 >= n) v1 = lane == j0 + 1 ? 1.0 : 0.0;
+        if (g0 + 2 >= n) v2 = lane == j0 + 2 ? 1.0 : 0.0;
+        if (g0 + 3 >= n) v3 = lane == j0 + 3 ? 1.0 : 0.0;
+    }
+    CHOL_FINE2(2);
+    LT[j0][lane] = v0; LT[j0 + 1][lane] = v1; LT[j0 + 2][lane] = v2; LT[j0 + 3][lane] = v3;
+    if (lane == 0) { *reinterpret_cast<double2*>(invd + j0) = make_double2(i0, i1); *reinterpret_cast<double2*>(invd + j0 + 2) = make_double2(i2, i3); }
+    CHOL_FINE2(3);
+}
+// col[q][h] = element (row `lane`, column 16q + 4w + h) of the (fully symmetric) tile.  Leaves the factor transposed in LT
+// (LT[j][r] = L(r,j) for r >= j; r < j: round-off, to be masked by the reader) and the reciprocal pivots in invd; ends with a
+// barrier.  stream: warp 0 hands every finished quad to the streaming warp through the quad's named barrier (ids 2..9, 32 + 32
+// threads; warp 0 only arrives) -- a hand-over compute-sanitizer's racecheck can see.
+__device__ __forceinline__ bool chol_tile_factor4(double (&col)[NB / (4 * PANEL_WARPS)][4], double (*LT)[NB], double* invd,
+                                                  int lane, int w, int gbase, int n, bool stream, int* bad_flag) {
     bool bad = false;
+    const bool tail = gbase + NB > n;
+    if (w == 0) CHOL_FINE(0);
 #pragma unroll 1
-    for (int jb = 0; jb < NB; jb += 2 * PANEL_WARPS) {
+    for (int jb = 0; jb < NB; jb += 4 * PANEL_WARPS) {
 #pragma unroll
-        for (int ow = 0; ow < PANEL_WARPS; ++ow) {                    // pivots j0, j0+1 are columns col[0][0..1] of warp ow
-            const int j0 = jb + 2 * ow, j1 = j0 + 1, pp = ow & 1;
+        for (int ow = 0; ow < PANEL_WARPS; ++ow) {                    // pivots j0..j0+3 are columns col[0][0..3] of warp ow
+            const int j0 = jb + 4 * ow;
             if (w == ow) {
-                const double a0 = col[0][0], a1 = col[0][1];
-                const double d0 = __shfl_sync(0xffffffffu, a0, j0), r10 = __shfl_sync(0xffffffffu, a0, j1), d1raw = __shfl_sync(0xffffffffu, a1, j1);
-                double l0, inv0, l1, inv1;
-                chol_pivot(d0, a0, lane, j0, gbase + j0 >= n, l0, inv0, bad);
-                const double t = r10 * inv0;                          // L(j1, j0)
-                chol_pivot(fma(-t, t, d1raw), fma(-l0, t, a1), lane, j1, gbase + j1 >= n, l1, inv1, bad);
-                cb[pp][0][lane] = l0; cb[pp][1][lane] = l1;
-                Ls[lane][j0] = l0; Ls[lane][j1] = l1;
-                if (lane == j0) invd[j0] = inv0;
-                if (lane == j1) invd[j1] = inv1;
+                CHOL_FINE(1 + (j0 / 4) * 4);
+                if (tail) chol_quad_owner<true>(col[0], LT, invd, lane, j0, gbase, n, bad);
+                else chol_quad_owner<false>(col[0], LT, invd, lane, j0, gbase, n, bad);
+                CHOL_FINE(2 + (j0 / 4) * 4);
             }
             chol_factor_barrier<true>();
-            // a 4-column group is final: warp 0 hands it to the streaming warp through the group's named barrier (ids 2..9,
-            // 32 + 32 threads; warp 0 only arrives) -- the hand-over compute-sanitizer's racecheck can see
-            if ((ow & 1) && groups_done && w == 0) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(2 + (j1 + 1) / PANEL_WARPS - 1) : "memory"); }
-            const double m0 = cb[pp][0][lane], m1 = cb[pp][1][lane];
+            if (w == 0) CHOL_FINE(3 + (j0 / 4) * 4);
+            if (stream && w == 0) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(2 + j0 / 4) : "memory"); }
+            const double m0 = LT[j0][lane], m1 = LT[j0 + 1][lane], m2 = LT[j0 + 2][lane], m3 = LT[j0 + 3][lane];
 #pragma unroll
-            for (int q = 0; q < NB / (2 * PANEL_WARPS); ++q) {
-                const int c0 = jb + 2 * PANEL_WARPS * q + 2 * w;      // columns held in col[q][0..1]; >= NB means wrapped (finished)
-                if (c0 > j1 && c0 < NB) {
-                    const double2 u0 = *reinterpret_cast<const double2*>(&cb[pp][0][c0]), u1 = *reinterpret_cast<const double2*>(&cb[pp][1][c0]);
-                    col[q][0] = fma(-m1, u1.x, fma(-m0, u0.x, col[q][0]));
-                    col[q][1] = fma(-m1, u1.y, fma(-m0, u0.y, col[q][1]));
+            for (int q = 0; q < NB / (4 * PANEL_WARPS); ++q) {
+                const int c0 = jb + 4 * PANEL_WARPS * q + 4 * w;      // columns held in col[q][0..3]; >= NB means wrapped (finished)
+                if (c0 > j0 && c0 < NB) {
+#pragma unroll
+                    for (int hh = 0; hh < 4; hh += 2) {
+                        const double2 u0 = *reinterpret_cast<const double2*>(&LT[j0][c0 + hh]), u1 = *reinterpret_cast<const double2*>(&LT[j0 + 1][c0 + hh]),
+                                      u2 = *reinterpret_cast<const double2*>(&LT[j0 + 2][c0 + hh]), u3 = *reinterpret_cast<const double2*>(&LT[j0 + 3][c0 + hh]);
+                        col[q][hh] = fma(-m3, u3.x, fma(-m2, u2.x, fma(-m1, u1.x, fma(-m0, u0.x, col[q][hh]))));
+                        col[q][hh + 1] = fma(-m3, u3.y, fma(-m2, u2.y, fma(-m1, u1.y, fma(-m0, u0.y, col[q][hh + 1]))));
+                    }
                 }
             }
         }
-        // rotate the register set by one pair
+        if (w == 0) CHOL_FINE(4 + (jb / 4 + 3) * 4);
+        // rotate the register set by one quad
 #pragma unroll
-        for (int q = 0; q < NB / (2 * PANEL_WARPS) - 1; ++q) { col[q][0] = col[q + 1][0]; col[q][1] = col[q + 1][1]; }
+        for (int q = 0; q < NB / (4 * PANEL_WARPS) - 1; ++q)
+#pragma unroll
+            for (int h = 0; h < 4; ++h) col[q][h] = col[q + 1][h];
     }
     if (bad) *bad_flag = 1;                        // a pivot is seen by its owning warp only
     chol_factor_barrier<true>();
@@ -160,6 +229,28 @@ __device__ __forceinline__ void chol_tile_trsm_group(double (&b)[NB], const doub
     for (int p2 = 0; p2 < NB - PANEL_WARPS; ++p2) b[p2] = b[p2 + PANEL_WARPS];
 #pragma unroll
     for (int u = 0; u < PANEL_WARPS; ++u) b[NB - PANEL_WARPS + u] = t[u];
+}
+// same with the factor stored transposed (LT[j][c] = L(c,j)), as chol_tile_factor4 leaves it
+__device__ __forceinline__ void chol_tile_trsm_t(double (&b)[NB], const double (*LT)[NB], const double* invd) {
+#pragma unroll 1
+    for (int jb = 0; jb < NB; jb += PANEL_WARPS) {
+#pragma unroll
+        for (int u = 0; u < PANEL_WARPS; ++u) {
+            const int j = jb + u;
+            const double xj = b[u] * invd[j];
+            b[u] = xj;
+#pragma unroll
+            for (int p2 = u + 1; p2 < NB; ++p2)
+                if (jb + p2 < NB) b[p2] = fma(-xj, LT[j][jb + p2], b[p2]);
+        }
+        double t[PANEL_WARPS];
+#pragma unroll
+        for (int u = 0; u < PANEL_WARPS; ++u) t[u] = b[u];
+#pragma unroll
+        for (int p2 = 0; p2 < NB - PANEL_WARPS; ++p2) b[p2] = b[p2 + PANEL_WARPS];
+#pragma unroll
+        for (int u = 0; u < PANEL_WARPS; ++u) b[NB - PANEL_WARPS + u] = t[u];
+    }
 }
 // all 32 pivots; on return b[] is back in natural order
 __device__ __forceinline__ void chol_tile_trsm(double (&b)[NB], const double (*Ls)[NB + 1], const double* invd) {
@@ -470,35 +561,40 @@ __device__ __forceinline__ void tile_to_smem_ts(double (*T)[TS], const double* _
         }
     }
 }
-__device__ __forceinline__ bool progress_wait(const unsigned* p, unsigned want) {
-    bool ok = (int)(ld_relaxed_gpu_u32(p) - want) >= 0;
-    if (!ok) {
-        const long long t0 = clock64();
-        for (;;) {
-            if ((int)(ld_relaxed_gpu_u32(p) - want) >= 0) { ok = true; break; }
-            if (clock64() - t0 > CF_TIMEOUT_CYCLES) break;
-        }
-    }
-    (void)ld_acquire_gpu_u32(p);
-    return ok;
+// Hand-over of a finished 4-column group between CTAs, flag-in-data ("LL" lines as in NCCL's low-latency protocol): a double
+// travels as one 16-byte line {lo, tag, hi, tag}; the reader polls the line itself and takes the value when both tags carry
+// the number of the current solve.  Against "store, __threadfence, flag / poll flag, then load" this takes the fence (the
+// streaming warp could publish one group per ~0.75 us, slower than the factorisation produces them) and one of the two L2
+// round trips out of the chain.  Only 8-byte atomicity of the store is assumed.  Lines of a group: [4 columns][32 rows], then
+// 4 reciprocal pivots; CHOL_LL_GROUP lines per group, 8 groups per tile.  Tags never repeat (solve numbers), so no reset.
+constexpr int CHOL_LL_GROUP = 4 * NB + 32;
+__host__ __device__ inline size_t chol_ll_bytes(int nbk) { return (size_t)nbk * (NB / PANEL_WARPS) * CHOL_LL_GROUP * 16; }
+__device__ __forceinline__ void ll_store(uint4* line, double v, unsigned tag) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(line), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ll_try(const uint4* line, unsigned tag, double& v) {
+    unsigned a, b, c, d;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(line) : "memory");
+    v = __hiloint2double((int)c, (int)a);
+    return b == tag && d == tag;
 }
 
 __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restrict__ A, int npad, int n, int nbk, int ntasks,
                                                                  double* __restrict__ dinv, int* __restrict__ fail,
-                                                                 unsigned* __restrict__ ready, unsigned* __restrict__ progress, unsigned epoch,
+                                                                 unsigned* __restrict__ ready, uint4* __restrict__ ll, unsigned epoch,
                                                                  double* __restrict__ Linv, unsigned long long* __restrict__ trace,
                                                                  const int* __restrict__ skip = nullptr, const unsigned* __restrict__ epoch_dev = nullptr) {
     if (skip && *skip) return;
     if (epoch_dev) epoch = *epoch_dev;       // CUDA-graph replays: the solve number lives on the device (kernel arguments are frozen)
     __shared__ __align__(16) double Pt[NB][TS], Qt[NB][TS], Xs[NB][TS];
     __shared__ double Ls[NB][NB + 1];
-    __shared__ __align__(16) double colbuf[2][2][NB];
-    __shared__ double invd[NB];
-    __shared__ int bad_flag, groups_done, ls_groups, abort_flag;
+    __shared__ __align__(16) double LT[NB][NB];        // factor of the diagonal tile, transposed (chol_tile_factor4)
+    __shared__ __align__(16) double invd[NB];
+    __shared__ int bad_flag, abort_flag;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, fr = lane >> 2, fc = lane & 3;
     const bool tile_warp = w < PANEL_WARPS;
-    const unsigned pbase = epoch * 16u;
-    if (threadIdx.x == 0) { bad_flag = 0; abort_flag = 0; groups_done = 0; ls_groups = 0; }
+    if (threadIdx.x == 0) { bad_flag = 0; abort_flag = 0; }
     __syncthreads();
 #define CHOL_TRACE(slot) do { if (trace && threadIdx.x == 0) trace[(size_t)t * 8 + (slot)] = chol_globaltimer(); } while (0)
 #define CHOL_TRACE_W4(slot) do { if (trace && threadIdx.x == PANEL_WARPS * 32) trace[(size_t)t * 8 + (slot)] = chol_globaltimer(); } while (0)
@@ -547,58 +643,85 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
             }
             __syncthreads();
             if (tile_warp) {
-                // loaders: warp w brings groups w, w+4 of L(c,c) (columns 4g..4g+3, rows >= 4g, reciprocal pivots) from A to
-                // Ls / invd as they are published -- four groups in flight -- and hands them to the solver in order
-                bool ok = true;
-#pragma unroll 1
-                for (int g = w; g < NB / PANEL_WARPS; g += PANEL_WARPS) {
-                    ok = progress_wait(progress + c, pbase + g + 1) && ok;
-                    if (g == 0) CHOL_TRACE(2);
-                    if (lane >= PANEL_WARPS * g) {
-                        const double* src = A + (size_t)(c * NB + lane) * npad + c * NB + PANEL_WARPS * g;
-                        const double2 v0 = __ldcg(reinterpret_cast<const double2*>(src)), v1 = __ldcg(reinterpret_cast<const double2*>(src + 2));
-                        Ls[lane][PANEL_WARPS * g] = v0.x; Ls[lane][PANEL_WARPS * g + 1] = v0.y; Ls[lane][PANEL_WARPS * g + 2] = v1.x; Ls[lane][PANEL_WARPS * g + 3] = v1.y;
-                    }
-                    if (lane < PANEL_WARPS) invd[PANEL_WARPS * g + lane] = __ldcg(dinv + c * NB + PANEL_WARPS * g + lane);
-                    // hand group g to the solver warp: a named barrier per group (ids 2..9, this warp + the solver warp = 64
-                    // threads): the loader arrives and goes on, the solver syncs on the groups in order.  (A spin on a shared-memory
-                    // counter did the same job; the barrier is what compute-sanitizer's racecheck understands.)
-                    __threadfence_block();
-                    asm volatile("bar.arrive %0, 64;" ::"r"(2 + g) : "memory");
-                }
-                if (!ok) abort_flag = 1;
-            } else {
-                double b[NB];
+                // X L(c,c)^T = tile, consumed group by group as the factor streams in.  A cycle-stamped trace showed a single
+                // solver warp (row per lane, all 32 columns: ~500 DFMA + ~500 LDS in one instruction stream, 4.3 us) falling behind
+                // a factorisation that now takes ~2.5 us, so the four tile warps share it: row per lane in EVERY warp, warp w owns
+                // the columns 4g+w (b[0] = column of the current group).  Per group: every warp posts its column of the group, ONE
+                // barrier (which the loader warp below joins when the group has arrived), every warp solves the 4x4 block
+                // for its row redundantly (10 FMAs) and applies the rank-4 update to its own <= 7 trailing columns.  After
+                // the last group only the 4x4 solve is left on the chain.
+                double (*exch)[PANEL_WARPS][NB] = reinterpret_cast<double (*)[PANEL_WARPS][NB]>(&LT[0][0]);     // [2][4][32], LT is idle here
+                double b[NB / PANEL_WARPS];
 #pragma unroll
-                for (int q = 0; q < NB; q += 2) { const double2 v = *reinterpret_cast<const double2*>(&Xs[lane][q]); b[q] = v.x; b[q + 1] = v.y; }
+                for (int p2 = 0; p2 < NB / PANEL_WARPS; ++p2) b[p2] = Xs[lane][PANEL_WARPS * p2 + w];
 #pragma unroll 1
                 for (int g = 0; g < NB / PANEL_WARPS; ++g) {
-                    asm volatile("bar.sync %0, 64;" ::"r"(2 + g) : "memory");
-                    chol_tile_trsm_group(b, Ls, invd, PANEL_WARPS * g);
-                }
-                if (!merged) {
-                    double* dst = A + (size_t)(i * NB + lane) * npad + c * NB;
+                    const int j0 = PANEL_WARPS * g;
+                    exch[g & 1][w][lane] = b[0];
+                    asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(CS_THREADS) : "memory");      // group g in Ls / invd (fifth warp) + every warp's column posted
+                    const double i0 = invd[j0], i1 = invd[j0 + 1], i2 = invd[j0 + 2], i3 = invd[j0 + 3];
+                    const double x0 = exch[g & 1][0][lane] * i0;
+                    const double x1 = fma(-x0, Ls[j0 + 1][j0], exch[g & 1][1][lane]) * i1;
+                    const double x2 = fma(-x1, Ls[j0 + 2][j0 + 1], fma(-x0, Ls[j0 + 2][j0], exch[g & 1][2][lane])) * i2;
+                    const double x3 = fma(-x2, Ls[j0 + 3][j0 + 2], fma(-x1, Ls[j0 + 3][j0 + 1], fma(-x0, Ls[j0 + 3][j0], exch[g & 1][3][lane]))) * i3;
 #pragma unroll
-                    for (int q = 0; q < NB; q += 2) *reinterpret_cast<double2*>(dst + q) = make_double2(b[q], b[q + 1]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < NB; q += 2) *reinterpret_cast<double2*>(&Xs[lane][q]) = make_double2(b[q], b[q + 1]);
-                }
-                CHOL_TRACE_W4(3);
-            }
-            __syncthreads();                                        // non-merged: stores issued; merged: X in Xs
-            if (abort_flag) { if (threadIdx.x == 0) atomicAdd(fail, 1000); return; }
-            if (merged) {
-                if (tile_warp) {
-#pragma unroll
-                    for (int u = 0; u < NB * NB / (2 * PANEL_WARPS * 32); ++u) {      // X -> A(i,c), coalesced
-                        const int e = threadIdx.x + u * PANEL_WARPS * 32, r = e >> 4, q = (e & 15) * 2;
-                        *reinterpret_cast<double2*>(A + (size_t)(i * NB + r) * npad + c * NB + q) = *reinterpret_cast<const double2*>(&Xs[r][q]);
+                    for (int p2 = 1; p2 < NB / PANEL_WARPS; ++p2) {
+                        if (g + p2 < NB / PANEL_WARPS) {
+                            const double* lr = &Ls[j0 + PANEL_WARPS * p2 + w][j0];          // row of this warp's column, broadcast
+                            b[p2] = fma(-x3, lr[3], fma(-x2, lr[2], fma(-x1, lr[1], fma(-x0, lr[0], b[p2]))));
+                        }
                     }
-                    tile_dmma_update(c2, Xs, Xs, lane, w, w + 1);
+                    if (w == (g & (PANEL_WARPS - 1))) {
+                        *reinterpret_cast<double2*>(&Xs[lane][j0]) = make_double2(x0, x1);
+                        *reinterpret_cast<double2*>(&Xs[lane][j0 + 2]) = make_double2(x2, x3);
+                    }
+#pragma unroll
+                    for (int p2 = 0; p2 < NB / PANEL_WARPS - 1; ++p2) b[p2] = b[p2 + 1];
                 }
-                __syncthreads();                                    // stores of X issued by every thread; Xs free
+                CHOL_TRACE(3);
+            } else {
+                // the fifth warp is the loader: it polls the LL lines of the groups in order, running ahead of the solve (the L2
+                // round trip of a poll stays off the chain), and hands group g over with the group's named barrier (ids 2..9)
+                bool ok = true;
+#pragma unroll 1
+                for (int g = 0; g < NB / PANEL_WARPS; ++g) {
+                    const int j0 = PANEL_WARPS * g;
+                    {
+                        // poll this thread's lines of group g: row `lane` of the 4 columns (rows >= 4g exist), lanes 0..3 a reciprocal pivot
+                        const uint4* grp = ll + ((size_t)c * (NB / PANEL_WARPS) + g) * CHOL_LL_GROUP;
+                        const bool has_row = lane >= j0;
+                        double v0 = 0, v1 = 0, v2 = 0, v3 = 0, vi = 0;
+                        bool done = false;
+                        const long long t0 = clock64();
+                        for (;;) {
+                            bool r = true;
+                            if (has_row) { r = ll_try(grp + lane, epoch, v0); r = ll_try(grp + NB + lane, epoch, v1) && r; r = ll_try(grp + 2 * NB + lane, epoch, v2) && r; r = ll_try(grp + 3 * NB + lane, epoch, v3) && r; }
+                            if (lane < PANEL_WARPS) r = ll_try(grp + 4 * NB + lane, epoch, vi) && r;
+                            if (r) { done = true; break; }
+                            if (clock64() - t0 > CF_TIMEOUT_CYCLES) break;
+                        }
+                        ok = done && ok;
+                        __syncwarp();
+                        if (g == 0) CHOL_TRACE_W4(2);
+                        if (has_row) { Ls[lane][j0] = v0; Ls[lane][j0 + 1] = v1; Ls[lane][j0 + 2] = v2; Ls[lane][j0 + 3] = v3; }
+                        if (lane < PANEL_WARPS) invd[j0 + lane] = vi;
+                    }
+                    __threadfence_block();
+                    asm volatile("bar.arrive %0, %1;" ::"r"(2 + g), "n"(CS_THREADS) : "memory");
+                }
+                if (!ok) abort_flag = 1;
             }
+            __syncthreads();                                        // X in Xs
+            if (abort_flag) { if (threadIdx.x == 0) atomicAdd(fail, 1000); return; }
+            if (tile_warp) {
+#pragma unroll
+                for (int u = 0; u < NB * NB / (2 * PANEL_WARPS * 32); ++u) {          // X -> A(i,c), coalesced
+                    const int e = threadIdx.x + u * PANEL_WARPS * 32, r = e >> 4, q = (e & 15) * 2;
+                    *reinterpret_cast<double2*>(A + (size_t)(i * NB + r) * npad + c * NB + q) = *reinterpret_cast<const double2*>(&Xs[r][q]);
+                }
+                if (merged) tile_dmma_update(c2, Xs, Xs, lane, w, w + 1);
+            }
+            __syncthreads();                                        // stores of X issued by every thread; Xs free
             if (threadIdx.x == PANEL_WARPS * 32) tile_publish(ready + i * nbk + c, epoch);     // the solver warp: its fence stalls nobody
             CHOL_TRACE_W4(4);
         }
@@ -611,34 +734,43 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
                     *reinterpret_cast<double2*>(&Xs[8 * w + fr][8 * cb + 2 * fc]) = make_double2(v0, v1);
                 }
                 chol_factor_barrier<true>();
-                double col[NB / (2 * PANEL_WARPS)][2];
+                double col[NB / (4 * PANEL_WARPS)][4];
 #pragma unroll
-                for (int q = 0; q < NB / (2 * PANEL_WARPS); ++q) {
-                    const double2 v = *reinterpret_cast<const double2*>(&Xs[lane][2 * PANEL_WARPS * q + 2 * w]);
-                    col[q][0] = v.x; col[q][1] = v.y;
+                for (int q = 0; q < NB / (4 * PANEL_WARPS); ++q) {
+                    const double2 v = *reinterpret_cast<const double2*>(&Xs[lane][4 * PANEL_WARPS * q + 4 * w]);
+                    const double2 v2 = *reinterpret_cast<const double2*>(&Xs[lane][4 * PANEL_WARPS * q + 4 * w + 2]);
+                    col[q][0] = v.x; col[q][1] = v.y; col[q][2] = v2.x; col[q][3] = v2.y;
                 }
-                const bool bad = chol_tile_factor2(col, Ls, colbuf, invd, lane, w, i * NB, n, &groups_done, &bad_flag);
+                const bool bad = chol_tile_factor4(col, LT, invd, lane, w, i * NB, n, true, &bad_flag);
                 if (bad && threadIdx.x == 0) atomicAdd(fail, 1);
                 CHOL_TRACE(5);
             } else {
 #pragma unroll 1
                 for (int g = 0; g < NB / PANEL_WARPS; ++g) {
                     asm volatile("bar.sync %0, 64;" ::"r"(2 + g) : "memory");         // group g of the factor is in Ls / invd
+                    uint4* grp = ll + ((size_t)i * (NB / PANEL_WARPS) + g) * CHOL_LL_GROUP;
                     if (lane >= PANEL_WARPS * g) {
-                        double* dst = A + (size_t)(i * NB + lane) * npad + i * NB + PANEL_WARPS * g;
-                        *reinterpret_cast<double2*>(dst) = make_double2(Ls[lane][PANEL_WARPS * g], Ls[lane][PANEL_WARPS * g + 1]);
-                        *reinterpret_cast<double2*>(dst + 2) = make_double2(Ls[lane][PANEL_WARPS * g + 2], Ls[lane][PANEL_WARPS * g + 3]);
+                        // rows above the diagonal inside the quad's 4x4 block hold round-off (chol_tile_factor4): store zeros
+                        const int rr = lane - PANEL_WARPS * g;
+                        const double v0 = LT[PANEL_WARPS * g][lane], v1 = rr >= 1 ? LT[PANEL_WARPS * g + 1][lane] : 0.0,
+                                     v2 = rr >= 2 ? LT[PANEL_WARPS * g + 2][lane] : 0.0, v3 = rr >= 3 ? LT[PANEL_WARPS * g + 3][lane] : 0.0;
+                        ll_store(grp + lane, v0, epoch); ll_store(grp + NB + lane, v1, epoch); ll_store(grp + 2 * NB + lane, v2, epoch); ll_store(grp + 3 * NB + lane, v3, epoch);
+                        double* dst = A + (size_t)(i * NB + lane) * npad + i * NB + PANEL_WARPS * g;       // for the back substitution (after the kernel)
+                        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                        *reinterpret_cast<double2*>(dst + 2) = make_double2(v2, v3);
                     }
-                    if (lane < PANEL_WARPS) dinv[i * NB + PANEL_WARPS * g + lane] = invd[PANEL_WARPS * g + lane];
-                    __syncwarp();
-                    if (lane == 0) { __threadfence(); st_relaxed_gpu_u32(progress + i, pbase + g + 1); }
+                    if (lane < PANEL_WARPS) {
+                        const double iv = invd[PANEL_WARPS * g + lane];
+                        ll_store(grp + 4 * NB + lane, iv, epoch);
+                        dinv[i * NB + PANEL_WARPS * g + lane] = iv;
+                    }
                 }
                 CHOL_TRACE_W4(6);
                 if (Linv) {             // off the critical path: L(i,i)^-1 (row-major) for the back substitution.  X L^T = I, X = L^-T
                     double b[NB];
 #pragma unroll
                     for (int q = 0; q < NB; ++q) b[q] = lane == q ? 1.0 : 0.0;
-                    chol_tile_trsm(b, Ls, invd);
+                    chol_tile_trsm_t(b, LT, invd);
 #pragma unroll
                     for (int q = 0; q < NB; ++q) Linv[((size_t)i * NB + q) * NB + lane] = b[q];      // Linv[q][lane] = X[lane][q]
                 }

@@ -43,11 +43,11 @@ int main(int argc, char** argv) {
             L[(size_t)r * npad + j] = v / ljj;
         }
     }
-    double *dA0, *dA, *ddinv, *dLinv, *dx; int* dfail; unsigned* dready; unsigned* dprogress; unsigned long long* dtrace;
+    double *dA0, *dA, *ddinv, *dLinv, *dx; int* dfail; unsigned* dready; uint4* dprogress; unsigned long long* dtrace;
     const size_t bytes = sizeof(double) * npad * npad;
     CK(cudaMalloc(&dA0, bytes)); CK(cudaMalloc(&dA, bytes)); CK(cudaMalloc(&ddinv, 8 * npad)); CK(cudaMalloc(&dfail, 16));
     CK(cudaMalloc(&dready, 4 * nbk * nbk)); CK(cudaMalloc(&dLinv, 8 * (size_t)npad * NB)); CK(cudaMalloc(&dx, 8 * npad)); CK(cudaMalloc(&dtrace, 64 * (size_t)nbk * nbk));
-    CK(cudaMemcpy(dA0, A.data(), bytes, cudaMemcpyHostToDevice)); CK(cudaMemset(dfail, 0, 16)); CK(cudaMemset(dready, 0, 4 * nbk * nbk)); CK(cudaMalloc(&dprogress, 4 * nbk)); CK(cudaMemset(dprogress, 0, 4 * nbk));
+    CK(cudaMemcpy(dA0, A.data(), bytes, cudaMemcpyHostToDevice)); CK(cudaMemset(dfail, 0, 16)); CK(cudaMemset(dready, 0, 4 * nbk * nbk)); CK(cudaMalloc(&dprogress, chol_ll_bytes(nbk))); CK(cudaMemset(dprogress, 0, chol_ll_bytes(nbk)));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     unsigned epoch = 0;
@@ -104,6 +104,17 @@ int main(int argc, char** argv) {
             if (merged) { seen[i] = us(2); solved[i] = us(3); pubx[i] = us(4); }
             if (variant == 1 && i == c + 1) { sub_seen[i] = us(2); sub_solved[i] = us(3); sub_pub[i] = us(4); }
         }
+#ifdef CHOL_FINE_TRACE
+        if (variant == 3) {
+            unsigned long long f[64]; CK(cudaMemcpyFromSymbol(f, g_chol_fine, sizeof f));
+            printf("  fine trace of the factorisation of tile 10 (cycles since entry): entry 0");
+            for (int k = 1; k < 36; ++k) if (f[k]) printf("%s %lld", (k % 4) == 1 ? "\n    round owner_in/owner_out/after_barrier/[after_update]:" : "", (long long)(f[k] - f[0]));
+            printf("\n");
+            unsigned long long g[64]; CK(cudaMemcpyFromSymbol(g, g_chol_fine2, sizeof g));
+            for (int r = 0; r < 8; ++r) printf("    round %d owner section, cycles: shuffles->pivots %lld, column vectors %lld, stores %lld\n", r,
+                                               (long long)(g[r * 8 + 1] - g[r * 8]), (long long)(g[r * 8 + 2] - g[r * 8 + 1]), (long long)(g[r * 8 + 3] - g[r * 8 + 2]));
+        }
+#endif
         printf("  j  published(j,j) us   step   | updates_done  diag_seen  solved  x_published  factored\n");
         for (int j = 0; j < nbk; ++j) {
             if (variant >= 2) printf("  %2d %10.2f %10.2f | %8.2f %8.2f %8.2f %8.2f %8.2f\n", j, pub[j], j ? pub[j] - pub[j - 1] : pub[j], upd[j], seen[j], solved[j], pubx[j], fact[j]);
