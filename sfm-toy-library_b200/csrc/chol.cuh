@@ -546,6 +546,14 @@ __device__ __forceinline__ void tile_dmma_update(double (&acc)[4][2], const doub
             if (cb < ncb) chol_dmma(acc[cb][0], acc[cb][1], a, Q[8 * cb + fr][4 * ks + fc]);
     }
 }
+// one k-step (columns 4ks..4ks+3 of P and Q) of the update above
+__device__ __forceinline__ void tile_dmma_update_k(double (&acc)[4][2], const double (*P)[TS], const double (*Q)[TS], int lane, int w, int ncb, int ks) {
+    const int fr = lane >> 2, fc = lane & 3;
+    const double a = -P[8 * w + fr][4 * ks + fc];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb)
+        if (cb < ncb) chol_dmma(acc[cb][0], acc[cb][1], a, Q[8 * cb + fr][4 * ks + fc]);
+}
 __device__ __forceinline__ void tile_to_smem_ts(double (*T)[TS], const double* __restrict__ A, int npad, int row0, int col0) {
     if (threadIdx.x < PANEL_WARPS * 32) {
         double2 v[NB * NB / (2 * PANEL_WARPS * 32)];
@@ -677,6 +685,9 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
                     }
 #pragma unroll
                     for (int p2 = 0; p2 < NB / PANEL_WARPS - 1; ++p2) b[p2] = b[p2 + 1];
+                    // lookahead tile: (c+1,c+1) -= X_G X_G^T for the PREVIOUS group (in Xs since this group's barrier), one DMMA k-step,
+                    // in the slack while the next group is on its way -- same k order as a whole-tile update, so the same bits
+                    if (merged && g > 0) tile_dmma_update_k(c2, Xs, Xs, lane, w, w + 1, g - 1);
                 }
                 CHOL_TRACE(3);
             } else {
@@ -714,31 +725,36 @@ __global__ void __launch_bounds__(CS_THREADS) chol_stream_kernel(double* __restr
             __syncthreads();                                        // X in Xs
             if (abort_flag) { if (threadIdx.x == 0) atomicAdd(fail, 1000); return; }
             if (tile_warp) {
+                if (merged) tile_dmma_update_k(c2, Xs, Xs, lane, w, w + 1, NB / PANEL_WARPS - 1);       // the last group's k-step
 #pragma unroll
                 for (int u = 0; u < NB * NB / (2 * PANEL_WARPS * 32); ++u) {          // X -> A(i,c), coalesced
                     const int e = threadIdx.x + u * PANEL_WARPS * 32, r = e >> 4, q = (e & 15) * 2;
                     *reinterpret_cast<double2*>(A + (size_t)(i * NB + r) * npad + c * NB + q) = *reinterpret_cast<const double2*>(&Xs[r][q]);
                 }
-                if (merged) tile_dmma_update(c2, Xs, Xs, lane, w, w + 1);
+                // the stores of X are issued: the fifth warp publishes the tile (its fence stalls nobody); the tile warps only arrive
+                asm volatile("bar.arrive 10, %0;" ::"n"(CS_THREADS) : "memory");
+            } else {
+                asm volatile("bar.sync 10, %0;" ::"n"(CS_THREADS) : "memory");
+                if (lane == 0) tile_publish(ready + i * nbk + c, epoch);
+                CHOL_TRACE_W4(4);
             }
-            __syncthreads();                                        // stores of X issued by every thread; Xs free
-            if (threadIdx.x == PANEL_WARPS * 32) tile_publish(ready + i * nbk + c, epoch);     // the solver warp: its fence stalls nobody
-            CHOL_TRACE_W4(4);
         }
         if (i == c || merged) {
-            // diagonal tile: fragment layout -> Xs -> phase-1 layout, factor; the solver warp streams the columns out
+            // diagonal tile: fragment layout -> Pt (free since the update loop; Xs may still be read) -> phase-1 layout, factor;
+            // the fifth warp streams the columns out
             if (tile_warp) {
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
                     const double v0 = merged ? c2[cb][0] : c1[cb][0], v1 = merged ? c2[cb][1] : c1[cb][1];
-                    *reinterpret_cast<double2*>(&Xs[8 * w + fr][8 * cb + 2 * fc]) = make_double2(v0, v1);
+                    *reinterpret_cast<double2*>(&Pt[8 * w + fr][8 * cb + 2 * fc]) = make_double2(v0, v1);
                 }
                 chol_factor_barrier<true>();
+                CHOL_TRACE(7);
                 double col[NB / (4 * PANEL_WARPS)][4];
 #pragma unroll
                 for (int q = 0; q < NB / (4 * PANEL_WARPS); ++q) {
-                    const double2 v = *reinterpret_cast<const double2*>(&Xs[lane][4 * PANEL_WARPS * q + 4 * w]);
-                    const double2 v2 = *reinterpret_cast<const double2*>(&Xs[lane][4 * PANEL_WARPS * q + 4 * w + 2]);
+                    const double2 v = *reinterpret_cast<const double2*>(&Pt[lane][4 * PANEL_WARPS * q + 4 * w]);
+                    const double2 v2 = *reinterpret_cast<const double2*>(&Pt[lane][4 * PANEL_WARPS * q + 4 * w + 2]);
                     col[q][0] = v.x; col[q][1] = v.y; col[q][2] = v2.x; col[q][3] = v2.y;
                 }
                 const bool bad = chol_tile_factor4(col, LT, invd, lane, w, i * NB, n, true, &bad_flag);

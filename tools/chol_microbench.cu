@@ -93,14 +93,14 @@ int main(int argc, char** argv) {
         // critical path: per diagonal tile j, the stamps of the task that factors it
         unsigned long long t_start = ~0ull;
         for (int t = 0; t < ntasks; ++t) t_start = std::min(t_start, tr[(size_t)t * 8]);
-        std::vector<double> pub(nbk, 0), seen(nbk, 0), solved(nbk, 0), pubx(nbk, 0), fact(nbk, 0), upd(nbk, 0);
+        std::vector<double> pub(nbk, 0), seen(nbk, 0), solved(nbk, 0), pubx(nbk, 0), fact(nbk, 0), upd(nbk, 0), fstart(nbk, 0);
         std::vector<double> sub_seen(nbk, 0), sub_solved(nbk, 0), sub_pub(nbk, 0);
         for (int t = 0; t < ntasks; ++t) {
             int i, c; bool merged;
             if (variant == 1) decode<false>(t, nbk, i, c, merged); else decode<true>(t, nbk, i, c, merged);
             const unsigned long long* e = &tr[(size_t)t * 8];
             auto us = [&](int slot) { return e[slot] ? (e[slot] - t_start) * 1e-3 : 0.0; };
-            if (i == c || merged) { pub[i] = us(6); fact[i] = us(5); upd[i] = us(1); }
+            if (i == c || merged) { pub[i] = us(6); fact[i] = us(5); upd[i] = us(1); fstart[i] = us(7); }
             if (merged) { seen[i] = us(2); solved[i] = us(3); pubx[i] = us(4); }
             if (variant == 1 && i == c + 1) { sub_seen[i] = us(2); sub_solved[i] = us(3); sub_pub[i] = us(4); }
         }
@@ -115,9 +115,9 @@ int main(int argc, char** argv) {
                                                (long long)(g[r * 8 + 1] - g[r * 8]), (long long)(g[r * 8 + 2] - g[r * 8 + 1]), (long long)(g[r * 8 + 3] - g[r * 8 + 2]));
         }
 #endif
-        printf("  j  published(j,j) us   step   | updates_done  diag_seen  solved  x_published  factored\n");
+        printf("  j  published(j,j) us   step   | updates_done  diag_seen  solved  x_published  factor_start  factored\n");
         for (int j = 0; j < nbk; ++j) {
-            if (variant >= 2) printf("  %2d %10.2f %10.2f | %8.2f %8.2f %8.2f %8.2f %8.2f\n", j, pub[j], j ? pub[j] - pub[j - 1] : pub[j], upd[j], seen[j], solved[j], pubx[j], fact[j]);
+            if (variant >= 2) printf("  %2d %10.2f %10.2f | %8.2f %8.2f %8.2f %8.2f %8.2f %8.2f\n", j, pub[j], j ? pub[j] - pub[j - 1] : pub[j], upd[j], seen[j], solved[j], pubx[j], fstart[j], fact[j]);
             else printf("  %2d %10.2f %10.2f | %8.2f (sub-diagonal owner: seen %8.2f solved %8.2f published %8.2f) factored %8.2f\n", j, pub[j], j ? pub[j] - pub[j - 1] : pub[j], upd[j], sub_seen[j], sub_solved[j], sub_pub[j], fact[j]);
         }
     }
