@@ -1024,7 +1024,7 @@ struct sfmb200_ba_problem {
     double* A; double* y_cf; double* dinv;
     int grid_point = 0, grid_backsub = 0, grid_camera = 0; bool one_wave = true;   // persistent grids = co-resident CTA count
     double* Linv = nullptr;           // [npad/NB][NB][NB] inverses of the diagonal tiles (dataflow Cholesky -> back substitution)
-    bool backsolve_staged = false;
+    bool backsolve_staged = false, backsolve_cluster = false;
     uint4* chol_ll = nullptr; int chol_grid_stream = 0; bool chol_stream = true;
     unsigned* chol_ready = nullptr; unsigned chol_epoch = 0; int chol_grid = 0; bool chol_fused = true, chol_lookahead = false;   // dataflow Cholesky (K4)
     unsigned* solve_counter = nullptr;   // device-side number of the current dense solve (incremented by ba_assemble_kernel)
@@ -1278,7 +1278,8 @@ static int dense_solve(sfmb200_ba_problem* P, const sfmb200_ba_options* opt, dou
     }
     {
         const size_t smem = chol_backsolve_smem(npad, P->backsolve_staged);
-        if (P->backsolve_staged && P->chol_fused) chol_backsolve_kernel<true, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
+        if (P->backsolve_cluster) chol_backsolve_cluster_kernel<<<BS_CLUSTER, chol_backsolve_cluster_threads(P->n), chol_backsolve_cluster_smem(P->n), ctx->stream>>>(P->A, P->Linv, npad, P->n, P->y_cf, P->fail + 1, skip);
+        else if (P->backsolve_staged && P->chol_fused) chol_backsolve_kernel<true, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
         else if (P->backsolve_staged) chol_backsolve_kernel<true, false><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
         else if (P->chol_fused) chol_backsolve_kernel<false, true><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
         else chol_backsolve_kernel<false, false><<<1, 640, smem, ctx->stream>>>(P->A, P->dinv, P->Linv, npad, P->n, P->y_cf, skip);
@@ -1455,6 +1456,17 @@ int sfmb200_ba_problem_create(sfmb200_ctx* ctx, int nc, int np, int nobs, const 
         if (P->backsolve_staged) {
             CRT(cudaFuncSetAttribute(chol_backsolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs));
             CRT(cudaFuncSetAttribute(chol_backsolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs));
+        }
+        // back substitution on a cluster of BS_CLUSTER SMs (needs the inverse diagonal tiles the dataflow factorisations leave)
+        const size_t cs = chol_backsolve_cluster_smem(P->n);
+        const int cthreads = chol_backsolve_cluster_threads(P->n);
+        if (P->chol_fused && !(bm && (strcmp(bm, "direct") == 0 || strcmp(bm, "single") == 0)) && cs <= 200 * 1024 && cthreads <= 512) {
+            CRT(cudaFuncSetAttribute(chol_backsolve_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(BS_CLUSTER); cfg.blockDim = dim3(cthreads); cfg.dynamicSmemBytes = cs;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, chol_backsolve_cluster_kernel, &cfg) == cudaSuccess && nclusters > 0) P->backsolve_cluster = true;
+            else (void)cudaGetLastError();
         }
     }
     CRT(cudaMemsetAsync(P->counters, 0, 64, st));

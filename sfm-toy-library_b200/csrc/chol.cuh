@@ -907,3 +907,130 @@ __global__ void __launch_bounds__(640) chol_backsolve_kernel(const double* __res
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// Back substitution on a thread-block CLUSTER (default when L(kb,kb)^-1 tiles exist).  The single-CTA kernel above is bound by
+// ONE SM's shared-memory bandwidth: every block row (32 x n doubles) is written to and read from shared memory once per step,
+// ~2 us per 32 unknowns.  Here BS_CLUSTER CTAs on BS_CLUSTER SMs share the columns -- CTA r owns the 32-column blocks b with
+// b mod BS_CLUSTER = r: their part of y, their slice of every block row (staged with cp.async one step ahead, as above), and the
+// solve of those blocks.  Per step the CTA that owns block kb turns y_kb into x_kb with the inverse tile (one 32-term dot product
+// per lane) and pushes the 32 values into every CTA's shared memory with st.async, which signals that CTA's mbarrier for the step
+// (complete_tx; armed locally with expect_tx = 256 bytes); every CTA waits on its own mbarrier and subtracts the block row's
+// contribution from its columns (slices staged TWO steps ahead: the L2 latency of a block row exceeds a step).  No cluster-wide barrier inside the loop: one DSMEM hop (~215 cycles) per step.
+// Slots (x block + mbarrier) are indexed kb mod BS_CLUSTER: a CTA solves one of any BS_CLUSTER consecutive blocks, so no CTA can
+// be more than BS_CLUSTER - 1 steps ahead of another and a slot is never overwritten while somebody still reads it.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BS_CLUSTER = 8;
+__host__ __device__ inline int chol_backsolve_cluster_threads(int n) { const int nb = (n - 1) / NB + 1; return 32 + 32 * ((nb + BS_CLUSTER - 1) / BS_CLUSTER); }
+__host__ __device__ inline size_t chol_backsolve_cluster_smem(int n) {
+    const size_t nwork = (size_t)chol_backsolve_cluster_threads(n) - 32;
+    return sizeof(double) * ((size_t)BS_CLUSTER * NB + (size_t)NB * NB + nwork + 2 * (size_t)NB * nwork);
+}
+__device__ __forceinline__ unsigned bs_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned bs_mapa(unsigned addr, unsigned rank) { unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ bool bs_mbar_try_wait(unsigned addr, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(512)
+chol_backsolve_cluster_kernel(const double* __restrict__ A, const double* __restrict__ Linv, int npad, int n, double* __restrict__ x,
+                              int* __restrict__ fail, const int* __restrict__ skip = nullptr) {
+    if (skip && *skip) return;                    // the same flag for every CTA of the cluster
+    extern __shared__ double sm[];
+    __shared__ __align__(8) unsigned long long mbar[BS_CLUSTER];
+    const int tid = threadIdx.x, lane = tid & 31, nwork = blockDim.x - 32, t = tid - 32;
+    const bool solver = tid < 32;
+    unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    const int kb_first = (n - 1) / NB;
+    double* xb = sm;                              // [BS_CLUSTER][NB]   x blocks as they arrive
+    double* dstage = xb + BS_CLUSTER * NB;        // [NB][NB]           inverse tile of the next block this CTA solves
+    double* yl = dstage + NB * NB;                // [nwork]            y of the own columns
+    double* stage = yl + nwork;                   // [2][NB][nwork]     own slices of the next two block rows (buffer kb & 1)
+    const int blk = (int)r + (t >> 5) * BS_CLUSTER, col = blk * NB + (t & 31);      // worker t's column
+    const bool own = !solver && blk <= kb_first;
+    auto arm = [&](int slot) {                    // one local arrival + the 256 bytes of an x block complete a phase
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bs_smem_u32(&mbar[slot])), "r"(NB * 8) : "memory");
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < BS_CLUSTER; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bs_smem_u32(&mbar[j])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < BS_CLUSTER && j <= kb_first; ++j) arm((kb_first - j) % BS_CLUSTER);      // first use of every slot
+    }
+    auto issue_row = [&](int kb) {                // worker: its column of block row kb -> stage buffer kb & 1
+        if (own && blk < kb) {
+            double* dst = stage + (size_t)(kb & 1) * NB * nwork + t;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) cp_async8(dst + (size_t)m * nwork, A + (size_t)(kb * NB + m) * npad + col);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto issue_tile = [&](int kb) {               // solver warp: column `lane` of L(kb,kb)^-1 (row-major)
+        if (kb >= 0) {
+#pragma unroll
+            for (int m = 0; m < NB; ++m) cp_async8(dstage + m * NB + lane, Linv + ((size_t)kb * NB + m) * NB + lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (solver) issue_tile(kb_first - ((kb_first - (int)r) % BS_CLUSTER + BS_CLUSTER) % BS_CLUSTER);
+    else { issue_row(kb_first); issue_row(kb_first - 1); }
+    if (own) yl[t] = col < n ? A[(size_t)n * npad + col] : 0.0;
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    bool ok = true;
+    for (int kb = kb_first; kb >= 0; --kb) {
+        const int slot = kb % BS_CLUSTER;
+        const unsigned parity = (unsigned)((kb_first - kb) / BS_CLUSTER) & 1u;
+        const bool active = own && blk < kb;
+        double reg[NB];
+        if (!solver) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");         // block row kb has landed (row kb-1 may still be in flight)
+            if (active) {
+                const double* src = stage + (size_t)(kb & 1) * NB * nwork + t;
+#pragma unroll
+                for (int m = 0; m < NB; ++m) reg[m] = src[(size_t)m * nwork];
+            }
+            issue_row(kb - 2);                                           // into the buffer just read (own slots only)
+        } else if ((int)r == slot) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const double* yk = yl + ((kb - (int)r) / BS_CLUSTER) * NB;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;      // x_r = sum_c Linv[c][r] y_c   (Linv lower triangular: exact zeros for c < r)
+#pragma unroll
+            for (int c = 0; c < NB; c += 4) {
+                s0 = fma(dstage[c * NB + lane], yk[c], s0); s1 = fma(dstage[(c + 1) * NB + lane], yk[c + 1], s1);
+                s2 = fma(dstage[(c + 2) * NB + lane], yk[c + 2], s2); s3 = fma(dstage[(c + 3) * NB + lane], yk[c + 3], s3);
+            }
+            const double xv = (s0 + s1) + (s2 + s3);
+            const unsigned xa = bs_smem_u32(xb + slot * NB + lane), ma = bs_smem_u32(&mbar[slot]);
+#pragma unroll
+            for (unsigned p = 0; p < BS_CLUSTER; ++p)                    // the store itself signals the peer's mbarrier (complete_tx, 8 bytes)
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                             :: "r"(bs_mapa(xa, p)), "l"(__double_as_longlong(xv)), "r"(bs_mapa(ma, p)) : "memory");
+            if (kb * NB + lane < n) x[kb * NB + lane] = xv;
+            __syncwarp();                          // every lane is done with dstage
+            issue_tile(kb - BS_CLUSTER);
+        }
+        {   // everybody waits for x_kb (every thread on every step: the parity of a slot is only meaningful in order)
+            const unsigned ma = bs_smem_u32(&mbar[slot]);
+            if (!bs_mbar_try_wait(ma, parity)) {
+                const long long t0 = clock64();
+                while (!bs_mbar_try_wait(ma, parity)) if (clock64() - t0 > CF_TIMEOUT_CYCLES) { ok = false; break; }
+            }
+            if (tid == 0 && kb - BS_CLUSTER >= 0) arm(slot);             // this phase is complete: arm the slot's next use
+        }
+        if (active) {
+            const double* xk = xb + slot * NB;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+            for (int m = 0; m < NB; m += 4) {
+                s0 = fma(reg[m], xk[m], s0); s1 = fma(reg[m + 1], xk[m + 1], s1); s2 = fma(reg[m + 2], xk[m + 2], s2); s3 = fma(reg[m + 3], xk[m + 3], s3);
+            }
+            yl[t] -= (s0 + s1) + (s2 + s3);
+        }
+        if (!__syncthreads_and(ok)) { if (tid == 0) atomicAdd(fail, 1000); break; }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    // nobody leaves while a peer may still push into its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}

@@ -135,6 +135,23 @@ int main(int argc, char** argv) {
             CK(cudaFuncSetAttribute(chol_backsolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_staged));
             CK(cudaFuncSetAttribute(chol_backsolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_staged));
         }
+        {   // cluster variant (BS_CLUSTER CTAs)
+            const size_t cs = chol_backsolve_cluster_smem(n); const int cthreads = chol_backsolve_cluster_threads(n);
+            CK(cudaFuncSetAttribute(chol_backsolve_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs));
+            float total = 0;
+            for (int rep = 0; rep < reps + 1; ++rep) {
+                CK(cudaMemset(dx, 0, 8 * npad)); CK(cudaDeviceSynchronize());
+                CK(cudaEventRecord(e0));
+                chol_backsolve_cluster_kernel<<<BS_CLUSTER, cthreads, cs>>>(dA, dLinv, npad, n, dx, dfail);
+                CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep) total += ms;
+            }
+            CK(cudaMemcpy(xg.data(), dx, 8 * n, cudaMemcpyDeviceToHost));
+            double err = 0, ref = 0;
+            for (int r = 0; r < n; ++r) { err = std::max(err, std::fabs(xg[r] - xr[r])); ref = std::max(ref, std::fabs(xr[r])); }
+            int fl[4]; CK(cudaMemcpy(fl, dfail, 16, cudaMemcpyDeviceToHost));
+            printf("{\"variant\": \"backsolve cluster of %d CTAs x %d threads, %zu B smem\", \"avg_us\": %.1f, \"max_abs_err\": %.3e, \"max_abs_x\": %.3e, \"fail\": %d}\n", BS_CLUSTER, cthreads, cs, total / reps * 1e3, err, ref, fl[0]);
+        }
         for (int v = 0; v < 4; ++v) {
             const bool staged = v & 1, inv = v & 2;
             if (staged && !can_stage) continue;
