@@ -6,7 +6,8 @@
 //   instruction, 8 instructions per tile.
 // L2 (BASELINE.json configs[3] wording: SIFT-128; cv::BFMatcher(NORM_L2)).  SIFT descriptors are integer-valued 0..255, so
 //   |a-b|^2 = |a|^2 + |b|^2 - 2 <a,b>  with <a,b> <= 128*255^2 < 2^31 is EXACT in u8 x u8 -> s32: 4 instructions per tile; the
-//   train norms ride along in shared memory, the epilogue ranks  e = |b|^2 - 2<a,b>  and adds |a|^2 at the end.
+//   train norms ride along in shared memory, the epilogue ranks  e = |b|^2 - 2<a,b>  (as packed keys e * 128 + column, one
+//   multiply-add per element, see l2_chunk) and adds |a|^2 at the end.
 //
 //   * operands: expanded ONCE per descriptor set (expand kernels) into blocks of 256 rows in the UMMA K-major, no-swizzle
 //     ("interleaved") canonical form: core matrix = 8 rows x 16 bytes, LBO = distance between the 16-byte K chunks, SBO =
@@ -105,7 +106,8 @@ __global__ void __launch_bounds__(256) expand_l2_blocks_kernel(const float* __re
         }
         *reinterpret_cast<uint4*>(out + (size_t)kc * (TC_N * 16) + off) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    norms[(size_t)blockIdx.x * TC_N + r] = valid ? nrm : 0;
+    // packed for the epilogue's key arithmetic: |b|^2 * 128 + (row & 127: the column inside its 128-column half of the tile); |b|^2 <= 128 * 255^2 < 2^23
+    norms[(size_t)blockIdx.x * TC_N + r] = ((valid ? nrm : 0) << 7) | (r & 127);
     if (!ok) atomicExch(bad, 1);
 }
 
@@ -168,6 +170,37 @@ __device__ __forceinline__ void hamming_chunk(const uint32_t (&v)[32], int cb, i
                 k1 = max(k1, lo); k0 = hi;
             }
             thr = k1 >> 16;             // a later candidate needs a strictly larger v: with equal v its index loses
+        }
+    }
+}
+
+// L2 key: e * 128 + (column inside the 128-column half of the tile), e = |b|^2 - 2<a,b> in [-2 * 128 * 255^2, 128 * 255^2] -- 25 bits, so the key
+// fits a signed 32-bit word exactly and ONE multiply-add makes it from the accumulator: key = nk - (acc << 8) with the packed norm
+// nk = |b|^2 * 128 + column that rides along in shared memory.  Smaller key = smaller distance, ties to the smaller column: the order
+// of cv::batchDistance inside a tile.  The keys only live for one tile (7 index bits): per 8-column group a 3-input-min tree and a
+// vote against thrk (the running second best of the whole row as a key bound, tightened by the tile's own second best), then the
+// {k0, k1, key} -> two smallest network; after the tile the two survivors are unpacked and merged into the (distance, index) pairs.
+constexpr int L2KEY_EMPTY = INT_MAX;
+template <bool PART>
+__device__ __forceinline__ void l2_chunk(const uint32_t (&v)[32], const int32_t* __restrict__ nk, int ncols, int& k0, int& k1, int& thrk) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int4 n0 = *reinterpret_cast<const int4*>(nk + 8 * g), n1 = *reinterpret_cast<const int4*>(nk + 8 * g + 4);
+        int key[8] = {n0.x - ((int)v[8 * g] << 8), n0.y - ((int)v[8 * g + 1] << 8), n0.z - ((int)v[8 * g + 2] << 8), n0.w - ((int)v[8 * g + 3] << 8),
+                      n1.x - ((int)v[8 * g + 4] << 8), n1.y - ((int)v[8 * g + 5] << 8), n1.z - ((int)v[8 * g + 6] << 8), n1.w - ((int)v[8 * g + 7] << 8)};
+        if (PART) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (8 * g + j >= ncols) key[j] = L2KEY_EMPTY;
+        }
+        int m = __vimin3_s32(key[0], key[1], key[2]);
+        m = __vimin3_s32(m, key[3], key[4]); m = __vimin3_s32(m, key[5], key[6]); m = min(m, key[7]);
+        if (PART || __any_sync(0xffffffffu, m < thrk)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int lo = min(k0, key[j]), hi = max(k0, key[j]);
+                k1 = min(k1, hi); k0 = lo;
+            }
+            thrk = min(thrk, k1);
         }
     }
 }
@@ -273,6 +306,8 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
             const int t_row0 = (tile0 + t) * TC_N, t_rows = min(TC_N, pd.nt - t_row0);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * TC_N + (uint32_t)h * TC_PART_COLS;
             const int32_t* nrm = sNorm + (t % TC_NORM_SLOTS) * TC_N;
+            int kt0 = L2KEY_EMPTY, kt1 = L2KEY_EMPTY;                         // L2: the tile's two smallest keys
+            if (L2) thr = best.i1 < 0 ? INT_MAX : (best.d1 << 7);           // a later row must be STRICTLY closer than the running second best
             // one 32-column chunk of this warp's column half
             auto chunk = [&](const uint32_t (&v)[32], int cc) {
                 const int c0 = h * TC_PART_COLS + cc;
@@ -282,25 +317,8 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
                     if (!part) hamming_chunk<false>(v, cb, 32, k0, k1, thr);
                     else hamming_chunk<true>(v, cb, t_rows - c0, k0, k1, thr);      // last tile of the image only
                 } else {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int4 n0 = *reinterpret_cast<const int4*>(nrm + c0 + 8 * g), n1 = *reinterpret_cast<const int4*>(nrm + c0 + 8 * g + 4);
-                        int e[8] = {n0.x - 2 * (int)v[8 * g], n0.y - 2 * (int)v[8 * g + 1], n0.z - 2 * (int)v[8 * g + 2], n0.w - 2 * (int)v[8 * g + 3],
-                                    n1.x - 2 * (int)v[8 * g + 4], n1.y - 2 * (int)v[8 * g + 5], n1.z - 2 * (int)v[8 * g + 6], n1.w - 2 * (int)v[8 * g + 7]};
-                        int m = __vimin3_s32(e[0], e[1], e[2]);
-                        m = __vimin3_s32(m, e[3], e[4]); m = __vimin3_s32(m, e[5], e[6]); m = min(m, e[7]);
-                        if (__any_sync(0xffffffffu, m < thr) || part) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int d = e[j], idx = t_row0 + c0 + 8 * g + j;
-                                const bool valid = !part || (c0 + 8 * g + j < t_rows);
-                                const bool lt0 = valid && d < best.d0, lt1 = valid && d < best.d1;
-                                const int nd1 = lt0 ? best.d0 : (lt1 ? d : best.d1), ni1 = lt0 ? best.i0 : (lt1 ? idx : best.i1);
-                                best.d0 = lt0 ? d : best.d0; best.i0 = lt0 ? idx : best.i0; best.d1 = nd1; best.i1 = ni1;
-                            }
-                            thr = best.d1;
-                        }
-                    }
+                    if (!part) l2_chunk<false>(v, nrm + c0, 32, kt0, kt1, thr);
+                    else l2_chunk<true>(v, nrm + c0, t_rows - c0, kt0, kt1, thr);
                 }
             };
             // software pipeline over the 4 chunks: the tcgen05.ld of the next chunk is in flight while this one is ranked
@@ -314,6 +332,15 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + a);
+            if (L2) {                                                       // the tile's survivors -> (e, global index), ascending key order
+                auto ins = [&](int key) {
+                    if (key == L2KEY_EMPTY) return;
+                    const int d = key >> 7, idx = t_row0 + (h >> 1) * 128 + (key & 127);       // this warp's 64 columns lie in half (h >> 1) of the tile
+                    if (d < best.d0) { best.d1 = best.d0; best.i1 = best.i0; best.d0 = d; best.i0 = idx; }
+                    else if (d < best.d1) { best.d1 = d; best.i1 = idx; }
+                };
+                ins(kt0); ins(kt1);
+            }
         }
         if (h > 0) half_best[(h - 1) * TC_M + q * 32 + lane] = L2 ? make_int4(best.d0, best.i0, best.d1, best.i1) : make_int4(k0, k1, 0, 0);
     }
@@ -350,7 +377,7 @@ __global__ void __launch_bounds__(TC_THREADS) knn2_tc_kernel(const uint8_t* __re
                 ins(o.x, o.y); ins(o.z, o.w);
             }
             if (row < pd.nq) {
-                const int na = norms[(size_t)(pd.q_blk + q_row0 / TC_N) * TC_N + (q_row0 % TC_N) + warp * 32 + lane];
+                const int na = norms[(size_t)(pd.q_blk + q_row0 / TC_N) * TC_N + (q_row0 % TC_N) + warp * 32 + lane] >> 7;      // packed: |a|^2 * 128 + column
                 partial[(size_t)(pd.out_row + row) * splits + sp] =
                     make_int4(best.i0 >= 0 ? na + best.d0 : INT_MAX, best.i0, best.i1 >= 0 ? na + best.d1 : INT_MAX, best.i1);
             }
