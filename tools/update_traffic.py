@@ -1,5 +1,6 @@
 """profiles/traffic.json from an `ncu --set full` capture of the K3 kernels (tools/prof_ba.py): DRAM bytes read + written per launch,
-stamped with a hash of csrc/ so that bench.py refuses a figure that does not belong to the sources it was built from.
+stamped with a hash of the bundle-adjustment sources in csrc/ (the files the K3/K4 kernels are compiled from) so that bench.py refuses a
+figure that does not belong to the sources it was built from.
     python tools/update_traffic.py gpurun_out/r02_ba.ncu-rep cfg3"""
 import csv
 import hashlib
@@ -10,14 +11,14 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BA_SOURCES = ("ba.cu", "ba_math.cuh", "ba_row.cuh", "chol.cuh", "common.cuh")   # what the captured kernels are built from
 
 
 def source_id():
     h = hashlib.sha1()
     d = os.path.join(ROOT, "sfm-toy-library_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    for f in BA_SOURCES:
+        h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
 
