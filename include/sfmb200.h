@@ -228,6 +228,41 @@ enum { SFMB200_MODEL_HOMOGRAPHY = 0, SFMB200_MODEL_ESSENTIAL = 1, SFMB200_MODEL_
 int sfmb200_ransac_score(sfmb200_ctx* ctx, int model, const float* a, const float* b, int n, const double* hyp, int nh, const double* aux9,
                          double threshold, int32_t* inlier_counts, int32_t* best_index, uint8_t* best_mask);
 
+/* ---- f-3 ("next" row of SURVEY.md 8): ORB feature extraction, the step before matching ------------------------ */
+/*
+ * SfM2DFeatureUtilities::extractFeatures (SfMToyLib/SfM2DFeatureUtilities.h:41-42, .cpp:46-51):
+ *     mDetector = ORB::create(5000);                                                         (.cpp:39)
+ *     mDetector->detectAndCompute(image, noArray(), features.keyPoints, features.descriptors);   (.cpp:48)
+ * called once per image by SfM::extractFeatures (SfM.cpp:141-154) on the BGR images cv::imread returned (SfM.cpp:124).
+ * ORB::create's other parameters are OpenCV's defaults (scaleFactor 1.2f, 8 levels, edgeThreshold 31, firstLevel 0, WTA_K 2,
+ * HARRIS_SCORE, patchSize 31, fastThreshold 20).  Output is bit-identical to OpenCV's (cv2 4.13 in this image): the same key points
+ * in the same order with the same pt / size / angle / response / octave, and the same 32-byte descriptors.
+ *   image        8-bit pixels, channels = 1 (grey) or 3 (B,G,R interleaved; converted like cvtColor(COLOR_BGR2GRAY)); row_stride in
+ *                bytes (0 = packed rows).  8 <= width, height <= 65535.  JPEG/PNG decoding stays with the caller (cv::imread).
+ *   keypoints    [max_keypoints] records with the memory layout of cv::KeyPoint (28 bytes), so a shim can copy them straight into a
+ *                std::vector<cv::KeyPoint>; class_id = -1.  KeyPointsToPoints (SfMCommon.cpp:89-94) is the x,y prefix of every record.
+ *   descriptors  [max_keypoints * 32]
+ *   n_keypoints  number of key points found.  OpenCV keeps ties at the selection thresholds, so this can exceed nfeatures; when it
+ *                exceeds max_keypoints only the first max_keypoints records were written -- call again with a larger capacity.
+ * The batch form extracts all images of a run (equal sizes) with shared launches and three host round trips per batch; keypoints /
+ * descriptors / n_keypoints are then [n_images][max_keypoints] / [n_images][max_keypoints * 32] / [n_images].
+ */
+typedef struct sfmb200_keypoint { float x, y, size, angle, response; int32_t octave, class_id; } sfmb200_keypoint;
+int sfmb200_orb_detect_and_compute(sfmb200_ctx* ctx, const uint8_t* image, int width, int height, int channels, size_t row_stride, int nfeatures,
+                                   int max_keypoints, sfmb200_keypoint* keypoints, uint8_t* descriptors, int32_t* n_keypoints);
+int sfmb200_orb_detect_and_compute_batch(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int width, int height, int channels,
+                                         size_t row_stride, int nfeatures, int max_keypoints, sfmb200_keypoint* keypoints,
+                                         uint8_t* descriptors, int32_t* n_keypoints);
+/* Host-side pieces of the stage, exported so that they can be tested without a GPU: the pyramid layout (8 levels: size, scale, key point
+ * quota), the tap table of resize(INTER_LINEAR_EXACT), and KeyPointsFilter::retainBest (returns the number of survivors, their
+ * original indices in OpenCV's output order in `order`; -1 on bad arguments). */
+int sfmb200_orb_layout(int width, int height, int nfeatures, int32_t* level_w, int32_t* level_h, float* level_scale, int32_t* level_quota);
+int sfmb200_orb_linear_exact_taps(int src, int dst, int32_t* i0, int32_t* i1, int32_t* weight);
+int sfmb200_orb_retain_best(const float* response, int n, int n_points, int32_t* order);
+/* Inspection of the last extraction (parity tests): one level of image `image` of the last batch; stage 0 = pyramid, 1 = blurred
+ * pyramid the descriptors sample, 2 = FAST score map.  out [level_w * level_h]. */
+int sfmb200_orb_download_level(sfmb200_ctx* ctx, int stage, int image, int level, uint8_t* out);
+
 /* ---- multi-GPU plumbing (NCCL, one process per GPU) ------------------------------------------------------ */
 #define SFMB200_UNIQUE_ID_BYTES 128
 int sfmb200_comm_unique_id(uint8_t* id /* [SFMB200_UNIQUE_ID_BYTES] */);       /* rank 0, then broadcast by the host */

@@ -205,6 +205,42 @@ class Context:
                                                C.c_double(float(threshold)), _p(counts, C.c_int32), C.byref(best), _p(mask, C.c_uint8) if want_mask else None))
         return counts[:nh], int(best.value), mask[:n]
 
+    # ------------------------------------------------------------------ f-3 ORB extraction
+    def orb_detect_and_compute(self, images, nfeatures=5000, capacity=None):
+        """sfmb200_orb_detect_and_compute[_batch]: `ORB::create(nfeatures)->detectAndCompute` (SfM2DFeatureUtilities.cpp:39, 48).
+        `images`: one uint8 array [h, w] / [h, w, 3] (B,G,R) or a list of equally sized ones.
+        Returns per image (key points [n, 7] float32: x, y, size, angle, response, octave, class_id -- cv::KeyPoint's fields -- and
+        descriptors [n, 32] uint8)."""
+        single = isinstance(images, np.ndarray)
+        imgs = [images] if single else list(images)
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in imgs]
+        if not imgs:
+            return []
+        h, w = imgs[0].shape[:2]; ch = 1 if imgs[0].ndim == 2 else imgs[0].shape[2]
+        if any(im.shape != imgs[0].shape for im in imgs):
+            raise SfmB200Error("batched ORB extraction needs equally sized images")
+        n = len(imgs)
+        cap = int(capacity) if capacity is not None else int(nfeatures) + 64
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        while True:
+            kp = np.zeros((n, max(cap, 1), 7), np.float32); desc = np.zeros((n, max(cap, 1), 32), np.uint8); cnt = np.zeros(n, np.int32)
+            self._check(lib().sfmb200_orb_detect_and_compute_batch(self._h, ptrs, n, int(w), int(h), int(ch), C.c_size_t(0), int(nfeatures), cap,
+                                                                   _p(kp, C.c_float), _p(desc, C.c_uint8), _p(cnt, C.c_int32)))
+            if cnt.max(initial=0) <= cap:
+                break
+            cap = int(cnt.max())                      # ties at a selection threshold: more key points than asked for
+        out = []
+        for i in range(n):
+            k = kp[i, :cnt[i]].copy()
+            k[:, 5:7] = k[:, 5:7].view(np.int32).astype(np.float32)      # octave, class_id are int32 in the record
+            out.append((k, desc[i, :cnt[i]].copy()))
+        return out[0] if single else out
+
+    def orb_download_level(self, stage, image, level, w, h):
+        out = np.zeros((h, w), np.uint8)
+        self._check(lib().sfmb200_orb_download_level(self._h, int(stage), int(image), int(level), _p(out, C.c_uint8)))
+        return out
+
     # ------------------------------------------------------------------ multi-GPU
     def comm_init(self, unique_id, rank, nranks):
         buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
@@ -213,6 +249,31 @@ class Context:
     @property
     def comm_size(self):
         return lib().sfmb200_comm_size(self._h)
+
+
+def orb_layout(width, height, nfeatures=5000):
+    """Pyramid layout of the ORB stage (host-side, no GPU): level widths, heights, scales, key point quotas."""
+    w = np.zeros(8, np.int32); h = np.zeros(8, np.int32); s = np.zeros(8, np.float32); q = np.zeros(8, np.int32)
+    rc = lib().sfmb200_orb_layout(int(width), int(height), int(nfeatures), _p(w, C.c_int32), _p(h, C.c_int32), _p(s, C.c_float), _p(q, C.c_int32))
+    if rc != 0:
+        raise SfmB200Error(f"sfmb200_orb_layout failed ({rc})")
+    return w, h, s, q
+
+
+def orb_linear_exact_taps(src, dst):
+    i0 = np.zeros(dst, np.int32); i1 = np.zeros(dst, np.int32); a = np.zeros(dst, np.int32)
+    rc = lib().sfmb200_orb_linear_exact_taps(int(src), int(dst), _p(i0, C.c_int32), _p(i1, C.c_int32), _p(a, C.c_int32))
+    if rc != 0:
+        raise SfmB200Error(f"sfmb200_orb_linear_exact_taps failed ({rc})")
+    return i0, i1, a
+
+
+def orb_retain_best(response, n_points):
+    r = np.ascontiguousarray(response, np.float32); order = np.zeros(max(len(r), 1), np.int32)
+    n = lib().sfmb200_orb_retain_best(_p(r, C.c_float), len(r), int(n_points), _p(order, C.c_int32))
+    if n < 0:
+        raise SfmB200Error("sfmb200_orb_retain_best: bad arguments")
+    return order[:n].copy()
 
 
 def comm_unique_id():

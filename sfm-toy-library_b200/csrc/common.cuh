@@ -78,6 +78,9 @@ struct MatchCache {
     void release() { desc.release(); exp.release(); entries.clear(); rows_cap = rows_used = 0; blk_cap = blk_used = 0; }
 };
 
+// Device buffers of the last ORB extraction (orb.cu), kept for sfmb200_orb_download_level (stage-by-stage parity tests).
+struct OrbLast { uint8_t *pyr = nullptr, *blur = nullptr, *score = nullptr; int slab = 0, nimg = 0, w = 0, h = 0, nfeatures = 0; };
+
 struct sfmb200_ctx {
     int device = 0;
     int sm_count = 0;
@@ -90,6 +93,11 @@ struct sfmb200_ctx {
     PinBuf pinned;              // per-call pinned staging (results read-back)
     BAWorkspace ba_ws;          // cached bundle-adjustment workspace
     MatchCache mcache;          // descriptor images resident between per-call matchFeatures invocations
+    DevBuf orb_dev, orb_lists;  // ORB extraction: pyramids / score maps / candidates of a batch of images; key point lists
+    PinBuf orb_pin;             // ORB extraction: pinned staging of the three host round trips
+    OrbLast orb_last;
+    cudaStream_t orb_stream = nullptr;            // the Gaussian blur of the pyramid runs beside the detection chain
+    cudaEvent_t orb_ev[2] = {nullptr, nullptr};   // pyramid ready / blur done
     bool tc_attr_set = false;   // cudaFuncSetAttribute(knn2_hamming_tc_kernel, max dynamic smem) done for THIS device
     // peer exchange buffers opened with cudaIpcOpenMemHandle, kept open across problems (the exchange buffer is part of the cached
     // BA workspace, so the one-shot solve sees the same handles on every call): handle bytes -> mapped base
