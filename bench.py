@@ -481,6 +481,13 @@ def run_ours(args):
                 line[key] = st
         except Exception as e:
             line["cfg4_cfg5"] = {"error": repr(e)}
+        # SURVEY.md 8 row f-3, the step before matching: ORB(5000) extraction of the 7 images of cfg 1 (1024 x 768, B,G,R) from HOST buffers,
+        # beside cv2's detectAndCompute on the host cores
+        try:
+            import bench_orb
+            line["f3_orb"] = bench_orb.run(n_images=7, reps=3, cpu=not args.no_cpu_baseline, ctx=ctx)
+        except Exception as e:
+            line["f3_orb"] = {"error": repr(e)}
     # ---- BASELINE configs[1] (cfg 2: 20 cameras / 10 k points / 80 k observations), N = 1: the same step, resident and one-shot
     if rank == 0 and world == 1 and not args.no_stages and args.workload != "cfg2":
         try:

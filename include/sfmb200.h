@@ -262,6 +262,12 @@ int sfmb200_orb_retain_best(const float* response, int n, int n_points, int32_t*
 /* Inspection of the last extraction (parity tests): one level of image `image` of the last batch; stage 0 = pyramid, 1 = blurred
  * pyramid the descriptors sample, 2 = FAST score map.  out [level_w * level_h]. */
 int sfmb200_orb_download_level(sfmb200_ctx* ctx, int stage, int image, int level, uint8_t* out);
+/* Host wall-clock (ms) of the phases of the last extraction call: 0 staging + upload + kernel enqueue, 1 wait for detection,
+ * 2 candidate read-back, 3 first retainBest, 4 Harris round trip, 5 second retainBest, 6 describe round trip, 7 copy-out. */
+int sfmb200_orb_last_timings(const sfmb200_ctx* ctx, double* ms8);
+/* Self-test of the context's host thread pool (csrc/host_pool.h; staging and retainBest tasks of the ORB stage run on it): `rounds`
+ * parallel loops of varying length on `n_threads` threads; returns a checksum >= 0, -1 on bad arguments, -2 on a wrong result. */
+int64_t sfmb200_host_pool_selftest(int n_threads, int rounds, int max_tasks);
 
 /* ---- multi-GPU plumbing (NCCL, one process per GPU) ------------------------------------------------------ */
 #define SFMB200_UNIQUE_ID_BYTES 128

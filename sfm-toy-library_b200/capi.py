@@ -236,6 +236,13 @@ class Context:
             out.append((k, desc[i, :cnt[i]].copy()))
         return out[0] if single else out
 
+    def orb_last_timings(self):
+        """Host wall-clock (ms) of the phases of the last ORB call (sfmb200_orb_last_timings)."""
+        ms = np.zeros(8)
+        self._check(lib().sfmb200_orb_last_timings(self._h, _p(ms, C.c_double)))
+        names = ("stage_upload_enqueue", "wait_detect", "candidates_d2h", "select_fast", "harris_roundtrip", "select_harris", "describe_roundtrip", "copy_out")
+        return dict(zip(names, ms.tolist()))
+
     def orb_download_level(self, stage, image, level, w, h):
         out = np.zeros((h, w), np.uint8)
         self._check(lib().sfmb200_orb_download_level(self._h, int(stage), int(image), int(level), _p(out, C.c_uint8)))

@@ -12,6 +12,7 @@
 #include <utility>
 
 #include "../../include/sfmb200.h"
+#include "host_pool.h"
 
 // One growable device buffer + one pinned host buffer per purpose, reused across calls (cudaMalloc/cudaFree are
 // milliseconds; the reference calls each stage many times per runSfM()).
@@ -94,7 +95,9 @@ struct sfmb200_ctx {
     BAWorkspace ba_ws;          // cached bundle-adjustment workspace
     MatchCache mcache;          // descriptor images resident between per-call matchFeatures invocations
     DevBuf orb_dev, orb_lists;  // ORB extraction: pyramids / score maps / candidates of a batch of images; key point lists
-    PinBuf orb_pin;             // ORB extraction: pinned staging of the three host round trips
+    PinBuf orb_pin_img, orb_pin_a, orb_pin_b, orb_pin_c;   // ORB extraction: pinned image staging / staging of the three host round trips
+    double orb_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // host wall-clock of the phases of the last extraction (sfmb200_orb_last_timings)
+    HostPool* pool = nullptr;   // host threads for the work that stays on the CPU (created on first use)
     OrbLast orb_last;
     cudaStream_t orb_stream = nullptr;            // the Gaussian blur of the pyramid runs beside the detection chain
     cudaEvent_t orb_ev[2] = {nullptr, nullptr};   // pyramid ready / blur done

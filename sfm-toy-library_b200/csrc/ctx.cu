@@ -46,7 +46,9 @@ void sfmb200_destroy(sfmb200_ctx* ctx) {
     for (auto& e : ctx->ipc_cache) if (e.second) cudaIpcCloseMemHandle(e.second);
     ctx->ipc_cache.clear();
     sfmb200_comm_destroy(ctx);
-    ctx->orb_dev.release(); ctx->orb_lists.release(); ctx->orb_pin.release();
+    ctx->orb_dev.release(); ctx->orb_lists.release();
+    ctx->orb_pin_img.release(); ctx->orb_pin_a.release(); ctx->orb_pin_b.release(); ctx->orb_pin_c.release();
+    delete ctx->pool; ctx->pool = nullptr;
     if (ctx->orb_stream) cudaStreamDestroy(ctx->orb_stream);
     for (auto& ev : ctx->orb_ev) if (ev) cudaEventDestroy(ev);
     ctx->scratch.release(); ctx->scratch2.release(); ctx->pinned.release(); ctx->ba_ws.release(); ctx->mcache.release();

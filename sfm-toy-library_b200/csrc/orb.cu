@@ -16,6 +16,8 @@
 //
 // Integer / byte work, HBM- and latency-bound (2.6 MB of pyramid per 1024x768 image): no tensor cores involved.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 
 #include "common.cuh"
 #include "orb_math.cuh"
@@ -27,14 +29,14 @@ namespace {
 constexpr int ORB_LEVELS = 8;
 constexpr int ORB_EDGE = 31;          // edgeThreshold
 constexpr int ORB_FAST_T = 20;        // fastThreshold
-constexpr int CHUNK = 256;            // pixels of one row handled by one CTA of the row-chunk kernels
+constexpr int CHUNK = 32;             // pixels per survivor-mask word
 
 struct OrbLevel { int w, h, off, row0; float scale, inv_scale; int quota, pad; };
 struct OrbLayout {
     OrbLevel lv[ORB_LEVELS];
     int total_rows;      // rows of all levels
     int slab;            // bytes of one image's pyramid (levels back to back, each 16-byte aligned)
-    int chunks;          // CTAs per row = ceil(level-0 width / CHUNK)
+    int chunks;          // survivor-mask words per row = ceil(level-0 width / 32), the same stride for every level
     int ncnt;            // total_rows * chunks
 };
 
@@ -93,13 +95,6 @@ void retain_best(std::vector<Rec>& k, int n_points) {
 }
 
 // ---------------------------------------------------------------------------------------------------- kernels
-__device__ __forceinline__ int level_of_row(const OrbLayout& L, int row) {
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < ORB_LEVELS; i++) l += (row >= L.lv[i].row0 && L.lv[i].h > 0) ? 1 : 0;   // levels are non-increasing, empty ones at the end
-    return l;
-}
-
 __global__ void __launch_bounds__(256) orb_gray_kernel(const uint8_t* __restrict__ raw, size_t raw_stride_img, int row_stride, int w, int h,
                                                         uint8_t* __restrict__ pyr, int slab) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
@@ -120,57 +115,67 @@ __global__ void __launch_bounds__(256) orb_resize_kernel(uint8_t* pyr, int slab,
     pyr[(size_t)img * slab + dst_off + (size_t)y * dw + x] = (uint8_t)v;
 }
 
-// FAST-9/16 score of every pyramid pixel (0 = no corner).  grid = (chunks, total_rows, images).
-__global__ void __launch_bounds__(CHUNK) orb_fast_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, OrbLayout L) {
-    const int row = blockIdx.y, img = blockIdx.z;
-    const int l = level_of_row(L, row);
-    const int w = L.lv[l].w, h = L.lv[l].h, y = row - L.lv[l].row0, x = blockIdx.x * CHUNK + threadIdx.x;
-    if (x >= w) return;
-    const size_t base = (size_t)img * L.slab + L.lv[l].off;
-    int s = 0;
-    if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
-        const uint8_t* c = pyr + base + (size_t)y * w + x;
-        const int v = c[0];
-        int p[16];
-        p[0] = c[3 * w];          p[1] = c[3 * w + 1];   p[2] = c[2 * w + 2];   p[3] = c[w + 3];
-        p[4] = c[3];              p[5] = c[-w + 3];      p[6] = c[-2 * w + 2];  p[7] = c[-3 * w + 1];
-        p[8] = c[-3 * w];         p[9] = c[-3 * w - 1];  p[10] = c[-2 * w - 2]; p[11] = c[-w - 3];
-        p[12] = c[-3];            p[13] = c[w - 3];      p[14] = c[2 * w - 2];  p[15] = c[3 * w - 1];
-        s = orbm::fast9_score(v, p, ORB_FAST_T);
+// FAST-9/16 score of one pixel of a level (0 = no corner, also within 3 pixels of the level's border)
+__device__ __forceinline__ int fast_at(const uint8_t* __restrict__ I, int w, int h, int x, int y) {
+    if (x < 3 || x >= w - 3 || y < 3 || y >= h - 3) return 0;
+    const uint8_t* c = I + (size_t)y * w + x;
+    const int v = c[0];
+    int p[16];
+    p[0] = c[3 * w]; p[4] = c[3]; p[8] = c[-3 * w]; p[12] = c[-3];
+    if (!orbm::fast9_may_be_corner(v, p[0], p[4], p[8], p[12], ORB_FAST_T)) return 0;
+    p[1] = c[3 * w + 1];   p[2] = c[2 * w + 2];   p[3] = c[w + 3];
+    p[5] = c[-w + 3];      p[6] = c[-2 * w + 2];  p[7] = c[-3 * w + 1];
+    p[9] = c[-3 * w - 1];  p[10] = c[-2 * w - 2]; p[11] = c[-w - 3];
+    p[13] = c[w - 3];      p[14] = c[2 * w - 2];  p[15] = c[3 * w - 1];
+    return orbm::fast9_score(v, p, ORB_FAST_T);
+}
+
+// FAST scores of a 32 x 8 tile (+1 halo) in shared memory -> score map; 3x3 non-maximum suppression (fast.cpp: strictly greater than the 8
+// neighbours) + KeyPointsFilter::runByImageBorder(edgeThreshold) -> one 32-bit survivor mask per (row, 32-pixel word).
+// grid = (words per row of level 0, tile rows of all levels, images), block = (32, 8).
+constexpr int FT_W = 32, FT_H = 8;
+__global__ void __launch_bounds__(FT_W * FT_H) orb_fast_nms_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, uint32_t* __restrict__ mask,
+                                                                    OrbLayout L, const int32_t* __restrict__ tile_lvl, const int32_t* __restrict__ tile_y0) {
+    __shared__ uint8_t sc[FT_H + 2][FT_W + 2 + 2];
+    const int l = tile_lvl[blockIdx.y], y0 = tile_y0[blockIdx.y], x0 = blockIdx.x * FT_W, img = blockIdx.z;
+    const int w = L.lv[l].w, h = L.lv[l].h;
+    if (x0 >= w) {                                   // words beyond this level's width: the row scan adds all `chunks` words of a row
+        if (threadIdx.x == 0 && y0 + (int)threadIdx.y < h) mask[(size_t)img * L.ncnt + (size_t)(L.lv[l].row0 + y0 + threadIdx.y) * L.chunks + blockIdx.x] = 0u;
+        return;
     }
-    score[base + (size_t)y * w + x] = (uint8_t)s;
+    const uint8_t* I = pyr + (size_t)img * L.slab + L.lv[l].off;
+    const int tid = threadIdx.y * FT_W + threadIdx.x;
+    for (int t = tid; t < (FT_W + 2) * (FT_H + 2); t += FT_W * FT_H) {
+        const int tx = t % (FT_W + 2), ty = t / (FT_W + 2);
+        sc[ty][tx] = (uint8_t)fast_at(I, w, h, x0 - 1 + tx, y0 - 1 + ty);
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int s = sc[threadIdx.y + 1][threadIdx.x + 1];
+    bool keep = false;
+    if (x < w && y < h) {
+        score[(size_t)img * L.slab + L.lv[l].off + (size_t)y * w + x] = (uint8_t)s;
+        if (s && x >= ORB_EDGE && x < w - ORB_EDGE && y >= ORB_EDGE && y < h - ORB_EDGE) {
+            const uint8_t* r0 = &sc[threadIdx.y][threadIdx.x]; const uint8_t* r1 = r0 + (FT_W + 4); const uint8_t* r2 = r1 + (FT_W + 4);
+            keep = s > r0[0] && s > r0[1] && s > r0[2] && s > r1[0] && s > r1[2] && s > r2[0] && s > r2[1] && s > r2[2];
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (threadIdx.x == 0 && y < h) mask[(size_t)img * L.ncnt + (size_t)(L.lv[l].row0 + y) * L.chunks + blockIdx.x] = m;
 }
 
-// fast.cpp non-maximum suppression (strictly greater than the 8 neighbours) + KeyPointsFilter::runByImageBorder(edgeThreshold)
-__device__ __forceinline__ int nms_keep(const uint8_t* __restrict__ sc, int w, int h, int x, int y) {
-    if (x < ORB_EDGE || x >= w - ORB_EDGE || y < ORB_EDGE || y >= h - ORB_EDGE) return 0;     // the border filter implies 1 <= x < w-1, ...
-    const uint8_t* c = sc + (size_t)y * w + x;
-    const int s = c[0];
-    if (s == 0) return 0;
-    return (s > c[-1] && s > c[1] && s > c[-w - 1] && s > c[-w] && s > c[-w + 1] && s > c[w - 1] && s > c[w] && s > c[w + 1]) ? s : 0;
-}
-
-// pass 1: survivors per (row, chunk).  grid = (chunks, total_rows, images)
-__global__ void __launch_bounds__(CHUNK) orb_nms_count_kernel(const uint8_t* __restrict__ score, OrbLayout L, int32_t* __restrict__ cnt) {
-    const int row = blockIdx.y, img = blockIdx.z;
-    const int l = level_of_row(L, row);
-    const int w = L.lv[l].w, h = L.lv[l].h, y = row - L.lv[l].row0, x = blockIdx.x * CHUNK + threadIdx.x;
-    const int keep = (x < w) ? (nms_keep(score + (size_t)img * L.slab + L.lv[l].off, w, h, x, y) != 0) : 0;
-    const int n = __syncthreads_count(keep);
-    if (threadIdx.x == 0) cnt[(size_t)img * L.ncnt + (size_t)row * L.chunks + blockIdx.x] = n;
-}
-
-// pass 2: exclusive scan of the counts of one image (one CTA per image); also the start of every level and the total.
-__global__ void __launch_bounds__(1024) orb_scan_kernel(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int32_t* __restrict__ lvl_start, OrbLayout L) {
+// Survivors per pyramid row -> exclusive scan over the rows of one image (one CTA per image); start of every level and the total.
+__global__ void __launch_bounds__(1024) orb_scan_kernel(const uint32_t* __restrict__ mask, int32_t* __restrict__ row_off, int32_t* __restrict__ lvl_start, OrbLayout L) {
     __shared__ int warp_sum[32];
     __shared__ int carry;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int32_t* c = cnt + (size_t)img * L.ncnt; int32_t* o = off + (size_t)img * L.ncnt;
+    const uint32_t* mk = mask + (size_t)img * L.ncnt; int32_t* o = row_off + (size_t)img * (L.total_rows + 1);
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < L.ncnt; base += 1024) {
-        const int i = base + tid;
-        const int v = i < L.ncnt ? c[i] : 0;
+    for (int base = 0; base < L.total_rows; base += 1024) {
+        const int r = base + tid;
+        int v = 0;
+        if (r < L.total_rows) for (int j = 0; j < L.chunks; j++) v += __popc(mk[(size_t)r * L.chunks + j]);
         int s = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += t; }
@@ -184,30 +189,44 @@ __global__ void __launch_bounds__(1024) orb_scan_kernel(const int32_t* __restric
         }
         __syncthreads();
         const int before = carry + (wid ? warp_sum[wid - 1] : 0) + s - v;
-        if (i < L.ncnt) o[i] = before;
+        if (r < L.total_rows) o[r] = before;
         __syncthreads();
         if (tid == 1023) carry = before + v;
         __syncthreads();
     }
-    if (tid < ORB_LEVELS) lvl_start[img * 16 + tid] = (L.lv[tid].h > 0 && L.lv[tid].row0 * L.chunks < L.ncnt) ? o[(size_t)L.lv[tid].row0 * L.chunks] : carry;
-    if (tid == ORB_LEVELS) lvl_start[img * 16 + ORB_LEVELS] = carry;
+    if (tid == 0) o[L.total_rows] = carry;
+    __syncthreads();
+    if (tid <= ORB_LEVELS) lvl_start[img * 16 + tid] = (tid < ORB_LEVELS && L.lv[tid].h > 0) ? o[L.lv[tid].row0] : carry;
 }
 
-// pass 3: ordered scatter -> candidates (x | y << 16, score) in raster order per level, levels back to back.
-__global__ void __launch_bounds__(CHUNK) orb_nms_scatter_kernel(const uint8_t* __restrict__ score, OrbLayout L, const int32_t* __restrict__ off,
-                                                                 uint2* __restrict__ cand, int cand_cap) {
-    __shared__ int warp_cnt[CHUNK / 32];
-    const int row = blockIdx.y, img = blockIdx.z, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int l = level_of_row(L, row);
-    const int w = L.lv[l].w, h = L.lv[l].h, y = row - L.lv[l].row0, x = blockIdx.x * CHUNK + threadIdx.x;
-    const int s = (x < w) ? nms_keep(score + (size_t)img * L.slab + L.lv[l].off, w, h, x, y) : 0;
-    const unsigned m = __ballot_sync(0xffffffffu, s != 0);
-    if (lane == 0) warp_cnt[wid] = __popc(m);
-    __syncthreads();
-    if (s) {
-        int pos = off[(size_t)img * L.ncnt + (size_t)row * L.chunks + blockIdx.x] + __popc(m & ((1u << lane) - 1u));
-        for (int i = 0; i < wid; i++) pos += warp_cnt[i];
-        if (pos < cand_cap) cand[(size_t)img * cand_cap + pos] = make_uint2((unsigned)x | ((unsigned)y << 16), (unsigned)s | ((unsigned)l << 16));
+// Ordered scatter: one warp per pyramid row -> candidates (x | y << 16, score | level << 16), raster order inside a level (the order cv::FAST
+// emits), levels back to back.
+__global__ void __launch_bounds__(256) orb_scatter_kernel(const uint32_t* __restrict__ mask, const uint8_t* __restrict__ score, const int32_t* __restrict__ row_off,
+                                                           OrbLayout L, uint2* __restrict__ cand, int cand_cap) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, img = blockIdx.z;
+    if (row >= L.total_rows) return;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ORB_LEVELS; i++) l += (L.lv[i].h > 0 && row >= L.lv[i].row0) ? 1 : 0;
+    const int w = L.lv[l].w, y = row - L.lv[l].row0;
+    const uint8_t* sc = score + (size_t)img * L.slab + L.lv[l].off + (size_t)y * w;
+    int pos = row_off[(size_t)img * (L.total_rows + 1) + row];
+    uint2* out = cand + (size_t)img * cand_cap;
+    for (int j0 = 0; j0 < L.chunks; j0 += 32) {
+        const int j = j0 + lane;
+        unsigned m = j < L.chunks ? mask[(size_t)img * L.ncnt + (size_t)row * L.chunks + j] : 0u;
+        const int c = __popc(m);
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        int at = pos + incl - c;
+        while (m) {
+            const int bit = __ffs(m) - 1; m &= m - 1;
+            const int x = j * 32 + bit;
+            if (at < cand_cap) out[at] = make_uint2((unsigned)x | ((unsigned)y << 16), (unsigned)sc[x] | ((unsigned)l << 16));
+            at++;
+        }
+        pos += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -331,7 +350,8 @@ struct OrbPlan {
     OrbLayout L;
     std::vector<int32_t> taps;        // per level l >= 1: x taps (3 * w_l) then y taps (3 * h_l)
     int taps_off[ORB_LEVELS];
-    std::vector<int32_t> tile_lvl, tile_y0;   // blur kernel: level and first row of every tile row
+    std::vector<int32_t> blur_lvl, blur_y0;   // blur kernel: level and first row of every tile row (BT_H rows)
+    std::vector<int32_t> fast_lvl, fast_y0;   // FAST kernel: the same for FT_H rows
 };
 
 void make_plan(int w, int h, int nfeatures, OrbPlan& P) {
@@ -349,55 +369,78 @@ void make_plan(int w, int h, int nfeatures, OrbPlan& P) {
         t += 3 * d.w;
         linear_exact_taps(s.h, d.h, t, t + d.h, t + 2 * d.h);
     }
-    P.tile_lvl.clear(); P.tile_y0.clear();
-    for (int l = 0; l < ORB_LEVELS; l++)
-        for (int y = 0; y < P.L.lv[l].h; y += BT_H) { P.tile_lvl.push_back(l); P.tile_y0.push_back(y); }
+    P.blur_lvl.clear(); P.blur_y0.clear(); P.fast_lvl.clear(); P.fast_y0.clear();
+    for (int l = 0; l < ORB_LEVELS; l++) {
+        for (int y = 0; y < P.L.lv[l].h; y += BT_H) { P.blur_lvl.push_back(l); P.blur_y0.push_back(y); }
+        for (int y = 0; y < P.L.lv[l].h; y += FT_H) { P.fast_lvl.push_back(l); P.fast_y0.push_back(y); }
+    }
 }
+
+inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w, int h, int channels, size_t row_stride, int nfeatures,
             int cap, KeyPointOut* kp_out, uint8_t* desc_out, int32_t* n_out) {
     OrbPlan P;
     make_plan(w, h, nfeatures, P);
     const OrbLayout& L = P.L;
-    if (L.total_rows > 65535) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "image too tall for one launch (%d pyramid rows)", L.total_rows);
+    if (L.total_rows > 65535 * FT_H) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "image too tall for one launch (%d pyramid rows)", L.total_rows);
     cudaStream_t st = ctx->stream;
     if (!ctx->orb_stream) {
         SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->orb_stream, cudaStreamNonBlocking));
         for (auto& ev : ctx->orb_ev) SFM_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
-    const size_t raw_img = channels == 3 ? (size_t)3 * w * h : 0;
+    if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads() - 1);
+    HostPool& pool = *ctx->pool;
+    double* tm = ctx->orb_ms;
+    for (int i = 0; i < 8; i++) tm[i] = 0.0;
+
+    const size_t img_bytes = (size_t)w * h * channels;
+    const size_t raw_img = channels == 3 ? img_bytes : 0;
     const int cand_cap = L.slab / 4 + 64;                    // 3x3 non-maximum suppression keeps at most one pixel of every 2x2 block
-    const size_t per_img = Carver::pad(raw_img) + 3 * Carver::pad(L.slab) + 2 * Carver::pad(4 * (size_t)L.ncnt) + Carver::pad(64) +
-                           Carver::pad(8 * (size_t)cand_cap);
-    const int slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_images, ((size_t)3 << 30) / per_img));
-    const size_t fixed = Carver::pad(4 * P.taps.size() + 16) + 2 * Carver::pad(4 * P.tile_lvl.size() + 16) + 4096;
-    SFM_CUDA(ctx, ctx->orb_dev.reserve(fixed + per_img * slots));
+    const size_t per_img = Carver::pad(raw_img) + 3 * Carver::pad(L.slab) + Carver::pad(4 * (size_t)L.ncnt) + Carver::pad(4 * (size_t)(L.total_rows + 1)) +
+                           Carver::pad(64) + Carver::pad(8 * (size_t)cand_cap);
+    // a batch = as many images as 2 GB of device scratch and 96 MB of pinned staging hold
+    const int slots = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n_images, ((size_t)2 << 30) / per_img, ((size_t)96 << 20) / img_bytes}));
+    const size_t fixed = Carver::pad(4 * P.taps.size() + 16) + 4 * Carver::pad(4 * P.fast_lvl.size() + 16) + 4096;
+    SFM_CUDA(ctx, ctx->orb_dev.reserve(fixed + per_img * slots + (size_t)slots * 2048));
     Carver cv(ctx->orb_dev.p);
     int32_t* d_taps = cv.take<int32_t>(P.taps.size() + 4);
-    int32_t* d_tile_lvl = cv.take<int32_t>(P.tile_lvl.size() + 4); int32_t* d_tile_y0 = cv.take<int32_t>(P.tile_y0.size() + 4);
+    int32_t* d_blur_lvl = cv.take<int32_t>(P.blur_lvl.size() + 4); int32_t* d_blur_y0 = cv.take<int32_t>(P.blur_y0.size() + 4);
+    int32_t* d_fast_lvl = cv.take<int32_t>(P.fast_lvl.size() + 4); int32_t* d_fast_y0 = cv.take<int32_t>(P.fast_y0.size() + 4);
     uint8_t* d_raw = cv.take<uint8_t>(raw_img * slots);
     uint8_t* d_pyr = cv.take<uint8_t>((size_t)L.slab * slots); uint8_t* d_blur = cv.take<uint8_t>((size_t)L.slab * slots);
     uint8_t* d_score = cv.take<uint8_t>((size_t)L.slab * slots);
-    int32_t* d_cnt = cv.take<int32_t>((size_t)L.ncnt * slots); int32_t* d_off = cv.take<int32_t>((size_t)L.ncnt * slots);
+    uint32_t* d_mask = cv.take<uint32_t>((size_t)L.ncnt * slots); int32_t* d_rowoff = cv.take<int32_t>((size_t)(L.total_rows + 1) * slots);
     int32_t* d_lvl = cv.take<int32_t>(16 * (size_t)slots);
     uint2* d_cand = cv.take<uint2>((size_t)cand_cap * slots);
     ctx->orb_last = OrbLast{d_pyr, d_blur, d_score, L.slab, 0, w, h, nfeatures};
     if (!P.taps.empty()) SFM_CUDA(ctx, cudaMemcpyAsync(d_taps, P.taps.data(), 4 * P.taps.size(), cudaMemcpyHostToDevice, st));
-    SFM_CUDA(ctx, cudaMemcpyAsync(d_tile_lvl, P.tile_lvl.data(), 4 * P.tile_lvl.size(), cudaMemcpyHostToDevice, st));
-    SFM_CUDA(ctx, cudaMemcpyAsync(d_tile_y0, P.tile_y0.data(), 4 * P.tile_y0.size(), cudaMemcpyHostToDevice, st));
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_blur_lvl, P.blur_lvl.data(), 4 * P.blur_lvl.size(), cudaMemcpyHostToDevice, st));
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_blur_y0, P.blur_y0.data(), 4 * P.blur_y0.size(), cudaMemcpyHostToDevice, st));
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_fast_lvl, P.fast_lvl.data(), 4 * P.fast_lvl.size(), cudaMemcpyHostToDevice, st));
+    SFM_CUDA(ctx, cudaMemcpyAsync(d_fast_y0, P.fast_y0.data(), 4 * P.fast_y0.size(), cudaMemcpyHostToDevice, st));
+    SFM_CUDA(ctx, ctx->orb_pin_img.reserve(img_bytes * slots + 256));
+    uint8_t* h_img = (uint8_t*)ctx->orb_pin_img.p;
 
-    std::vector<Rec> recs;
-    std::vector<uint2> sel;                 // records handed to the Harris / describe kernels
-    std::vector<int> seg;                   // per (slot, level): number of records
+    std::vector<std::vector<Rec>> task((size_t)slots * ORB_LEVELS);
+    std::atomic<int> task_err{0};
     for (int i0 = 0; i0 < n_images; i0 += slots) {
         const int nb = std::min(slots, n_images - i0);
-        // ---- upload, grey, pyramid, FAST, ordered compaction, blur: one stream, no host involvement
-        for (int s = 0; s < nb; s++) {
-            if (channels == 1)
-                SFM_CUDA(ctx, cudaMemcpy2DAsync(d_pyr + (size_t)s * L.slab, w, images[i0 + s], row_stride, w, h, cudaMemcpyHostToDevice, st));
-            else
-                SFM_CUDA(ctx, cudaMemcpy2DAsync(d_raw + (size_t)s * raw_img, (size_t)3 * w, images[i0 + s], row_stride, (size_t)3 * w, h, cudaMemcpyHostToDevice, st));
-        }
+        double t0 = now_ms();
+        // ---- staging: every pool thread packs one image into pinned memory and sends it off itself, so the DMA of the first images
+        //      overlaps the packing of the later ones (a pageable cudaMemcpy would do both serially on one thread)
+        const int dev = ctx->device;
+        pool.parallel_for(nb, [&](int s) {
+            cudaSetDevice(dev);
+            uint8_t* dst = h_img + (size_t)s * img_bytes; const uint8_t* src = images[i0 + s];
+            const size_t rb = (size_t)w * channels;
+            if (row_stride == rb) memcpy(dst, src, img_bytes);
+            else for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * rb, src + (size_t)y * row_stride, rb);
+            uint8_t* d = channels == 1 ? d_pyr + (size_t)s * L.slab : d_raw + (size_t)s * raw_img;
+            if (cudaMemcpyAsync(d, dst, img_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) task_err.store(1);
+        });
+        if (task_err.load()) return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        // ---- grey, pyramid, blur (second stream), FAST + suppression, ordered compaction: no host involvement
         if (channels == 3) {
             orb_gray_kernel<<<dim3(ceil_div(w, 256), h, nb), 256, 0, st>>>(d_raw, raw_img, 3 * w, w, h, d_pyr, L.slab);
             SFM_LAUNCH_CHECK(ctx);
@@ -408,109 +451,118 @@ int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w,
             orb_resize_kernel<<<dim3(ceil_div(d.w, 256), d.h, nb), 256, 0, st>>>(d_pyr, L.slab, s.off, s.w, d.off, d.w, d.h, d_taps + P.taps_off[l]);
             SFM_LAUNCH_CHECK(ctx);
         }
-        // the blur only needs the pyramid: second stream, joined again before the descriptors
         SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[0], st));
         SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->orb_stream, ctx->orb_ev[0], 0));
-        orb_blur_kernel<<<dim3(ceil_div(w, BT_W), (unsigned)P.tile_lvl.size(), nb), 256, 0, ctx->orb_stream>>>(d_pyr, d_blur, L, d_tile_lvl, d_tile_y0);
+        orb_blur_kernel<<<dim3(ceil_div(w, BT_W), (unsigned)P.blur_lvl.size(), nb), 256, 0, ctx->orb_stream>>>(d_pyr, d_blur, L, d_blur_lvl, d_blur_y0);
         SFM_LAUNCH_CHECK(ctx);
         SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[1], ctx->orb_stream));
-        const dim3 grid_rows(L.chunks, L.total_rows, nb);
-        orb_fast_kernel<<<grid_rows, CHUNK, 0, st>>>(d_pyr, d_score, L); SFM_LAUNCH_CHECK(ctx);
-        orb_nms_count_kernel<<<grid_rows, CHUNK, 0, st>>>(d_score, L, d_cnt); SFM_LAUNCH_CHECK(ctx);
-        orb_scan_kernel<<<nb, 1024, 0, st>>>(d_cnt, d_off, d_lvl, L); SFM_LAUNCH_CHECK(ctx);
-        orb_nms_scatter_kernel<<<grid_rows, CHUNK, 0, st>>>(d_score, L, d_off, d_cand, cand_cap); SFM_LAUNCH_CHECK(ctx);
-        SFM_CUDA(ctx, ctx->orb_pin.reserve(64 * (size_t)nb + 64));
-        int32_t* h_lvl = (int32_t*)ctx->orb_pin.p;
+        orb_fast_nms_kernel<<<dim3(L.chunks, (unsigned)P.fast_lvl.size(), nb), dim3(FT_W, FT_H), 0, st>>>(d_pyr, d_score, d_mask, L, d_fast_lvl, d_fast_y0);
+        SFM_LAUNCH_CHECK(ctx);
+        orb_scan_kernel<<<nb, 1024, 0, st>>>(d_mask, d_rowoff, d_lvl, L); SFM_LAUNCH_CHECK(ctx);
+        orb_scatter_kernel<<<dim3(ceil_div(L.total_rows * 32, 256), 1, nb), 256, 0, st>>>(d_mask, d_score, d_rowoff, L, d_cand, cand_cap);
+        SFM_LAUNCH_CHECK(ctx);
+        SFM_CUDA(ctx, ctx->orb_pin_a.reserve(64 * (size_t)nb + 64));
+        int32_t* h_lvl = (int32_t*)ctx->orb_pin_a.p;
         SFM_CUDA(ctx, cudaMemcpyAsync(h_lvl, d_lvl, 64 * (size_t)nb, cudaMemcpyDeviceToHost, st));
+        double t1 = now_ms(); tm[0] += t1 - t0;
         SFM_CUDA(ctx, cudaStreamSynchronize(st));
         ctx->orb_last.nimg = nb;
+        double t2 = now_ms(); tm[1] += t2 - t1;
         // ---- round trip 1: candidates of every image (raster order per level)
-        std::vector<int32_t> lvl(h_lvl, h_lvl + 16 * (size_t)nb);      // the pinned buffer is re-carved below
-        size_t total_cand = 0;
+        std::vector<int32_t> lvl(h_lvl, h_lvl + 16 * (size_t)nb);
+        std::vector<size_t> cand_at(nb + 1, 0);
         for (int s = 0; s < nb; s++) {
             if (lvl[16 * s + ORB_LEVELS] > cand_cap) return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "candidate buffer overflow (internal)");
-            total_cand += lvl[16 * s + ORB_LEVELS];
+            cand_at[s + 1] = cand_at[s] + lvl[16 * s + ORB_LEVELS];
         }
-        SFM_CUDA(ctx, ctx->orb_pin.reserve(8 * total_cand + 4 * total_cand + 64 + (size_t)nb * 64));
-        uint2* h_cand = (uint2*)ctx->orb_pin.p;
-        {
-            size_t at = 0;
-            for (int s = 0; s < nb; s++) {
-                const int n = lvl[16 * s + ORB_LEVELS];
-                if (n) SFM_CUDA(ctx, cudaMemcpyAsync(h_cand + at, d_cand + (size_t)s * cand_cap, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
-                at += n;
-            }
-            SFM_CUDA(ctx, cudaStreamSynchronize(st));
+        const size_t total_cand = cand_at[nb];
+        SFM_CUDA(ctx, ctx->orb_pin_b.reserve(8 * total_cand + 64));
+        uint2* h_cand = (uint2*)ctx->orb_pin_b.p;
+        for (int s = 0; s < nb; s++) {
+            const size_t n = cand_at[s + 1] - cand_at[s];
+            if (n) SFM_CUDA(ctx, cudaMemcpyAsync(h_cand + cand_at[s], d_cand + (size_t)s * cand_cap, 8 * n, cudaMemcpyDeviceToHost, st));
         }
-        // ---- first selection: best 2 * quota FAST scores per level (KeyPointsFilter::retainBest keeps ties)
-        sel.clear(); seg.assign((size_t)nb * ORB_LEVELS, 0);
-        {
-            size_t at = 0;
-            for (int s = 0; s < nb; s++) {
-                for (int l = 0; l < ORB_LEVELS; l++) {
-                    const int b = lvl[16 * s + l], e = lvl[16 * s + l + 1];
-                    recs.resize(e - b);
-                    for (int k = b; k < e; k++) recs[k - b] = Rec{(float)(h_cand[at + k].y & 0xFFFF), k};
-                    retain_best(recs, 2 * L.lv[l].quota);
-                    for (const Rec& r : recs) sel.push_back(make_uint2(h_cand[at + r.idx].x, (unsigned)l | ((unsigned)s << 8)));
-                    seg[(size_t)s * ORB_LEVELS + l] = (int)recs.size();
-                }
-                at += lvl[16 * s + ORB_LEVELS];
-            }
-        }
-        const size_t nsel = sel.size();
+        SFM_CUDA(ctx, cudaStreamSynchronize(st));
+        double t3 = now_ms(); tm[2] += t3 - t2;
+        // ---- first selection: best 2 * quota FAST scores per (image, level); KeyPointsFilter::retainBest keeps ties
+        pool.parallel_for(nb * ORB_LEVELS, [&](int t) {
+            const int s = t / ORB_LEVELS, l = t % ORB_LEVELS;
+            const int b = lvl[16 * s + l], e = lvl[16 * s + l + 1];
+            std::vector<Rec>& r = task[t];
+            r.resize(e - b);
+            const uint2* c = h_cand + cand_at[s];
+            for (int k = b; k < e; k++) r[k - b] = Rec{(float)(c[k].y & 0xFFFF), k};
+            retain_best(r, 2 * L.lv[l].quota);
+        });
+        std::vector<size_t> sel_at((size_t)nb * ORB_LEVELS + 1, 0);
+        for (int t = 0; t < nb * ORB_LEVELS; t++) sel_at[t + 1] = sel_at[t] + task[t].size();
+        const size_t nsel = sel_at[(size_t)nb * ORB_LEVELS];
+        SFM_CUDA(ctx, ctx->orb_pin_c.reserve(Carver::pad(8 * nsel + 16) * 2 + Carver::pad(4 * nsel + 16) * 2 + 1024));
+        Carver pc(ctx->orb_pin_c.p);
+        uint2* h_sel = pc.take<uint2>(nsel + 2); float* h_resp = pc.take<float>(nsel + 4);
+        uint2* h_fin = pc.take<uint2>(nsel + 2); float* h_fresp = pc.take<float>(nsel + 4);
+        pool.parallel_for(nb * ORB_LEVELS, [&](int t) {
+            const int s = t / ORB_LEVELS, l = t % ORB_LEVELS;
+            const uint2* c = h_cand + cand_at[s];
+            uint2* o = h_sel + sel_at[t];
+            for (const Rec& r : task[t]) *o++ = make_uint2(c[r.idx].x, (unsigned)l | ((unsigned)s << 8));
+        });
         SFM_CUDA(ctx, ctx->orb_lists.reserve(Carver::pad(8 * nsel + 16) * 2 + Carver::pad(4 * nsel + 16) * 2 + Carver::pad(28 * nsel + 32) + Carver::pad(32 * nsel + 32) + 4096));
         Carver lc(ctx->orb_lists.p);
         uint2* d_sel = lc.take<uint2>(nsel + 2); float* d_resp = lc.take<float>(nsel + 4);
         uint2* d_fin = lc.take<uint2>(nsel + 2); float* d_fresp = lc.take<float>(nsel + 4);
         KeyPointOut* d_kp = lc.take<KeyPointOut>(nsel + 1); uint8_t* d_desc = lc.take<uint8_t>(32 * nsel + 32);
-        std::vector<float> resp(nsel);
+        double t4 = now_ms(); tm[3] += t4 - t3;
         if (nsel) {
-            SFM_CUDA(ctx, cudaMemcpyAsync(d_sel, sel.data(), 8 * nsel, cudaMemcpyHostToDevice, st));
+            SFM_CUDA(ctx, cudaMemcpyAsync(d_sel, h_sel, 8 * nsel, cudaMemcpyHostToDevice, st));
             orb_harris_kernel<<<(unsigned)ceil_div64((int64_t)nsel * 32, 256), 256, 0, st>>>(d_pyr, L, d_sel, (int)nsel, d_resp);
             SFM_LAUNCH_CHECK(ctx);
-            SFM_CUDA(ctx, cudaMemcpyAsync(resp.data(), d_resp, 4 * nsel, cudaMemcpyDeviceToHost, st));
+            SFM_CUDA(ctx, cudaMemcpyAsync(h_resp, d_resp, 4 * nsel, cudaMemcpyDeviceToHost, st));
             SFM_CUDA(ctx, cudaStreamSynchronize(st));                                              // round trip 2
         }
-        // ---- second selection: best quota Harris responses per level
-        std::vector<uint2> fin; std::vector<float> fresp; std::vector<int> n_img(nb, 0);
-        fin.reserve(nsel); fresp.reserve(nsel);
-        {
-            size_t at = 0;
-            for (int s = 0; s < nb; s++)
-                for (int l = 0; l < ORB_LEVELS; l++) {
-                    const int n = seg[(size_t)s * ORB_LEVELS + l];
-                    recs.resize(n);
-                    for (int k = 0; k < n; k++) recs[k] = Rec{resp[at + k], k};
-                    retain_best(recs, L.lv[l].quota);
-                    for (const Rec& r : recs) { fin.push_back(sel[at + r.idx]); fresp.push_back(r.response); }
-                    n_img[s] += (int)recs.size();
-                    at += n;
-                }
-        }
-        const size_t nfin = fin.size();
+        double t5 = now_ms(); tm[4] += t5 - t4;
+        // ---- second selection: best quota Harris responses per (image, level)
+        pool.parallel_for(nb * ORB_LEVELS, [&](int t) {
+            const int l = t % ORB_LEVELS;
+            const int n = (int)(sel_at[t + 1] - sel_at[t]);
+            std::vector<Rec>& r = task[t];
+            r.resize(n);
+            const float* rs = h_resp + sel_at[t];
+            for (int k = 0; k < n; k++) r[k] = Rec{rs[k], k};
+            retain_best(r, L.lv[l].quota);
+        });
+        std::vector<size_t> fin_at((size_t)nb * ORB_LEVELS + 1, 0);
+        for (int t = 0; t < nb * ORB_LEVELS; t++) fin_at[t + 1] = fin_at[t] + task[t].size();
+        const size_t nfin = fin_at[(size_t)nb * ORB_LEVELS];
+        pool.parallel_for(nb * ORB_LEVELS, [&](int t) {
+            uint2* o = h_fin + fin_at[t]; float* f = h_fresp + fin_at[t];
+            const uint2* src = h_sel + sel_at[t];
+            for (const Rec& r : task[t]) { *o++ = src[r.idx]; *f++ = r.response; }
+        });
+        double t6 = now_ms(); tm[5] += t6 - t5;
         if (nfin) {
-            SFM_CUDA(ctx, ctx->orb_pin.reserve((28 + 32) * nfin + 256));
-            KeyPointOut* h_kp = (KeyPointOut*)ctx->orb_pin.p; uint8_t* h_desc = (uint8_t*)(h_kp + nfin);
-            SFM_CUDA(ctx, cudaMemcpyAsync(d_fin, fin.data(), 8 * nfin, cudaMemcpyHostToDevice, st));
-            SFM_CUDA(ctx, cudaMemcpyAsync(d_fresp, fresp.data(), 4 * nfin, cudaMemcpyHostToDevice, st));
+            SFM_CUDA(ctx, ctx->orb_pin_a.reserve((28 + 32) * nfin + 256));
+            KeyPointOut* h_kp = (KeyPointOut*)ctx->orb_pin_a.p; uint8_t* h_desc = (uint8_t*)(h_kp + nfin);
+            SFM_CUDA(ctx, cudaMemcpyAsync(d_fin, h_fin, 8 * nfin, cudaMemcpyHostToDevice, st));
+            SFM_CUDA(ctx, cudaMemcpyAsync(d_fresp, h_fresp, 4 * nfin, cudaMemcpyHostToDevice, st));
             SFM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->orb_ev[1], 0));
             orb_describe_kernel<<<(unsigned)ceil_div64((int64_t)nfin * 32, 256), 256, 0, st>>>(d_pyr, d_blur, L, d_fin, d_fresp, (int)nfin, d_kp, d_desc);
             SFM_LAUNCH_CHECK(ctx);
             SFM_CUDA(ctx, cudaMemcpyAsync(h_kp, d_kp, 28 * nfin, cudaMemcpyDeviceToHost, st));
             SFM_CUDA(ctx, cudaMemcpyAsync(h_desc, d_desc, 32 * nfin, cudaMemcpyDeviceToHost, st));
             SFM_CUDA(ctx, cudaStreamSynchronize(st));                                              // round trip 3
-            size_t at = 0;
-            for (int s = 0; s < nb; s++) {
-                const int n = std::min(n_img[s], cap);
-                if (n > 0) {
-                    memcpy(kp_out + (size_t)(i0 + s) * cap, h_kp + at, 28 * (size_t)n);
-                    memcpy(desc_out + (size_t)(i0 + s) * cap * 32, h_desc + 32 * at, 32 * (size_t)n);
+            double t7 = now_ms(); tm[6] += t7 - t6;
+            pool.parallel_for(nb, [&](int s) {
+                const size_t at = fin_at[(size_t)s * ORB_LEVELS], n_all = fin_at[(size_t)(s + 1) * ORB_LEVELS] - at;
+                const size_t n = std::min<size_t>(n_all, (size_t)cap);
+                if (n) {
+                    memcpy(kp_out + (size_t)(i0 + s) * cap, h_kp + at, 28 * n);
+                    memcpy(desc_out + (size_t)(i0 + s) * cap * 32, h_desc + 32 * at, 32 * n);
                 }
-                at += n_img[s];
-            }
+            });
+            tm[7] += now_ms() - t7;
         }
-        for (int s = 0; s < nb; s++) n_out[i0 + s] = n_img[s];
+        for (int s = 0; s < nb; s++) n_out[i0 + s] = (int32_t)(fin_at[(size_t)(s + 1) * ORB_LEVELS] - fin_at[(size_t)s * ORB_LEVELS]);
         SFM_CUDA(ctx, cudaStreamSynchronize(ctx->orb_stream));        // the next batch (and a download for inspection) reuses the blur buffer
     }
     return SFMB200_OK;
@@ -570,6 +622,25 @@ int sfmb200_orb_retain_best(const float* response, int n, int n_points, int32_t*
     retain_best(k, n_points);
     for (size_t i = 0; i < k.size(); i++) order[i] = k[i].idx;
     return (int)k.size();
+}
+
+int64_t sfmb200_host_pool_selftest(int n_threads, int rounds, int max_tasks) {
+    if (n_threads < 1 || rounds < 0 || max_tasks < 0) return -1;
+    HostPool pool(n_threads - 1);
+    int64_t total = 0;
+    for (int r = 0; r < rounds; r++) {
+        const int n = max_tasks ? (r * 7919) % (max_tasks + 1) : 0;
+        std::vector<int64_t> out((size_t)n, 0);
+        pool.parallel_for(n, [&](int i) { int64_t a = 0; for (int k = 0; k <= i % 97; k++) a += k; out[i] = a + i; });
+        for (int i = 0; i < n; i++) { int64_t a = 0; for (int k = 0; k <= i % 97; k++) a += k; if (out[i] != a + i) return -2; total += out[i]; }
+    }
+    return total;
+}
+
+int sfmb200_orb_last_timings(const sfmb200_ctx* ctx, double* ms8) {
+    if (!ctx || !ms8) return SFMB200_ERR_INVALID;
+    for (int i = 0; i < 8; i++) ms8[i] = ctx->orb_ms[i];
+    return SFMB200_OK;
 }
 
 int sfmb200_orb_download_level(sfmb200_ctx* ctx, int stage, int image, int level, uint8_t* out) {

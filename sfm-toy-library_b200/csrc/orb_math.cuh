@@ -50,35 +50,37 @@ ORB_HD int resize_linear_exact(int s00, int s01, int s10, int s11, int ax, int a
 
 // FAST-9/16 (fast.cpp + cornerScore<16>, fast_score.cpp).  v = centre, p[16] = the circle of radius 3 in OpenCV's order.
 // Returns 0 when the pixel is no corner for `threshold`, else the corner score (>= threshold, <= 254): the largest t' for which the
-// pixel is still a corner = max over the 16 arcs of 9 of min(v - p) resp. min(p - v), minus 1.
+// pixel is still a corner = max over the 16 arcs of 9 of min(v - p) resp. min(p - v), minus 1.  Branch-free: the minimum (maximum) over
+// every window of 9 comes from a doubling network (2, 4, 8, +1), all indices compile-time constants so the values stay in registers.
 ORB_HD int fast9_score(int v, const int* p, int threshold) {
-    unsigned dark = 0, bright = 0;
+    int d[16], lo[16], hi[16], t[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = v - p[k];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { lo[k] = d[k] < d[(k + 1) & 15] ? d[k] : d[(k + 1) & 15]; hi[k] = d[k] > d[(k + 1) & 15] ? d[k] : d[(k + 1) & 15]; }
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = lo[k] < lo[(k + 2) & 15] ? lo[k] : lo[(k + 2) & 15];
+#pragma unroll
+    for (int k = 0; k < 16; k++) lo[k] = t[k] < t[(k + 4) & 15] ? t[k] : t[(k + 4) & 15];          // min of d[k .. k+7]
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = hi[k] > hi[(k + 2) & 15] ? hi[k] : hi[(k + 2) & 15];
+#pragma unroll
+    for (int k = 0; k < 16; k++) hi[k] = t[k] > t[(k + 4) & 15] ? t[k] : t[(k + 4) & 15];          // max of d[k .. k+7]
+    int a = -256, b = 256;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int d = v - p[k];
-        dark |= (unsigned)(d > threshold) << k;
-        bright |= (unsigned)(d < -threshold) << k;
+        const int e = d[(k + 8) & 15];
+        const int mn = lo[k] < e ? lo[k] : e, mx = hi[k] > e ? hi[k] : e;                            // over the arc k .. k+8
+        a = mn > a ? mn : a; b = mx < b ? mx : b;
     }
-    unsigned md = dark | (dark << 16), mb = bright | (bright << 16), rd = md, rb = mb;
-#pragma unroll
-    for (int i = 1; i < 9; i++) { rd &= md >> i; rb &= mb >> i; }
-    rd &= 0xFFFFu; rb &= 0xFFFFu;
-    if (!(rd | rb)) return 0;
-    int best = -256;
-    // only arcs that are runs beyond the threshold can carry the maximum (any other arc has a minimum <= threshold)
-    for (int k = 0; k < 16; k++) {
-        if ((rd >> k) & 1u) {
-            int m = 255;
-            for (int j = 0; j < 9; j++) { const int d = v - p[(k + j) & 15]; m = d < m ? d : m; }
-            best = m > best ? m : best;
-        }
-        if ((rb >> k) & 1u) {
-            int m = 255;
-            for (int j = 0; j < 9; j++) { const int d = p[(k + j) & 15] - v; m = d < m ? d : m; }
-            best = m > best ? m : best;
-        }
-    }
-    return best - 1;
+    const int s = (a > -b ? a : -b) - 1;
+    return s >= threshold ? s : 0;
+}
+// Cheap necessary condition on the four compass points of the circle (p[0], p[4], p[8], p[12]): any arc of 9 holds at least two of them.
+ORB_HD bool fast9_may_be_corner(int v, int p0, int p4, int p8, int p12, int threshold) {
+    const int nd = (v - p0 > threshold) + (v - p4 > threshold) + (v - p8 > threshold) + (v - p12 > threshold);
+    const int nb = (p0 - v > threshold) + (p4 - v > threshold) + (p8 - v > threshold) + (p12 - v > threshold);
+    return nd >= 2 || nb >= 2;
 }
 
 // orb.cpp HarrisResponses (blockSize 7, k = 0.04f): a, b, c = integer sums of Ix*Ix, Iy*Iy, Ix*Iy over the 7x7 window;

@@ -18,7 +18,12 @@ typedef Point_<float> Point2f;
 template <typename T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T a, T b, T c) : x(a), y(b), z(c) {} };
 typedef Point3_<float> Point3f;
 
-struct KeyPoint { Point2f pt; float size; KeyPoint() : size(0) {} KeyPoint(Point2f p, float s) : pt(p), size(s) {} };
+// same members, order and size (28 bytes) as cv::KeyPoint
+struct KeyPoint {
+    Point2f pt; float size, angle, response; int octave, class_id;
+    KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
+    KeyPoint(Point2f p, float s, float a = -1, float r = 0, int o = 0, int c = -1) : pt(p), size(s), angle(a), response(r), octave(o), class_id(c) {}
+};
 
 struct DMatch {
     int queryIdx, trainIdx, imgIdx; float distance;
@@ -49,6 +54,7 @@ public:
     bool isContinuous() const { return true; }
     Mat clone() const { Mat m(rows, cols, type_); if (data) std::memcpy(m.data, data, (size_t)rows * cols * elem(type_)); return m; }
     size_t elemSize() const { return elem(type_); }
+    int channels() const { return type_ == CV_8UC3 ? 3 : 1; }
     template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data)[(size_t)r * cols + c]; }
     template <typename T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data)[(size_t)r * cols + c]; }
     template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data) + (size_t)r * cols; }

@@ -4,6 +4,7 @@
 //
 // Mirrors, name for name and argument for argument:
 //   data carriers                         reference SfMToyLib/SfMCommon.h:55-99
+//   SfM2DFeatureUtilities::extractFeatures reference SfMToyLib/SfM2DFeatureUtilities.h:38-42 (constructor, destructor, member function)
 //   SfM2DFeatureUtilities::matchFeatures  reference SfMToyLib/SfM2DFeatureUtilities.h:44-46
 //   SfMStereoUtilities::triangulateViews  reference SfMToyLib/SfMStereoUtilities.h:82-91
 //   SfMBundleAdjustmentUtils::adjustBundle reference SfMToyLib/SfMBundleAdjustmentUtils.h:44-49
@@ -31,6 +32,9 @@ typedef cv::Matx34f Pose;
 
 class SfM2DFeatureUtilities {
 public:
+    SfM2DFeatureUtilities();
+    virtual ~SfM2DFeatureUtilities();
+    Features extractFeatures(const cv::Mat& image);
     static Matching matchFeatures(const Features& featuresLeft, const Features& featuresRight);
 };
 

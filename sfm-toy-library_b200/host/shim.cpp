@@ -1,6 +1,6 @@
-// shim.cpp -- the three stage functions of the reference, re-implemented as thin marshalling over the C ABI
+// shim.cpp -- the stage functions of the reference, re-implemented as thin marshalling over the C ABI
 // (include/sfmb200.h).  Linking this object instead of the bodies in the reference's
-//   SfMToyLib/SfM2DFeatureUtilities.cpp:53-71, SfMToyLib/SfMStereoUtilities.cpp:120-206,
+//   SfMToyLib/SfM2DFeatureUtilities.cpp:37-71 (constructor, extractFeatures, matchFeatures), SfMToyLib/SfMStereoUtilities.cpp:120-206,
 //   SfMToyLib/SfMBundleAdjustmentUtils.cpp:99-222
 // leaves SfM.cpp and main.cpp untouched.  No arithmetic happens here: only flattening of the
 // std::vector / std::map / cv::Mat containers into the plain arrays of the ABI and back.
@@ -14,6 +14,7 @@
 #include "../../include/sfmb200.h"
 
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <iostream>
 #include <mutex>
@@ -43,12 +44,49 @@ void check(int rc, const char* what) {
     }
 }
 
+#if defined(SFMB200_WITH_REFERENCE_HEADERS) || defined(SFMB200_WITH_OPENCV)
+const int kType8U = CV_8U;                    // OpenCV's macro
+#else
+const int kType8U = cv::CV_8U;                // cv_min.h
+#endif
 const double kNNMatchRatio = 0.8f;            // NN_MATCH_RATIO: the float literal widened to double
 const float kMaxReprojectionError = 10.0f;    // MIN_REPROJECTION_ERROR
 
 }  // namespace
 
 namespace sfmtoylib {
+
+// SfM2DFeatureUtilities.cpp:37-44: the reference creates the ORB detector and a matcher here; both live in libsfmb200.so now, the
+// members (cv::Ptr, reference header :48-49) stay empty.
+SfM2DFeatureUtilities::SfM2DFeatureUtilities() {}
+SfM2DFeatureUtilities::~SfM2DFeatureUtilities() {}
+
+// SfM2DFeatureUtilities.cpp:46-51: mDetector->detectAndCompute(image, noArray(), keyPoints, descriptors) with ORB::create(5000),
+// then KeyPointsToPoints.  `image` is what cv::imread returned (8-bit B,G,R; SfM.cpp:124) or an 8-bit grey image.
+Features SfM2DFeatureUtilities::extractFeatures(const cv::Mat& image) {
+    static_assert(sizeof(cv::KeyPoint) == sizeof(sfmb200_keypoint), "cv::KeyPoint must be the 28-byte record of the ABI");
+    Features features;
+    if (image.empty()) return features;
+    const cv::Mat img = image.isContinuous() ? image : image.clone();
+    const int nfeatures = 5000;                                                    // ORB::create(5000), :39
+    int cap = nfeatures + 64, n = 0;
+    std::vector<sfmb200_keypoint> kp;
+    std::vector<uint8_t> desc;
+    for (;;) {
+        kp.resize(cap); desc.resize(32 * (size_t)cap);
+        check(sfmb200_orb_detect_and_compute(context(), img.ptr<uint8_t>(0), img.cols, img.rows, img.channels(), 0, nfeatures, cap, kp.data(),
+                                             desc.data(), &n), "sfmb200_orb_detect_and_compute");
+        if (n <= cap) break;
+        cap = n;                                                                   // ties at a selection threshold: OpenCV returns them all
+    }
+    features.keyPoints.resize(n);
+    if (n) std::memcpy((void*)features.keyPoints.data(), kp.data(), sizeof(sfmb200_keypoint) * (size_t)n);
+    features.descriptors = cv::Mat(n, 32, kType8U);
+    if (n) std::memcpy(features.descriptors.ptr<uint8_t>(0), desc.data(), 32 * (size_t)n);
+    features.points.clear();                                                       // KeyPointsToPoints, SfMCommon.cpp:89-94
+    for (const auto& k : features.keyPoints) features.points.push_back(k.pt);
+    return features;
+}
 
 Matching SfM2DFeatureUtilities::matchFeatures(const Features& featuresLeft, const Features& featuresRight) {
     // the ABI wants packed rows; a cv::Mat view (ROI, step > cols) is cloned first -- the reference accepts any cv::Mat

@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
+#include <string>
 #include "../../include/sfmb200.h"
 
 using namespace sfmtoylib;
@@ -161,8 +163,66 @@ static void test_adjust_bundle() {
     std::printf("adjustBundle: focal %.2f (truth %.0f), reprojection RMS %.3f px over %d observations\n", f, f_true, std::sqrt(ss / n), n);
 }
 
-int main() {
+// extractFeatures (SfM2DFeatureUtilities.cpp:46-51) on a generated image: container invariants here; bit-for-bit parity with cv2 is
+// checked by tests/test_gpu_host_shim.py through the file mode below.
+static cv::Mat generated_image(int w, int h, int channels) {
+    cv::Mat img(h, w, channels == 3 ? cv::CV_8UC3 : cv::CV_8U);
+    uint32_t s = 12345u;
+    std::vector<uint8_t> g((size_t)w * h, 120);
+    for (int b = 0; b < 500; b++) {
+        s = s * 1664525u + 1013904223u; const int x0 = (s >> 8) % w;
+        s = s * 1664525u + 1013904223u; const int y0 = (s >> 8) % h;
+        s = s * 1664525u + 1013904223u; const int sz = 4 + (s >> 8) % 36;
+        s = s * 1664525u + 1013904223u; const uint8_t c = (uint8_t)(s >> 16);
+        for (int y = y0; y < y0 + sz && y < h; y++) for (int x = x0; x < x0 + sz && x < w; x++) g[(size_t)y * w + x] = c;
+    }
+    for (size_t i = 0; i < g.size(); i++) for (int c = 0; c < channels; c++) img.data[i * channels + c] = (uint8_t)(g[i] + (c ? 0 : 0));
+    return img;
+}
+
+static void test_extract_features() {
+    SfM2DFeatureUtilities util;
+    const cv::Mat grey = generated_image(640, 480, 1), bgr = generated_image(640, 480, 3);
+    const Features a = util.extractFeatures(grey), b = util.extractFeatures(bgr);
+    EXPECT(a.keyPoints.size() > 500 && a.keyPoints.size() <= 5064, "ORB finds key points");
+    EXPECT(a.points.size() == a.keyPoints.size() && (size_t)a.descriptors.rows == a.keyPoints.size() && a.descriptors.cols == 32, "container sizes");
+    bool same = a.keyPoints.size() == b.keyPoints.size(), pts = true, inside = true;
+    for (size_t i = 0; i < a.keyPoints.size(); i++) {
+        pts = pts && a.points[i].x == a.keyPoints[i].pt.x && a.points[i].y == a.keyPoints[i].pt.y;
+        inside = inside && a.keyPoints[i].pt.x >= 31 && a.keyPoints[i].pt.x < 640 - 31 && a.keyPoints[i].octave >= 0 && a.keyPoints[i].octave < 8 &&
+                 a.keyPoints[i].angle >= 0 && a.keyPoints[i].angle < 360 && a.keyPoints[i].class_id == -1;
+        if (same) same = std::memcmp(&a.keyPoints[i], &b.keyPoints[i], sizeof(cv::KeyPoint)) == 0;
+    }
+    if (same) same = std::memcmp(a.descriptors.data, b.descriptors.data, 32 * a.keyPoints.size()) == 0;
+    EXPECT(pts, "points = KeyPointsToPoints(keyPoints)");
+    EXPECT(inside, "key point fields in range");
+    EXPECT(same, "B = G = R image gives the grey image's features");
+    std::printf("extractFeatures: %zu key points\n", a.keyPoints.size());
+}
+
+// file mode: test_shim --orb image.raw width height channels out.bin   (out: int32 n, n x 28-byte key points, n x 32 descriptor bytes)
+static int orb_file_mode(char** argv) {
+    const int w = std::atoi(argv[3]), h = std::atoi(argv[4]), ch = std::atoi(argv[5]);
+    cv::Mat img(h, w, ch == 3 ? cv::CV_8UC3 : cv::CV_8U);
+    FILE* f = std::fopen(argv[2], "rb");
+    if (!f || std::fread(img.data, 1, (size_t)w * h * ch, f) != (size_t)w * h * ch) { std::fprintf(stderr, "cannot read %s\n", argv[2]); return 2; }
+    std::fclose(f);
+    SfM2DFeatureUtilities util;
+    const Features ft = util.extractFeatures(img);
+    FILE* o = std::fopen(argv[6], "wb");
+    if (!o) return 2;
+    const int32_t n = (int32_t)ft.keyPoints.size();
+    std::fwrite(&n, 4, 1, o);
+    std::fwrite(ft.keyPoints.data(), sizeof(cv::KeyPoint), n, o);
+    std::fwrite(ft.descriptors.data, 32, n, o);
+    std::fclose(o);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc == 7 && std::string(argv[1]) == "--orb") return orb_file_mode(argv);
     test_triangulate_from_2_views();
+    test_extract_features();
     test_match_features();
     test_adjust_bundle();
     std::printf(failures ? "SHIM_TEST FAIL (%d)\n" : "SHIM_TEST PASS\n", failures);

@@ -115,6 +115,18 @@ class SfM:
         self.seconds = {"match": 0.0, "homography": 0.0, "essential": 0.0, "triangulate": 0.0, "bundle": 0.0, "pnp": 0.0, "glue": 0.0}
         self.calls = {k: 0 for k in self.seconds}
 
+    @classmethod
+    def from_images(cls, images, extractAllFeatures: Callable = None, **kw):
+        """setImagesDirectory + extractFeatures of the reference driver (SfM.cpp:97-139, 141-154) for already decoded images
+        (uint8 B,G,R or grey, equal sizes): ORB(5000) per image through the injected stage (default: stages.extractAllFeatures, GPU)."""
+        t0 = time.perf_counter()
+        feats = (extractAllFeatures or stages.extractAllFeatures)(list(images))
+        dt = time.perf_counter() - t0
+        h, w = images[0].shape[:2]
+        sfm = cls(feats, (w, h), **kw)
+        sfm.seconds["extract"] = dt; sfm.calls["extract"] = len(images)
+        return sfm
+
     # ---- timing helper
     def _timed(self, key, fn, *a, **kw):
         t0 = time.perf_counter()

@@ -1,7 +1,8 @@
 """Host-side mirror (Python) of the reference's stage interface, over the C ABI.
 
-Same names, argument order and semantics as the three static functions the reference's SfM class calls
-(SfM.cpp:197, 293, 435, 325):
+Same names, argument order and semantics as the stage functions the reference's SfM class calls
+(SfM.cpp:148, 197, 293, 435, 325):
+    SfM2DFeatureUtilities::extractFeatures      SfMToyLib/SfM2DFeatureUtilities.h:41-42   
     SfM2DFeatureUtilities::matchFeatures        SfMToyLib/SfM2DFeatureUtilities.h:44-46
     SfMStereoUtilities::triangulateViews        SfMToyLib/SfMStereoUtilities.h:82-91
     SfMBundleAdjustmentUtils::adjustBundle      SfMToyLib/SfMBundleAdjustmentUtils.h:44-49
@@ -61,6 +62,29 @@ def GetAlignedMatching(size):          # SfMCommon.cpp:120-126
     m = np.zeros(size, DMATCH)
     m["queryIdx"] = np.arange(size); m["trainIdx"] = np.arange(size)
     return m
+
+
+ORB_FEATURES = 5000                    # mDetector = ORB::create(5000), SfM2DFeatureUtilities.cpp:39
+
+
+def _features_from(kp, desc) -> Features:
+    # keyPoints: the cv::KeyPoint fields as rows (x, y, size, angle, response, octave, class_id); points = KeyPointsToPoints (SfMCommon.cpp:89-94)
+    return Features(keyPoints=kp, points=np.ascontiguousarray(kp[:, :2]), descriptors=desc)
+
+
+def extractFeatures(image: np.ndarray, ctx=None) -> Features:
+    """SfM2DFeatureUtilities::extractFeatures (SfM2DFeatureUtilities.cpp:46-51): ORB(5000) detectAndCompute + KeyPointsToPoints.
+    `image`: uint8 [h, w, 3] in B,G,R order (what cv::imread returns, SfM.cpp:124) or [h, w] grey."""
+    ctx = ctx or default_context()
+    return _features_from(*ctx.orb_detect_and_compute(image, ORB_FEATURES))
+
+
+def extractAllFeatures(images: List[np.ndarray], ctx=None) -> List[Features]:
+    """The batched form of SfM::extractFeatures (SfM.cpp:141-154): all (equally sized) images of a run in one launch sequence."""
+    ctx = ctx or default_context()
+    if len({im.shape for im in images}) > 1:
+        return [extractFeatures(im, ctx) for im in images]
+    return [_features_from(k, d) for k, d in ctx.orb_detect_and_compute(list(images), ORB_FEATURES)]
 
 
 def matchFeatures(featuresLeft: Features, featuresRight: Features, ctx=None) -> np.ndarray:

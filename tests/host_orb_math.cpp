@@ -30,7 +30,7 @@ void orbh_fast_score_map(const uint8_t* I, int w, int h, int threshold, uint8_t*
             const uint8_t* c = I + y * w + x;
             int p[16] = {c[3 * w], c[3 * w + 1], c[2 * w + 2], c[w + 3], c[3], c[-w + 3], c[-2 * w + 2], c[-3 * w + 1],
                          c[-3 * w], c[-3 * w - 1], c[-2 * w - 2], c[-w - 3], c[-3], c[w - 3], c[2 * w - 2], c[3 * w - 1]};
-            out[y * w + x] = (uint8_t)orbm::fast9_score(c[0], p, threshold);
+            out[y * w + x] = orbm::fast9_may_be_corner(c[0], p[0], p[4], p[8], p[12], threshold) ? (uint8_t)orbm::fast9_score(c[0], p, threshold) : 0;
         }
 }
 

@@ -99,3 +99,17 @@ def test_exported_host_pieces_match_the_oracle():
         assert np.array_equal(capi.orb_retain_best(r, k), O.retain_best(r, k))
         r = rng.rand(n).astype(np.float32)
         assert np.array_equal(capi.orb_retain_best(r, k), O.retain_best(r, k))
+
+
+def test_host_thread_pool():
+    """csrc/host_pool.h: the pool the ORB stage stages images and runs its retainBest tasks on (many short loops, late-waking workers)."""
+    import ctypes as C
+    from sfm_toy_library_b200 import capi
+    f = capi.lib().sfmb200_host_pool_selftest; f.restype = C.c_int64
+    want = None
+    for threads in (1, 2, 8, 16):
+        got = f(threads, 3000, 64)
+        assert got >= 0
+        want = got if want is None else want
+        assert got == want
+    assert f(4, 200, 5000) > 0 and f(4, 10, 0) == 0 and f(0, 1, 1) == -1

@@ -16,26 +16,29 @@ from orb_util import textured  # noqa: E402
 from sfm_toy_library_b200 import capi  # noqa: E402
 
 
-def run(n_images=7, reps=5, cpu=True, nfeatures=5000, w=1024, h=768, channels=3):
+def run(n_images=7, reps=5, cpu=True, nfeatures=5000, w=1024, h=768, channels=3, ctx=None):
     imgs = [textured(h, w, 100 + i) for i in range(n_images)]
     if channels == 3:
         imgs = [np.ascontiguousarray(np.stack([im, np.roll(im, 1, 0), np.roll(im, 1, 1)], 2)) for im in imgs]
-    ctx = capi.Context(0)
+    own = ctx is None
+    ctx = ctx or capi.Context(0)
     ctx.orb_detect_and_compute(imgs, nfeatures)                       # warm-up: allocations
     l0 = ctx.kernel_launches
     ts = []
     for _ in range(reps):
         t = time.perf_counter(); out = ctx.orb_detect_and_compute(imgs, nfeatures); ts.append(time.perf_counter() - t)
     launches = (ctx.kernel_launches - l0) // reps
+    phases = ctx.orb_last_timings()
     t1 = []
     for _ in range(reps):
         t = time.perf_counter(); ctx.orb_detect_and_compute(imgs[0], nfeatures); t1.append(time.perf_counter() - t)
-    ctx.close()
+    if own:
+        ctx.close()
     best = min(ts)
     line = {"stage": "orb_extract", "metric": "images per second (ORB(%d) detectAndCompute, %dx%d, %d channel(s))" % (nfeatures, w, h, channels),
             "value": n_images / best, "unit": "images/s", "images": n_images, "keypoints": int(sum(len(k) for k, _ in out)),
             "ms_per_batch": best * 1e3, "ms_per_image_batched": best * 1e3 / n_images, "ms_single_image_call": min(t1) * 1e3,
-            "gpu_launches": int(launches), "dtype": "u8 (f32 for Harris / angle / blur)",
+            "gpu_launches": int(launches), "host_phases_ms": {k: round(v, 3) for k, v in phases.items()}, "dtype": "u8 (f32 for Harris / angle / blur)",
             "e2e": {"value": n_images / best, "unit": "images/s", "h2d_bytes_per_step": int(sum(im.nbytes for im in imgs)),
                     "d2h_bytes_per_step": int(sum(len(k) for k, _ in out)) * 60,
                     "note": "host buffers in, key points + descriptors out; includes both host-side retainBest selections"}}
