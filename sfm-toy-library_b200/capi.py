@@ -236,6 +236,22 @@ class Context:
             out.append((k, desc[i, :cnt[i]].copy()))
         return out[0] if single else out
 
+    def orb_prepare(self, images, nfeatures=5000, capacity=None):
+        """Pre-marshalled form of orb_detect_and_compute for timing the C call itself: returns (call, kp, desc, cnt); call() runs
+        sfmb200_orb_detect_and_compute_batch into the preallocated kp [n, cap, 7] (raw records) / desc [n, cap, 32] / cnt [n]."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        h, w = imgs[0].shape[:2]; ch = 1 if imgs[0].ndim == 2 else imgs[0].shape[2]
+        n = len(imgs); cap = int(capacity) if capacity is not None else int(nfeatures) + 64
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        kp = np.zeros((n, cap, 7), np.float32); desc = np.zeros((n, cap, 32), np.uint8); cnt = np.zeros(n, np.int32)
+        args = (self._h, ptrs, n, int(w), int(h), int(ch), C.c_size_t(0), int(nfeatures), cap, _p(kp, C.c_float), _p(desc, C.c_uint8), _p(cnt, C.c_int32))
+        fn = lib().sfmb200_orb_detect_and_compute_batch
+
+        def call(_keep=imgs):
+            self._check(fn(*args))
+            return cnt
+        return call, kp, desc, cnt
+
     def orb_last_timings(self):
         """Host wall-clock (ms) of the phases of the last ORB call (sfmb200_orb_last_timings)."""
         ms = np.zeros(8)

@@ -115,39 +115,54 @@ __global__ void __launch_bounds__(256) orb_resize_kernel(uint8_t* pyr, int slab,
     pyr[(size_t)img * slab + dst_off + (size_t)y * dw + x] = (uint8_t)v;
 }
 
-// FAST-9/16 score of one pixel of a level (0 = no corner, also within 3 pixels of the level's border)
-__device__ __forceinline__ int fast_at(const uint8_t* __restrict__ I, int w, int h, int x, int y) {
-    if (x < 3 || x >= w - 3 || y < 3 || y >= h - 3) return 0;
+// FAST-9/16: the four compass points decide whether a position can be a corner at all (9-18 % of the pixels of a photograph pass, but
+// half of all 32-pixel rows hold at least one such pixel), so a tile first collects the positions that pass in a shared list and then
+// spends the 12 remaining loads and the 9-arc network on a DENSE list instead of on half-empty warps.
+__device__ __forceinline__ bool fast_candidate(const uint8_t* __restrict__ I, int w, int h, int x, int y) {
+    if (x < 3 || x >= w - 3 || y < 3 || y >= h - 3) return false;
     const uint8_t* c = I + (size_t)y * w + x;
-    const int v = c[0];
+    return orbm::fast9_may_be_corner(c[0], c[3 * w], c[3], c[-3 * w], c[-3], ORB_FAST_T);
+}
+__device__ __forceinline__ int fast_full(const uint8_t* __restrict__ I, int w, int x, int y) {
+    const uint8_t* c = I + (size_t)y * w + x;
     int p[16];
-    p[0] = c[3 * w]; p[4] = c[3]; p[8] = c[-3 * w]; p[12] = c[-3];
-    if (!orbm::fast9_may_be_corner(v, p[0], p[4], p[8], p[12], ORB_FAST_T)) return 0;
-    p[1] = c[3 * w + 1];   p[2] = c[2 * w + 2];   p[3] = c[w + 3];
-    p[5] = c[-w + 3];      p[6] = c[-2 * w + 2];  p[7] = c[-3 * w + 1];
-    p[9] = c[-3 * w - 1];  p[10] = c[-2 * w - 2]; p[11] = c[-w - 3];
-    p[13] = c[w - 3];      p[14] = c[2 * w - 2];  p[15] = c[3 * w - 1];
-    return orbm::fast9_score(v, p, ORB_FAST_T);
+    p[0] = c[3 * w];       p[1] = c[3 * w + 1];   p[2] = c[2 * w + 2];   p[3] = c[w + 3];
+    p[4] = c[3];           p[5] = c[-w + 3];      p[6] = c[-2 * w + 2];  p[7] = c[-3 * w + 1];
+    p[8] = c[-3 * w];      p[9] = c[-3 * w - 1];  p[10] = c[-2 * w - 2]; p[11] = c[-w - 3];
+    p[12] = c[-3];         p[13] = c[w - 3];      p[14] = c[2 * w - 2];  p[15] = c[3 * w - 1];
+    return orbm::fast9_score(c[0], p, ORB_FAST_T);
 }
 
 // FAST scores of a 32 x 8 tile (+1 halo) in shared memory -> score map; 3x3 non-maximum suppression (fast.cpp: strictly greater than the 8
-// neighbours) + KeyPointsFilter::runByImageBorder(edgeThreshold) -> one 32-bit survivor mask per (row, 32-pixel word).
+// neighbours) + KeyPointsFilter::runByImageBorder(edgeThreshold) -> one 32-bit survivor mask per (row, 32-pixel word) and the number of
+// survivors per pyramid row (integer atomics: order-independent).
 // grid = (words per row of level 0, tile rows of all levels, images), block = (32, 8).
-constexpr int FT_W = 32, FT_H = 8;
+constexpr int FT_W = 32, FT_H = 8, FT_N = (FT_W + 2) * (FT_H + 2);
 __global__ void __launch_bounds__(FT_W * FT_H) orb_fast_nms_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, uint32_t* __restrict__ mask,
-                                                                    OrbLayout L, const int32_t* __restrict__ tile_lvl, const int32_t* __restrict__ tile_y0) {
+                                                                    int32_t* __restrict__ row_cnt, OrbLayout L, const int32_t* __restrict__ tile_lvl,
+                                                                    const int32_t* __restrict__ tile_y0) {
     __shared__ uint8_t sc[FT_H + 2][FT_W + 2 + 2];
+    __shared__ uint16_t list[FT_N];
+    __shared__ int nlist;
     const int l = tile_lvl[blockIdx.y], y0 = tile_y0[blockIdx.y], x0 = blockIdx.x * FT_W, img = blockIdx.z;
     const int w = L.lv[l].w, h = L.lv[l].h;
-    if (x0 >= w) {                                   // words beyond this level's width: the row scan adds all `chunks` words of a row
+    if (x0 >= w) {                                   // words beyond this level's width: the scatter walks all `chunks` words of a row
         if (threadIdx.x == 0 && y0 + (int)threadIdx.y < h) mask[(size_t)img * L.ncnt + (size_t)(L.lv[l].row0 + y0 + threadIdx.y) * L.chunks + blockIdx.x] = 0u;
         return;
     }
     const uint8_t* I = pyr + (size_t)img * L.slab + L.lv[l].off;
     const int tid = threadIdx.y * FT_W + threadIdx.x;
-    for (int t = tid; t < (FT_W + 2) * (FT_H + 2); t += FT_W * FT_H) {
+    if (tid == 0) nlist = 0;
+    __syncthreads();
+    for (int t = tid; t < FT_N; t += FT_W * FT_H) {
         const int tx = t % (FT_W + 2), ty = t / (FT_W + 2);
-        sc[ty][tx] = (uint8_t)fast_at(I, w, h, x0 - 1 + tx, y0 - 1 + ty);
+        sc[ty][tx] = 0;
+        if (fast_candidate(I, w, h, x0 - 1 + tx, y0 - 1 + ty)) list[atomicAdd(&nlist, 1)] = (uint16_t)t;
+    }
+    __syncthreads();
+    for (int i = tid; i < nlist; i += FT_W * FT_H) {
+        const int t = list[i], tx = t % (FT_W + 2), ty = t / (FT_W + 2);
+        sc[ty][tx] = (uint8_t)fast_full(I, w, x0 - 1 + tx, y0 - 1 + ty);
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -161,21 +176,24 @@ __global__ void __launch_bounds__(FT_W * FT_H) orb_fast_nms_kernel(const uint8_t
         }
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (threadIdx.x == 0 && y < h) mask[(size_t)img * L.ncnt + (size_t)(L.lv[l].row0 + y) * L.chunks + blockIdx.x] = m;
+    if (threadIdx.x == 0 && y < h) {
+        const int row = L.lv[l].row0 + y;
+        mask[(size_t)img * L.ncnt + (size_t)row * L.chunks + blockIdx.x] = m;
+        if (m) atomicAdd(&row_cnt[(size_t)img * (L.total_rows + 1) + row], __popc(m));
+    }
 }
 
-// Survivors per pyramid row -> exclusive scan over the rows of one image (one CTA per image); start of every level and the total.
-__global__ void __launch_bounds__(1024) orb_scan_kernel(const uint32_t* __restrict__ mask, int32_t* __restrict__ row_off, int32_t* __restrict__ lvl_start, OrbLayout L) {
+// Exclusive scan of the survivors per pyramid row of one image (one CTA per image); start of every level and the total.
+__global__ void __launch_bounds__(1024) orb_scan_kernel(const int32_t* __restrict__ row_cnt, int32_t* __restrict__ row_off, int32_t* __restrict__ lvl_start, OrbLayout L) {
     __shared__ int warp_sum[32];
     __shared__ int carry;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t* mk = mask + (size_t)img * L.ncnt; int32_t* o = row_off + (size_t)img * (L.total_rows + 1);
+    const int32_t* c = row_cnt + (size_t)img * (L.total_rows + 1); int32_t* o = row_off + (size_t)img * (L.total_rows + 1);
     if (tid == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < L.total_rows; base += 1024) {
         const int r = base + tid;
-        int v = 0;
-        if (r < L.total_rows) for (int j = 0; j < L.chunks; j++) v += __popc(mk[(size_t)r * L.chunks + j]);
+        const int v = r < L.total_rows ? c[r] : 0;
         int s = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += t; }
@@ -397,7 +415,7 @@ int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w,
     const size_t img_bytes = (size_t)w * h * channels;
     const size_t raw_img = channels == 3 ? img_bytes : 0;
     const int cand_cap = L.slab / 4 + 64;                    // 3x3 non-maximum suppression keeps at most one pixel of every 2x2 block
-    const size_t per_img = Carver::pad(raw_img) + 3 * Carver::pad(L.slab) + Carver::pad(4 * (size_t)L.ncnt) + Carver::pad(4 * (size_t)(L.total_rows + 1)) +
+    const size_t per_img = Carver::pad(raw_img) + 3 * Carver::pad(L.slab) + Carver::pad(4 * (size_t)L.ncnt) + 2 * Carver::pad(4 * (size_t)(L.total_rows + 1)) +
                            Carver::pad(64) + Carver::pad(8 * (size_t)cand_cap);
     // a batch = as many images as 2 GB of device scratch and 96 MB of pinned staging hold
     const int slots = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n_images, ((size_t)2 << 30) / per_img, ((size_t)96 << 20) / img_bytes}));
@@ -411,6 +429,7 @@ int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w,
     uint8_t* d_pyr = cv.take<uint8_t>((size_t)L.slab * slots); uint8_t* d_blur = cv.take<uint8_t>((size_t)L.slab * slots);
     uint8_t* d_score = cv.take<uint8_t>((size_t)L.slab * slots);
     uint32_t* d_mask = cv.take<uint32_t>((size_t)L.ncnt * slots); int32_t* d_rowoff = cv.take<int32_t>((size_t)(L.total_rows + 1) * slots);
+    int32_t* d_rowcnt = cv.take<int32_t>((size_t)(L.total_rows + 1) * slots);
     int32_t* d_lvl = cv.take<int32_t>(16 * (size_t)slots);
     uint2* d_cand = cv.take<uint2>((size_t)cand_cap * slots);
     ctx->orb_last = OrbLast{d_pyr, d_blur, d_score, L.slab, 0, w, h, nfeatures};
@@ -456,9 +475,10 @@ int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w,
         orb_blur_kernel<<<dim3(ceil_div(w, BT_W), (unsigned)P.blur_lvl.size(), nb), 256, 0, ctx->orb_stream>>>(d_pyr, d_blur, L, d_blur_lvl, d_blur_y0);
         SFM_LAUNCH_CHECK(ctx);
         SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[1], ctx->orb_stream));
-        orb_fast_nms_kernel<<<dim3(L.chunks, (unsigned)P.fast_lvl.size(), nb), dim3(FT_W, FT_H), 0, st>>>(d_pyr, d_score, d_mask, L, d_fast_lvl, d_fast_y0);
+        SFM_CUDA(ctx, cudaMemsetAsync(d_rowcnt, 0, 4 * (size_t)(L.total_rows + 1) * nb, st));
+        orb_fast_nms_kernel<<<dim3(L.chunks, (unsigned)P.fast_lvl.size(), nb), dim3(FT_W, FT_H), 0, st>>>(d_pyr, d_score, d_mask, d_rowcnt, L, d_fast_lvl, d_fast_y0);
         SFM_LAUNCH_CHECK(ctx);
-        orb_scan_kernel<<<nb, 1024, 0, st>>>(d_mask, d_rowoff, d_lvl, L); SFM_LAUNCH_CHECK(ctx);
+        orb_scan_kernel<<<nb, 1024, 0, st>>>(d_rowcnt, d_rowoff, d_lvl, L); SFM_LAUNCH_CHECK(ctx);
         orb_scatter_kernel<<<dim3(ceil_div(L.total_rows * 32, 256), 1, nb), 256, 0, st>>>(d_mask, d_score, d_rowoff, L, d_cand, cand_cap);
         SFM_LAUNCH_CHECK(ctx);
         SFM_CUDA(ctx, ctx->orb_pin_a.reserve(64 * (size_t)nb + 64));

