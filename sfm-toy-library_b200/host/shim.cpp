@@ -56,6 +56,7 @@ const float kMaxReprojectionError = 10.0f;    // MIN_REPROJECTION_ERROR
 
 namespace sfmtoylib {
 
+#ifndef SFMB200_SHIM_KEEP_ORB     // define it to keep the reference's own constructor + extractFeatures (OpenCV's ORB) and replace only the matcher
 // SfM2DFeatureUtilities.cpp:37-44: the reference creates the ORB detector and a matcher here; both live in libsfmb200.so now, the
 // members (cv::Ptr, reference header :48-49) stay empty.
 SfM2DFeatureUtilities::SfM2DFeatureUtilities() {}
@@ -87,6 +88,7 @@ Features SfM2DFeatureUtilities::extractFeatures(const cv::Mat& image) {
     for (const auto& k : features.keyPoints) features.points.push_back(k.pt);
     return features;
 }
+#endif  // SFMB200_SHIM_KEEP_ORB
 
 Matching SfM2DFeatureUtilities::matchFeatures(const Features& featuresLeft, const Features& featuresRight) {
     // the ABI wants packed rows; a cv::Mat view (ROI, step > cols) is cloned first -- the reference accepts any cv::Mat
