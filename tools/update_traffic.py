@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BA_SOURCES = ("ba.cu", "ba_math.cuh", "ba_row.cuh", "chol.cuh", "common.cuh")   # what the captured kernels are built from
+BA_SOURCES = ("ba.cu", "ba_math.cuh", "ba_row.cuh", "chol.cuh")   # the files the captured kernels are written in (common.cuh: context plumbing only)
 
 
 def source_id():
