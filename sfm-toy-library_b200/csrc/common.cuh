@@ -82,6 +82,15 @@ struct MatchCache {
 // Device buffers of the last ORB extraction (orb.cu), kept for sfmb200_orb_download_level (stage-by-stage parity tests).
 struct OrbLast { uint8_t *pyr = nullptr, *blur = nullptr, *score = nullptr; int slab = 0, nimg = 0, w = 0, h = 0, nfeatures = 0; };
 
+// Device memory of one descriptor set (match.cu), kept by the context between sets: SfM::createFeatureMatchMatrix builds one set per run and
+// a benchmark one per repetition -- cudaMalloc / cudaFree (a device-wide synchronisation each) cost more than matching 21 image pairs.
+// One set at a time borrows it; further live sets allocate their own memory.
+struct DescWorkspace {
+    DevBuf desc, exp, norms;
+    bool in_use = false;
+    void release() { desc.release(); exp.release(); norms.release(); }
+};
+
 struct sfmb200_ctx {
     int device = 0;
     int sm_count = 0;
@@ -94,6 +103,7 @@ struct sfmb200_ctx {
     PinBuf pinned;              // per-call pinned staging (results read-back)
     BAWorkspace ba_ws;          // cached bundle-adjustment workspace
     MatchCache mcache;          // descriptor images resident between per-call matchFeatures invocations
+    DescWorkspace ds_ws;        // cached device memory of a descriptor set
     DevBuf orb_dev, orb_lists;  // ORB extraction: pyramids / score maps / candidates of a batch of images; key point lists
     PinBuf orb_pin_img, orb_pin_a, orb_pin_b, orb_pin_c;   // ORB extraction: pinned image staging / staging of the three host round trips
     double orb_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // host wall-clock of the phases of the last extraction (sfmb200_orb_last_timings)

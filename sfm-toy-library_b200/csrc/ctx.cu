@@ -51,7 +51,7 @@ void sfmb200_destroy(sfmb200_ctx* ctx) {
     delete ctx->pool; ctx->pool = nullptr;
     if (ctx->orb_stream) cudaStreamDestroy(ctx->orb_stream);
     for (auto& ev : ctx->orb_ev) if (ev) cudaEventDestroy(ev);
-    ctx->scratch.release(); ctx->scratch2.release(); ctx->pinned.release(); ctx->ba_ws.release(); ctx->mcache.release();
+    ctx->scratch.release(); ctx->scratch2.release(); ctx->pinned.release(); ctx->ba_ws.release(); ctx->mcache.release(); ctx->ds_ws.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

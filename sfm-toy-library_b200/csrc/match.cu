@@ -221,7 +221,35 @@ struct sfmb200_descset {
     std::vector<int32_t> img_blk;      // first block of each image
     int kind = 0;                      // 0 = Hamming, 1 = L2 (exact u8 GEMM)
     int32_t* d_norms = nullptr;        // L2: squared norms, [blocks][256]
+    bool borrowed = false;             // device memory belongs to ctx->ds_ws (returned, not freed, by destroy)
 };
+
+// device memory of a set: the context's cached workspace when it is free (no cudaMalloc / cudaFree in the steady state), else own allocations
+static cudaError_t descset_alloc(sfmb200_descset* s, size_t desc_bytes, size_t exp_bytes, size_t norm_bytes) {
+    sfmb200_ctx* ctx = s->ctx;
+    if (!ctx->ds_ws.in_use) {
+        cudaError_t e = cudaSuccess;
+        if (desc_bytes) e = ctx->ds_ws.desc.reserve(desc_bytes);
+        if (e == cudaSuccess && exp_bytes) e = ctx->ds_ws.exp.reserve(exp_bytes);
+        if (e == cudaSuccess && norm_bytes) e = ctx->ds_ws.norms.reserve(norm_bytes);
+        if (e != cudaSuccess) return e;
+        ctx->ds_ws.in_use = true; s->borrowed = true;
+        s->d_desc = desc_bytes ? (uint32_t*)ctx->ds_ws.desc.p : nullptr;
+        s->d_exp = exp_bytes ? (uint8_t*)ctx->ds_ws.exp.p : nullptr;
+        s->d_norms = norm_bytes ? (int32_t*)ctx->ds_ws.norms.p : nullptr;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaSuccess;
+    if (desc_bytes) e = cudaMalloc(&s->d_desc, desc_bytes);
+    if (e == cudaSuccess && exp_bytes) e = cudaMalloc(&s->d_exp, exp_bytes);
+    if (e == cudaSuccess && norm_bytes) e = cudaMalloc(&s->d_norms, norm_bytes);
+    return e;
+}
+static void descset_free(sfmb200_descset* s) {            // caller holds ctx->mu (or is the only user of the set)
+    if (s->borrowed) { s->ctx->ds_ws.in_use = false; s->borrowed = false; }
+    else { if (s->d_desc) cudaFree(s->d_desc); if (s->d_exp) cudaFree(s->d_exp); if (s->d_norms) cudaFree(s->d_norms); }
+    s->d_desc = nullptr; s->d_exp = nullptr; s->d_norms = nullptr;
+}
 
 // core: pairs already on the host as PairDesc; descriptors on the device.  Leaves the dense compacted results in
 // d_out_* (device) and per-pair dense start positions in d_pair_start [n_pairs+1].
@@ -316,16 +344,10 @@ int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc, const int32_t*
         s->max_rows = std::max(s->max_rows, img_off[i + 1] - img_off[i]);
     }
     const size_t bytes = (size_t)img_off[n_img] * desc_bytes;
-    cudaError_t e = cudaMalloc(&s->d_desc, bytes + 16);
-    if (e != cudaSuccess) { delete s; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
-    if (bytes) {
-        e = cudaMemcpyAsync(s->d_desc, desc, bytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { cudaFree(s->d_desc); delete s; return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e)); }
-    }
-    if (s->words == 8 && img_off[n_img] > 0) {      // expanded operand store for the tensor-core kernel
+    const bool tc = desc_bytes == 32 && img_off[n_img] > 0;      // expanded operand store for the tensor-core kernel
+    std::vector<int2> blocks;
+    if (tc) {
         const int br = match_tc_block_rows();
-        std::vector<int2> blocks;
         s->img_blk.resize(n_img + 1);
         for (int i = 0; i < n_img; ++i) {
             s->img_blk[i] = (int)blocks.size();
@@ -333,17 +355,24 @@ int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc, const int32_t*
             for (int b0 = 0; b0 < rows; b0 += br) blocks.push_back(make_int2(img_off[i] + b0, std::min(br, rows - b0)));
         }
         s->img_blk[n_img] = (int)blocks.size();
-        int2* d_blocks = nullptr;
-        e = cudaMalloc(&s->d_exp, blocks.size() * match_tc_block_bytes(false));
-        if (e == cudaSuccess) e = cudaMalloc(&d_blocks, blocks.size() * sizeof(int2));
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
-        int rc = e == cudaSuccess ? match_tc_expand(ctx, s->d_desc, d_blocks, (int)blocks.size(), s->d_exp) : SFMB200_ERR_NOMEM;
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (d_blocks) cudaFree(d_blocks);
-        if (e != cudaSuccess || rc) {
-            cudaFree(s->d_desc); if (s->d_exp) cudaFree(s->d_exp); delete s;
-            return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "expanded operand store: %s", cudaGetErrorString(e));
+    }
+    cudaError_t e = descset_alloc(s, bytes + 16, tc ? blocks.size() * match_tc_block_bytes(false) : 0, 0);
+    if (e != cudaSuccess) { descset_free(s); delete s; return sfmb200_fail(ctx, SFMB200_ERR_NOMEM, "descriptor set memory (%zu bytes): %s", bytes, cudaGetErrorString(e)); }
+    if (bytes) e = cudaMemcpyAsync(s->d_desc, desc, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = SFMB200_OK;
+    if (e == cudaSuccess && tc) {
+        int2* d_blocks = nullptr;                 // the block list lives in the context's reusable scratch
+        e = ctx->scratch2.reserve(Carver::pad(blocks.size() * sizeof(int2) + 16) + 256);
+        if (e == cudaSuccess) {
+            d_blocks = (int2*)ctx->scratch2.p;
+            e = cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
         }
+        if (e == cudaSuccess) rc = match_tc_expand(ctx, s->d_desc, d_blocks, (int)blocks.size(), s->d_exp);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      // the caller's descriptors (and the block list) may go away
+    if (e != cudaSuccess || rc) {
+        descset_free(s); delete s;
+        return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "descriptor upload / operand expansion: %s", cudaGetErrorString(e));
     }
     *out = s;
     return SFMB200_OK;
@@ -351,10 +380,12 @@ int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc, const int32_t*
 
 void sfmb200_descset_destroy(sfmb200_descset* s) {
     if (!s) return;
-    cudaSetDevice(s->ctx->device);
-    cudaFree(s->d_desc);
-    if (s->d_exp) cudaFree(s->d_exp);
-    if (s->d_norms) cudaFree(s->d_norms);
+    {
+        std::lock_guard<std::mutex> lk(s->ctx->mu);
+        cudaSetDevice(s->ctx->device);
+        if (s->borrowed) cudaStreamSynchronize(s->ctx->stream);        // nothing of this set may still be in flight when the next set reuses the memory
+        descset_free(s);
+    }
     delete s;
 }
 
@@ -389,8 +420,7 @@ int sfmb200_descset_create_l2(sfmb200_ctx* ctx, const float* desc, const int32_t
         d_f = cv.take<float>((size_t)img_off[n_img] * dim + 4); d_blocks = cv.take<int2>(nb + 2);
         d_bad = reinterpret_cast<int*>(d_blocks + nb);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_exp, nb * match_tc_block_bytes(true));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_norms, nb * br * sizeof(int32_t));
+    if (e == cudaSuccess) e = descset_alloc(s, 0, nb * match_tc_block_bytes(true), nb * br * sizeof(int32_t));
     int h_bad = 0, rc = SFMB200_OK;
     if (e == cudaSuccess && fbytes) e = cudaMemcpyAsync(d_f, desc, fbytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
@@ -401,8 +431,7 @@ int sfmb200_descset_create_l2(sfmb200_ctx* ctx, const float* desc, const int32_t
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess || rc || h_bad) {
-        if (s->d_exp) cudaFree(s->d_exp);
-        if (s->d_norms) cudaFree(s->d_norms);
+        descset_free(s);
         delete s;
         if (h_bad) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "L2 descriptor set: values must be integers in [0, 255] (SIFT-like) for the exact tensor-core path");
         return sfmb200_fail(ctx, e == cudaErrorMemoryAllocation ? SFMB200_ERR_NOMEM : SFMB200_ERR_CUDA, "L2 descriptor set: %s", cudaGetErrorString(e));
