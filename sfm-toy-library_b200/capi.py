@@ -394,6 +394,25 @@ class DescriptorSet:
                                                   _p(oq, C.c_int32), _p(ot, C.c_int32), _p(od, C.c_float), _p(off, C.c_int64), _p(cnt, C.c_int32)))
         return [(oq[off[p]:off[p] + cnt[p]], ot[off[p]:off[p] + cnt[p]], od[off[p]:off[p] + cnt[p]]) for p in range(npairs)]   # views
 
+    def match_pairs_prepare(self, pairs, ratio=RATIO_REFERENCE, buffers=None):
+        """Pre-marshalled sfmb200_match_pairs for timing the C call itself: caller-owned result buffers (touched once), no per-call numpy work.
+        Returns (call, buffers); call() -> (off, cnt); buffers = (oq, ot, od, off, cnt) can be handed to another set of the same sizes."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        npairs = pairs.shape[0]
+        if buffers is None:
+            total = int(sum(self.sizes[l] for l, _ in pairs))
+            buffers = (np.zeros(max(total, 1), np.int32), np.zeros(max(total, 1), np.int32), np.zeros(max(total, 1), np.float32),
+                       np.zeros(npairs + 1, np.int64), np.zeros(max(npairs, 1), np.int32))
+        oq, ot, od, off, cnt = buffers
+        args = (self.ctx._h, self._h, _p(pairs, C.c_int32), npairs, C.c_double(ratio), _p(oq, C.c_int32), _p(ot, C.c_int32), _p(od, C.c_float),
+                _p(off, C.c_int64), _p(cnt, C.c_int32))
+        fn = lib().sfmb200_match_pairs
+
+        def call(_keep=(pairs,)):
+            self.ctx._check(fn(*args))
+            return off, cnt
+        return call, buffers
+
     def match_pairs_device(self, pairs, d_q, d_t, d_d, d_pair_start, d_total, ratio=RATIO_REFERENCE):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         self.ctx._check(lib().sfmb200_match_pairs_device(self.ctx._h, self._h, _p(pairs, C.c_int32), pairs.shape[0], C.c_double(ratio),
