@@ -133,53 +133,60 @@ __device__ __forceinline__ int fast_full(const uint8_t* __restrict__ I, int w, i
     return orbm::fast9_score(c[0], p, ORB_FAST_T);
 }
 
-// FAST scores of a 32 x 8 tile (+1 halo) in shared memory -> score map; 3x3 non-maximum suppression (fast.cpp: strictly greater than the 8
+// FAST scores of a 32 x 32 tile (+1 halo) in shared memory -> score map; 3x3 non-maximum suppression (fast.cpp: strictly greater than the 8
 // neighbours) + KeyPointsFilter::runByImageBorder(edgeThreshold) -> one 32-bit survivor mask per (row, 32-pixel word) and the number of
-// survivors per pyramid row (integer atomics: order-independent).
-// grid = (words per row of level 0, tile rows of all levels, images), block = (32, 8).
-constexpr int FT_W = 32, FT_H = 8, FT_N = (FT_W + 2) * (FT_H + 2);
-__global__ void __launch_bounds__(FT_W * FT_H) orb_fast_nms_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, uint32_t* __restrict__ mask,
-                                                                    int32_t* __restrict__ row_cnt, OrbLayout L, const int32_t* __restrict__ tile_lvl,
-                                                                    const int32_t* __restrict__ tile_y0) {
+// survivors per pyramid row (integer atomics: order-independent).  The tile is 32 rows high so that the dense candidate list (~150 of
+// 1156 positions) fills the CTA's 8 warps in the scoring phase -- with 8-row tiles two warps scored while six waited at the barrier
+// (ncu: barrier = top stall) -- and the halo costs 13 % instead of 33 %.
+// grid = (words per row of level 0, tile rows of all levels, images), block = (32, 8): thread (x, y) owns rows y, y+8, y+16, y+24.
+constexpr int FT_W = 32, FT_H = 32, FT_TY = 8, FT_N = (FT_W + 2) * (FT_H + 2);
+__global__ void __launch_bounds__(FT_W * FT_TY) orb_fast_nms_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, uint32_t* __restrict__ mask,
+                                                                     int32_t* __restrict__ row_cnt, OrbLayout L, const int32_t* __restrict__ tile_lvl,
+                                                                     const int32_t* __restrict__ tile_y0) {
     __shared__ uint8_t sc[FT_H + 2][FT_W + 2 + 2];
     __shared__ uint16_t list[FT_N];
     __shared__ int nlist;
     const int l = tile_lvl[blockIdx.y], y0 = tile_y0[blockIdx.y], x0 = blockIdx.x * FT_W, img = blockIdx.z;
     const int w = L.lv[l].w, h = L.lv[l].h;
     if (x0 >= w) {                                   // words beyond this level's width: the scatter walks all `chunks` words of a row
-        if (threadIdx.x == 0 && y0 + (int)threadIdx.y < h) mask[(size_t)img * L.ncnt + (size_t)(L.lv[l].row0 + y0 + threadIdx.y) * L.chunks + blockIdx.x] = 0u;
+        if (threadIdx.x == 0)
+            for (int ry = threadIdx.y; ry < FT_H && y0 + ry < h; ry += FT_TY) mask[(size_t)img * L.ncnt + (size_t)(L.lv[l].row0 + y0 + ry) * L.chunks + blockIdx.x] = 0u;
         return;
     }
     const uint8_t* I = pyr + (size_t)img * L.slab + L.lv[l].off;
     const int tid = threadIdx.y * FT_W + threadIdx.x;
     if (tid == 0) nlist = 0;
     __syncthreads();
-    for (int t = tid; t < FT_N; t += FT_W * FT_H) {
+    for (int t = tid; t < FT_N; t += FT_W * FT_TY) {
         const int tx = t % (FT_W + 2), ty = t / (FT_W + 2);
         sc[ty][tx] = 0;
         if (fast_candidate(I, w, h, x0 - 1 + tx, y0 - 1 + ty)) list[atomicAdd(&nlist, 1)] = (uint16_t)t;
     }
     __syncthreads();
-    for (int i = tid; i < nlist; i += FT_W * FT_H) {
+    for (int i = tid; i < nlist; i += FT_W * FT_TY) {
         const int t = list[i], tx = t % (FT_W + 2), ty = t / (FT_W + 2);
         sc[ty][tx] = (uint8_t)fast_full(I, w, x0 - 1 + tx, y0 - 1 + ty);
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const int s = sc[threadIdx.y + 1][threadIdx.x + 1];
-    bool keep = false;
-    if (x < w && y < h) {
-        score[(size_t)img * L.slab + L.lv[l].off + (size_t)y * w + x] = (uint8_t)s;
-        if (s && x >= ORB_EDGE && x < w - ORB_EDGE && y >= ORB_EDGE && y < h - ORB_EDGE) {
-            const uint8_t* r0 = &sc[threadIdx.y][threadIdx.x]; const uint8_t* r1 = r0 + (FT_W + 4); const uint8_t* r2 = r1 + (FT_W + 4);
-            keep = s > r0[0] && s > r0[1] && s > r0[2] && s > r1[0] && s > r1[2] && s > r2[0] && s > r2[1] && s > r2[2];
+    const int x = x0 + threadIdx.x;
+#pragma unroll
+    for (int ry = threadIdx.y; ry < FT_H; ry += FT_TY) {
+        const int y = y0 + ry;
+        const int s = sc[ry + 1][threadIdx.x + 1];
+        bool keep = false;
+        if (x < w && y < h) {
+            score[(size_t)img * L.slab + L.lv[l].off + (size_t)y * w + x] = (uint8_t)s;
+            if (s && x >= ORB_EDGE && x < w - ORB_EDGE && y >= ORB_EDGE && y < h - ORB_EDGE) {
+                const uint8_t* r0 = &sc[ry][threadIdx.x]; const uint8_t* r1 = r0 + (FT_W + 4); const uint8_t* r2 = r1 + (FT_W + 4);
+                keep = s > r0[0] && s > r0[1] && s > r0[2] && s > r1[0] && s > r1[2] && s > r2[0] && s > r2[1] && s > r2[2];
+            }
         }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (threadIdx.x == 0 && y < h) {
-        const int row = L.lv[l].row0 + y;
-        mask[(size_t)img * L.ncnt + (size_t)row * L.chunks + blockIdx.x] = m;
-        if (m) atomicAdd(&row_cnt[(size_t)img * (L.total_rows + 1) + row], __popc(m));
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (threadIdx.x == 0 && y < h) {
+            const int row = L.lv[l].row0 + y;
+            mask[(size_t)img * L.ncnt + (size_t)row * L.chunks + blockIdx.x] = m;
+            if (m) atomicAdd(&row_cnt[(size_t)img * (L.total_rows + 1) + row], __popc(m));
+        }
     }
 }
 
@@ -401,7 +408,7 @@ int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w,
     OrbPlan P;
     make_plan(w, h, nfeatures, P);
     const OrbLayout& L = P.L;
-    if (L.total_rows > 65535 * FT_H) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "image too tall for one launch (%d pyramid rows)", L.total_rows);
+    if (L.total_rows > 65535 * BT_H) return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "image too tall for one launch (%d pyramid rows)", L.total_rows);
     cudaStream_t st = ctx->stream;
     if (!ctx->orb_stream) {
         SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->orb_stream, cudaStreamNonBlocking));
@@ -476,7 +483,7 @@ int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w,
         SFM_LAUNCH_CHECK(ctx);
         SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[1], ctx->orb_stream));
         SFM_CUDA(ctx, cudaMemsetAsync(d_rowcnt, 0, 4 * (size_t)(L.total_rows + 1) * nb, st));
-        orb_fast_nms_kernel<<<dim3(L.chunks, (unsigned)P.fast_lvl.size(), nb), dim3(FT_W, FT_H), 0, st>>>(d_pyr, d_score, d_mask, d_rowcnt, L, d_fast_lvl, d_fast_y0);
+        orb_fast_nms_kernel<<<dim3(L.chunks, (unsigned)P.fast_lvl.size(), nb), dim3(FT_W, FT_TY), 0, st>>>(d_pyr, d_score, d_mask, d_rowcnt, L, d_fast_lvl, d_fast_y0);
         SFM_LAUNCH_CHECK(ctx);
         orb_scan_kernel<<<nb, 1024, 0, st>>>(d_rowcnt, d_rowoff, d_lvl, L); SFM_LAUNCH_CHECK(ctx);
         orb_scatter_kernel<<<dim3(ceil_div(L.total_rows * 32, 256), 1, nb), 256, 0, st>>>(d_mask, d_score, d_rowoff, L, d_cand, cand_cap);

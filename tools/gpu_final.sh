@@ -14,3 +14,7 @@ python tools/summarize_launches.py gpurun_out/launches.csv 2>/dev/null | head -3
 echo "== ncu full (kernels of LM iteration 2)"
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:ba_pair_kernel|ba_point_kernel|ba_camera_kernel|ba_combine_kernel|ba_backsub_z|chol_stream|chol_backsolve' -s 8 -c 7 -o gpurun_out/prof_step -f python tools/prof_ba.py --iters 4 > gpurun_out/ncu_full_step.log 2>&1 ; echo "rc=$?"; tail -3 gpurun_out/ncu_full_step.log
 ls -la gpurun_out/prof_step.ncu-rep
+echo "== ORB stage"; timeout 300 python tools/bench_orb.py --images 7 > gpurun_out/bench_orb7.json 2> gpurun_out/bench_orb7.err; echo "rc=$?"; cut -c1-900 gpurun_out/bench_orb7.json
+timeout 300 python tools/bench_orb.py --images 50 --no-cpu > gpurun_out/bench_orb50.json 2> gpurun_out/bench_orb50.err; echo "rc=$?"; cut -c1-500 gpurun_out/bench_orb50.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/orb_launches.csv python tools/bench_orb.py --images 7 --reps 2 --no-cpu > gpurun_out/ncu_orb.log 2>&1; echo "rc=$?"
+python tools/summarize_launches.py gpurun_out/orb_launches.csv 2>/dev/null | head -12
