@@ -34,6 +34,23 @@ def shard_pairs(pairs, rank, world):
     return [pr for i, pr in enumerate(pairs) if i % world == rank]
 
 
+def extract_features_sharded(images, rank, world, extract, dist_module=None):
+    """SfM::extractFeatures (SfM.cpp:141-154) over several GPUs: images are independent, so rank r extracts the contiguous chunk
+    shard_bounds(len(images), r, world) with `extract(list_of_images) -> list of per-image results` (stages.extractAllFeatures on its own
+    GPU) and the per-image results are gathered on the host in image order on every rank -- no collective on the data path
+    ("chunk split only")."""
+    b, e = shard_bounds(len(images), rank, world)
+    mine = extract(list(images[b:e])) if e > b else []
+    if world == 1:
+        return mine
+    dist = dist_module
+    if dist is None:
+        import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    return [f for part in parts for f in part]
+
+
 def init_comm(ctx, dist_module=None):
     """Create the library's NCCL communicator for the current torch.distributed world (no-op for world size 1)."""
     from . import capi

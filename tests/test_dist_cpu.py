@@ -26,6 +26,12 @@ def test_shard_pairs_round_robin():
     assert got == sorted(pairs)
 
 
+def test_sharded_feature_extraction_single_rank_is_the_plain_call():
+    imgs = [np.full((4, 4), i, np.uint8) for i in range(5)]
+    out = sdist.extract_features_sharded(imgs, 0, 1, lambda chunk: [int(im[0, 0]) * 10 for im in chunk])
+    assert out == [0, 10, 20, 30, 40]
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     return port
@@ -57,6 +63,21 @@ def _worker(rank, world, port, out_dir):
     obj = [b"x" * 128 if rank == 0 else None]
     dist.broadcast_object_list(obj, src=0)
     assert obj[0] == b"x" * 128
+    # ORB extraction shards images (row f-3): every rank extracts its chunk, the host gathers the per-image results in image order;
+    # the extractor here is the ORB oracle (CPU), the GPU stage is bit-identical to it
+    from oracle import orb_oracle
+    rs = np.random.RandomState(7)
+    imgs = [rs.randint(0, 256, (96, 128), dtype=np.uint8) for _ in range(3)]
+    calls = []
+
+    def extract(chunk):
+        calls.append(len(chunk))
+        return [orb_oracle.detect_and_compute(im, 200) for im in chunk]
+    feats = sdist.extract_features_sharded(imgs, rank, world, extract)
+    assert calls == [2 if rank == 0 else 1] and len(feats) == 3
+    for im, (k, d) in zip(imgs, feats):
+        ko, do = orb_oracle.detect_and_compute(im, 200)
+        assert np.array_equal(k, ko) and np.array_equal(d, do)
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
