@@ -55,4 +55,7 @@ CASES = [
     ("nf20000_1024x768", lambda: blobs(768, 1024, 9, 3000), 20000),
     ("textured_1024x768", lambda: textured(768, 1024, 10), 5000),
     ("textured_bgr_700x500", lambda: np.stack([textured(500, 700, 11 + c) for c in range(3)], 2), 2000),
+    ("large_2000x1500_nf8000", lambda: textured(1500, 2000, 14), 8000),
+    ("wide_1900x120", lambda: textured(120, 1900, 15), 3000),
+    ("tall_90x1300", lambda: blobs(1300, 90, 16, 900), 3000),
 ]
