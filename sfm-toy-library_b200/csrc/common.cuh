@@ -110,6 +110,8 @@ struct sfmb200_ctx {
     HostPool* pool = nullptr;   // host threads for the work that stays on the CPU (created on first use)
     OrbLast orb_last;
     cudaStream_t orb_stream = nullptr;            // the Gaussian blur of the pyramid runs beside the detection chain
+    cudaStream_t orb_up = nullptr;                // image uploads run beside the detection of the images that have already landed
+    std::vector<cudaEvent_t> orb_img_ev;          // "image s of the batch is on the device"
     cudaEvent_t orb_ev[2] = {nullptr, nullptr};   // pyramid ready / blur done
     bool tc_attr_set = false;   // cudaFuncSetAttribute(knn2_hamming_tc_kernel, max dynamic smem) done for THIS device
     // peer exchange buffers opened with cudaIpcOpenMemHandle, kept open across problems (the exchange buffer is part of the cached

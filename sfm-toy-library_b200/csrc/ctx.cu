@@ -50,6 +50,8 @@ void sfmb200_destroy(sfmb200_ctx* ctx) {
     ctx->orb_pin_img.release(); ctx->orb_pin_a.release(); ctx->orb_pin_b.release(); ctx->orb_pin_c.release();
     delete ctx->pool; ctx->pool = nullptr;
     if (ctx->orb_stream) cudaStreamDestroy(ctx->orb_stream);
+    if (ctx->orb_up) cudaStreamDestroy(ctx->orb_up);
+    for (auto& ev : ctx->orb_img_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->orb_ev) if (ev) cudaEventDestroy(ev);
     ctx->scratch.release(); ctx->scratch2.release(); ctx->pinned.release(); ctx->ba_ws.release(); ctx->mcache.release(); ctx->ds_ws.release();
     cudaStreamDestroy(ctx->stream);

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <memory>
 
 #include "common.cuh"
 #include "orb_math.cuh"
@@ -412,6 +413,7 @@ int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w,
     cudaStream_t st = ctx->stream;
     if (!ctx->orb_stream) {
         SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->orb_stream, cudaStreamNonBlocking));
+        SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->orb_up, cudaStreamNonBlocking));
         for (auto& ev : ctx->orb_ev) SFM_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
     if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads() - 1);
@@ -453,38 +455,61 @@ int orb_run(sfmb200_ctx* ctx, const uint8_t* const* images, int n_images, int w,
     for (int i0 = 0; i0 < n_images; i0 += slots) {
         const int nb = std::min(slots, n_images - i0);
         double t0 = now_ms();
-        // ---- staging: every pool thread packs one image into pinned memory and sends it off itself, so the DMA of the first images
-        //      overlaps the packing of the later ones (a pageable cudaMemcpy would do both serially on one thread)
+        // ---- staging + upload, pipelined against detection.  The pool packs quarter images into pinned memory IN IMAGE ORDER and every
+        //      thread sends its piece off itself on the upload stream (a pageable cudaMemcpy would pack and copy serially on one thread);
+        //      whoever enqueues the last piece of an image records that image's event.  Detection runs per GROUP of images on the
+        //      main stream as soon as the group's images have landed, i.e. under the DMA of the following groups: the call is PCIe-bound.
         const int dev = ctx->device;
-        pool.parallel_for(nb, [&](int s) {
+        constexpr int PIECES = 4;
+        while ((int)ctx->orb_img_ev.size() < nb) {
+            cudaEvent_t ev = nullptr;
+            SFM_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->orb_img_ev.push_back(ev);
+        }
+        std::unique_ptr<std::atomic<int>[]> pieces_done(new std::atomic<int>[nb]);
+        for (int s = 0; s < nb; s++) pieces_done[s].store(0);
+        cudaStream_t up = ctx->orb_up;
+        SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[0], st));                 // the previous batch's kernels have read the buffers the uploads overwrite
+        SFM_CUDA(ctx, cudaStreamWaitEvent(up, ctx->orb_ev[0], 0));
+        pool.parallel_for(nb * PIECES, [&](int t) {
             cudaSetDevice(dev);
-            uint8_t* dst = h_img + (size_t)s * img_bytes; const uint8_t* src = images[i0 + s];
-            const size_t rb = (size_t)w * channels;
-            if (row_stride == rb) memcpy(dst, src, img_bytes);
-            else for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * rb, src + (size_t)y * row_stride, rb);
-            uint8_t* d = channels == 1 ? d_pyr + (size_t)s * L.slab : d_raw + (size_t)s * raw_img;
-            if (cudaMemcpyAsync(d, dst, img_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) task_err.store(1);
+            const int s = t / PIECES, c = t % PIECES;
+            const int y0 = (int)((int64_t)h * c / PIECES), y1 = (int)((int64_t)h * (c + 1) / PIECES);
+            const size_t rb = (size_t)w * channels, off = (size_t)y0 * rb, bytes = (size_t)(y1 - y0) * rb;
+            uint8_t* dst = h_img + (size_t)s * img_bytes + off; const uint8_t* src = images[i0 + s] + (size_t)y0 * row_stride;
+            if (row_stride == rb) memcpy(dst, src, bytes);
+            else for (int y = 0; y < y1 - y0; y++) memcpy(dst + (size_t)y * rb, src + (size_t)y * row_stride, rb);
+            uint8_t* d = (channels == 1 ? d_pyr + (size_t)s * L.slab : d_raw + (size_t)s * raw_img) + off;
+            if (bytes && cudaMemcpyAsync(d, dst, bytes, cudaMemcpyHostToDevice, up) != cudaSuccess) task_err.store(1);
+            if (pieces_done[s].fetch_add(1) + 1 == PIECES && cudaEventRecord(ctx->orb_img_ev[s], up) != cudaSuccess) task_err.store(1);
         });
         if (task_err.load()) return sfmb200_fail(ctx, SFMB200_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-        // ---- grey, pyramid, blur (second stream), FAST + suppression, ordered compaction: no host involvement
-        if (channels == 3) {
-            orb_gray_kernel<<<dim3(ceil_div(w, 256), h, nb), 256, 0, st>>>(d_raw, raw_img, 3 * w, w, h, d_pyr, L.slab);
-            SFM_LAUNCH_CHECK(ctx);
-        }
-        for (int l = 1; l < ORB_LEVELS; l++) {
-            const OrbLevel& d = L.lv[l]; const OrbLevel& s = L.lv[l - 1];
-            if (d.w == 0) break;
-            orb_resize_kernel<<<dim3(ceil_div(d.w, 256), d.h, nb), 256, 0, st>>>(d_pyr, L.slab, s.off, s.w, d.off, d.w, d.h, d_taps + P.taps_off[l]);
-            SFM_LAUNCH_CHECK(ctx);
-        }
-        SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[0], st));
-        SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->orb_stream, ctx->orb_ev[0], 0));
-        orb_blur_kernel<<<dim3(ceil_div(w, BT_W), (unsigned)P.blur_lvl.size(), nb), 256, 0, ctx->orb_stream>>>(d_pyr, d_blur, L, d_blur_lvl, d_blur_y0);
-        SFM_LAUNCH_CHECK(ctx);
-        SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[1], ctx->orb_stream));
+        // ---- grey, pyramid, blur (side stream), FAST + suppression per group; ordered compaction for the whole batch: no host involvement
         SFM_CUDA(ctx, cudaMemsetAsync(d_rowcnt, 0, 4 * (size_t)(L.total_rows + 1) * nb, st));
-        orb_fast_nms_kernel<<<dim3(L.chunks, (unsigned)P.fast_lvl.size(), nb), dim3(FT_W, FT_TY), 0, st>>>(d_pyr, d_score, d_mask, d_rowcnt, L, d_fast_lvl, d_fast_y0);
-        SFM_LAUNCH_CHECK(ctx);
+        const int groups = std::min(4, nb), gsz = ceil_div(nb, groups);
+        for (int s0 = 0; s0 < nb; s0 += gsz) {
+            const int n = std::min(gsz, nb - s0);
+            for (int s = s0; s < s0 + n; s++) SFM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->orb_img_ev[s], 0));
+            uint8_t* g_pyr = d_pyr + (size_t)s0 * L.slab;
+            if (channels == 3) {
+                orb_gray_kernel<<<dim3(ceil_div(w, 256), h, n), 256, 0, st>>>(d_raw + (size_t)s0 * raw_img, raw_img, 3 * w, w, h, g_pyr, L.slab);
+                SFM_LAUNCH_CHECK(ctx);
+            }
+            for (int l = 1; l < ORB_LEVELS; l++) {
+                const OrbLevel& d = L.lv[l]; const OrbLevel& sl = L.lv[l - 1];
+                if (d.w == 0) break;
+                orb_resize_kernel<<<dim3(ceil_div(d.w, 256), d.h, n), 256, 0, st>>>(g_pyr, L.slab, sl.off, sl.w, d.off, d.w, d.h, d_taps + P.taps_off[l]);
+                SFM_LAUNCH_CHECK(ctx);
+            }
+            SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[0], st));
+            SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->orb_stream, ctx->orb_ev[0], 0));
+            orb_blur_kernel<<<dim3(ceil_div(w, BT_W), (unsigned)P.blur_lvl.size(), n), 256, 0, ctx->orb_stream>>>(g_pyr, d_blur + (size_t)s0 * L.slab, L, d_blur_lvl, d_blur_y0);
+            SFM_LAUNCH_CHECK(ctx);
+            orb_fast_nms_kernel<<<dim3(L.chunks, (unsigned)P.fast_lvl.size(), n), dim3(FT_W, FT_TY), 0, st>>>(
+                g_pyr, d_score + (size_t)s0 * L.slab, d_mask + (size_t)s0 * L.ncnt, d_rowcnt + (size_t)s0 * (L.total_rows + 1), L, d_fast_lvl, d_fast_y0);
+            SFM_LAUNCH_CHECK(ctx);
+        }
+        SFM_CUDA(ctx, cudaEventRecord(ctx->orb_ev[1], ctx->orb_stream));
         orb_scan_kernel<<<nb, 1024, 0, st>>>(d_rowcnt, d_rowoff, d_lvl, L); SFM_LAUNCH_CHECK(ctx);
         orb_scatter_kernel<<<dim3(ceil_div(L.total_rows * 32, 256), 1, nb), 256, 0, st>>>(d_mask, d_score, d_rowoff, L, d_cand, cand_cap);
         SFM_LAUNCH_CHECK(ctx);
