@@ -113,3 +113,23 @@ def test_host_thread_pool():
         want = got if want is None else want
         assert got == want
     assert f(4, 200, 5000) > 0 and f(4, 10, 0) == 0 and f(0, 1, 1) == -1
+
+
+def test_retain_best_properties():
+    """KeyPointsFilter::retainBest through the C ABI: survivors are exactly the responses >= the n-th largest (ties kept), every index
+    appears once, and the order is the oracle's (libstdc++ nth_element + partition) for tie-heavy and tie-free inputs alike."""
+    from sfm_toy_library_b200 import capi
+    rng = np.random.RandomState(11)
+    for trial in range(60):
+        n = int(rng.randint(1, 4000)); k = int(rng.randint(0, n + 50))
+        r = (rng.randint(0, 1 + rng.randint(1, 50), n) if trial % 2 else rng.rand(n)).astype(np.float32)
+        o = capi.orb_retain_best(r, k)
+        assert np.array_equal(o, O.retain_best(r, k))
+        assert len(set(o.tolist())) == len(o)
+        if k >= n:
+            assert np.array_equal(o, np.arange(n))
+        elif k == 0:
+            assert len(o) == 0
+        else:
+            thr = np.sort(r)[::-1][k - 1]
+            assert set(o.tolist()) == set(np.nonzero(r >= thr)[0].tolist())
