@@ -64,3 +64,17 @@ def test_retain_best_keeps_ties_and_order():
     o = O.retain_best(r, 3)                      # threshold response 7: all four 7s stay
     assert sorted(r[o].tolist(), reverse=True) == [9, 7, 7, 7, 7]
     assert len(O.retain_best(r, 0)) == 0 and np.array_equal(O.retain_best(r, 20), np.arange(8))
+
+
+def test_all_seven_crazyhorse_images_reproduce_the_cfg1_goldens(golden):
+    """Where the reference tree is present (this container, not the GPU box): the oracle on the 7 original JPEGs (decoded B,G,R like
+    cv::imread, SfM.cpp:124) gives exactly the key points and descriptors the committed cfg-1 goldens hold (cv2 ORB at generation time)."""
+    import glob
+    cv2 = pytest.importorskip("cv2")
+    files = sorted(glob.glob("/root/reference/dataset/crazyhorse/*.JPG"))
+    if len(files) != 7:
+        pytest.skip("reference dataset not present")
+    c1 = golden("cfg1_crazyhorse.npz")
+    for i, f in enumerate(files):
+        kp, desc = O.detect_and_compute(cv2.imread(f), 5000)
+        assert np.array_equal(kp[:, :2], c1[f"pts_{i}"]) and np.array_equal(desc, c1[f"desc_{i}"]), f
