@@ -238,7 +238,7 @@ int sfmb200_ransac_score(sfmb200_ctx* ctx, int model, const float* a, const floa
  * HARRIS_SCORE, patchSize 31, fastThreshold 20).  Output is bit-identical to OpenCV's (cv2 4.13 in this image): the same key points
  * in the same order with the same pt / size / angle / response / octave, and the same 32-byte descriptors.
  *   image        8-bit pixels, channels = 1 (grey) or 3 (B,G,R interleaved; converted like cvtColor(COLOR_BGR2GRAY)); row_stride in
- *                bytes (0 = packed rows).  8 <= width, height <= 65535.  JPEG/PNG decoding stays with the caller (cv::imread).
+ *                bytes (0 = packed rows).  8 <= width, height <= 65535, width * height <= 2^28.  JPEG/PNG decoding stays with the caller (cv::imread).
  *   keypoints    [max_keypoints] records with the memory layout of cv::KeyPoint (28 bytes), so a shim can copy them straight into a
  *                std::vector<cv::KeyPoint>; class_id = -1.  KeyPointsToPoints (SfMCommon.cpp:89-94) is the x,y prefix of every record.
  *   descriptors  [max_keypoints * 32]

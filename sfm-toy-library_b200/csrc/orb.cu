@@ -637,6 +637,8 @@ int sfmb200_orb_detect_and_compute_batch(sfmb200_ctx* ctx, const uint8_t* const*
     if (channels != 1 && channels != 3) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "channels must be 1 (grey) or 3 (BGR), got %d", channels);
     if (width < 8 || height < 8 || width > 65535 || height > 65535)
         return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "image size %dx%d outside [8, 65535]", width, height);
+    if ((int64_t)width * height > ((int64_t)1 << 28))          // pyramid offsets are 32-bit: 3.3 x the image must stay below 2^31 bytes
+        return sfmb200_fail(ctx, SFMB200_ERR_UNSUPPORTED, "image of %dx%d pixels is too large (limit 2^28 pixels)", width, height);
     if (row_stride == 0) row_stride = (size_t)width * channels;
     if (row_stride < (size_t)width * channels) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "row_stride smaller than a row");
     if (nfeatures < 0) return sfmb200_fail(ctx, SFMB200_ERR_INVALID, "nfeatures < 0");
