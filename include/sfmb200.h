@@ -79,6 +79,8 @@ int sfmb200_descset_create(sfmb200_ctx* ctx, const uint8_t* desc /* concatenated
 /* same for L2 matching: float descriptors [rows*dim], dim <= 128, values must be integers in [0, 255] (SFMB200_ERR_UNSUPPORTED
  * otherwise).  sfmb200_match_pairs / _device then return float distances sqrtf(|a-b|^2) like cv::BFMatcher(NORM_L2). */
 int sfmb200_descset_create_l2(sfmb200_ctx* ctx, const float* desc, const int32_t* img_off, int n_img, int dim, sfmb200_descset** set);
+/* Destroy a set BEFORE its context.  One set at a time borrows its device memory from the context (no cudaMalloc / cudaFree per set,
+ * the usual case: one set per run); further sets that are alive at the same time allocate their own. */
 void sfmb200_descset_destroy(sfmb200_descset* set);
 /* pairs [2*n_pairs] = (left,right) image ids.  Results of pair p are written to out_*[out_off[p] .. out_off[p]+out_cnt[p])
  * where out_off[p] = sum of the LEFT image sizes of pairs < p (computed here, returned in out_off [n_pairs+1]);
